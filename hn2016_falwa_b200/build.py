@@ -1,0 +1,69 @@
+"""Builds ``libfalwa_b200.so`` (hand-written sm_100a CUDA + the C ABI of include/falwa_b200.h) in-tree.
+
+nvcc cross-compiles without a GPU.  ``-fmad=false`` keeps the device arithmetic free of FMA contraction
+so that stencil outputs are bit-comparable with the CPU oracle (the kernels are HBM-bound, the extra
+DMUL/DADD issue slots are free); files listed in FMAD_ON are the FP64-ALU-heavy solvers whose results are
+compared with a tolerance anyway.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libfalwa_b200.so")
+SOURCES = ["qgpv.cu", "refstate.cu", "flux.cu", "version.cu"]
+FMAD_ON = set()
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return "nvcc"
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "falwa_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    env = dict(os.environ)
+    env.pop("CXX", None)  # the image exports CXX=/opt/gcc/bin/g++; let nvcc pick the system host compiler
+    env.pop("CC", None)
+    objs = []
+    logs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + ([] if src in FMAD_ON else ["-fmad=false"]) + \
+              ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True)
+        logs.append(r.stderr)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError(f"nvcc failed on {src}")
+        objs.append(obj)
+    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    with open(os.path.join(objdir, "ptxas.log"), "w") as f:
+        f.write("\n".join(logs))
+    if verbose:
+        print("\n".join(logs))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

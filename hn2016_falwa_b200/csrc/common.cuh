@@ -1,0 +1,105 @@
+// Shared helpers for the falwa_b200 kernels (sm_100a, fp64).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cmath>
+#include <vector>
+#include "../../include/falwa_b200.h"
+
+#define FALWA_CUDA_TRY(expr)                         \
+    do {                                             \
+        cudaError_t _e = (expr);                     \
+        if (_e != cudaSuccess) return (int)_e;       \
+    } while (0)
+
+#define FALWA_LAUNCH_CHECK() FALWA_CUDA_TRY(cudaGetLastError())
+
+namespace falwa {
+
+constexpr int kWarp = 32;
+
+// Streaming (read-once) global load: do not pollute L1.
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum; result valid in every thread.  `red` = shared scratch of >= 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect `red` from a previous use
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = (lane < nw) ? red[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+// Order-preserving map double <-> uint64 so that atomicMax/Min on integers gives the exact fp max/min.
+__device__ __forceinline__ unsigned long long f64_to_ordered(double d) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ordered_to_f64(unsigned long long u) {
+    u = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)u);
+}
+
+// Small stream-ordered device buffer filled from a host vector (tables of a few KB).
+struct DeviceTable {
+    double* d = nullptr;
+    cudaStream_t s = nullptr;
+    int upload(const std::vector<double>& h, cudaStream_t stream) {
+        s = stream;
+        FALWA_CUDA_TRY(cudaMallocAsync((void**)&d, h.size() * sizeof(double), stream));
+        // pageable source: the copy is staged before the call returns, so `h` may die afterwards
+        FALWA_CUDA_TRY(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+        return 0;
+    }
+    ~DeviceTable() {
+        if (d) cudaFreeAsync(d, s);
+    }
+};
+
+// Raw stream-ordered scratch.
+template <typename T>
+struct DeviceScratch {
+    T* d = nullptr;
+    cudaStream_t s = nullptr;
+    int alloc(size_t n, cudaStream_t stream, bool zero_fill = false) {
+        s = stream;
+        FALWA_CUDA_TRY(cudaMallocAsync((void**)&d, n * sizeof(T), stream));
+        if (zero_fill) FALWA_CUDA_TRY(cudaMemsetAsync(d, 0, n * sizeof(T), stream));
+        return 0;
+    }
+    ~DeviceScratch() {
+        if (d) cudaFreeAsync(d, s);
+    }
+};
+
+inline double host_pi() { return std::acos(-1.0); }
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace falwa

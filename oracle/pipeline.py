@@ -16,7 +16,27 @@ import numpy as np
 from scipy.interpolate import interp1d, UnivariateSpline
 from scipy.linalg.lapack import dgetrf, dgetri
 
-from . import f2py_shim as nat
+from . import f2py_shim as _oracle_native
+
+nat = _oracle_native
+
+
+class use_native:
+    """Context manager: run the same host restatement on top of another set of the nine native callables
+    (e.g. ``hn2016_falwa_b200.f90_modules`` — the drop-in test of the GPU kernels)."""
+
+    def __init__(self, namespace):
+        self.ns = namespace
+
+    def __enter__(self):
+        global nat
+        self.prev, nat = nat, self.ns
+        return self
+
+    def __exit__(self, *exc):
+        global nat
+        nat = self.prev
+        return False
 
 P_GROUND, SCALE_HEIGHT, CP, DRY_GAS_CONSTANT = 1000., 7000., 1004., 287.  # constant.py:5-8
 EARTH_RADIUS, EARTH_OMEGA = 6.378e+6, 7.29e-5  # constant.py:9-10
