@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfalwa_b200.so")
-SOURCES = ["qgpv.cu", "refstate.cu", "flux.cu", "version.cu"]
+SOURCES = ["falwa_b200.cu"]  # includes the stage files (one translation unit)
 FMAD_ON = set()
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

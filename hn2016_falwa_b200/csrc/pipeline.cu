@@ -1,0 +1,772 @@
+// Section B of the C ABI: the fused, batched, device-resident QGField pipeline
+// (interpolate_fields -> compute_reference_states -> compute_lwa_and_barotropic_fluxes) behind
+// hn2016_falwa_b200.QGFieldNH18 / QGFieldNHN22 / QGDataset.
+//
+// Reference call stacks restated: SURVEY.md §3.1-3.2 (oopinterface.py:467-535, :1604-1674,
+// :1774-1888, :716-982, data_storage.py:32-62,170-179, utilities.py:189-233).
+//
+// Frames: every 3-D field is kept once, in the global frame [k][lat south->north][lon].  The
+// reference processes the southern hemisphere by flipping latitude and negating pv, v and qref
+// (SURVEY Q12); here that is index arithmetic: hemispheric row jj (1 = equator .. nd = pole) lives
+// in global row  g(jj) = nd-2+jj (north)  or  nd-jj (south)  (0-based), with sign factors.
+#include "common.cuh"
+
+namespace falwa {
+
+enum Out2D {
+    O_ASTAR1 = 0, O_ASTAR2, O_LWA, O_UA1, O_UA2, O_EP1, O_EP2, O_EP3, O_EP4, O_NCF, O_UBARO,
+    O_CONV, O_DIVEMF, O_FLAMBDA, O_FPHI, O_COUNT
+};
+
+}  // namespace falwa
+
+struct falwa_plan {
+    int kind, nlon, nlat, nlev, kmax, jb, nd, jd, npart, maxit;
+    double a, omega, dz, h, rr, cp, tol, rjac, prefactor, dphi, dlambda;
+    std::vector<double> height;
+    double* d_tab = nullptr;
+    int* d_lo = nullptr;
+    // offsets into d_tab
+    size_t o_fac, o_clat, o_whi, o_wlo, o_qg, o_alat, o_da, o_cosmid, o_norm, o_vw, o_sinlat;
+    size_t o_ajk, o_bjk, o_fact, o_cosj, o_cor, o_cosw, o_eref, o_ez, o_uzc1, o_uzc2;       // NH18 (nd rows)
+    size_t o_najk, o_nbjk, o_nfact, o_topcoef, o_topden, o_cosrow, o_sinrow, o_sinnd;       // NHN22
+    size_t o_cosphi, o_sinphi, o_aaw, o_ep11a;                                             // flux (nd+2)
+    size_t ntab;
+};
+
+namespace falwa {
+
+// ---------------------------------------------------------------------------------------------
+// three area-analysis histograms in one pass over pv and avort (north: +pv, south: -pv, avort)
+// hist layout: [b][3][k][2][nb]
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void hist_flush(double* sh, int nb, int cur, double sa, double sc) {
+    if (cur > 0) {
+        atomicAdd(&sh[cur - 1], sa);
+        atomicAdd(&sh[nb + cur - 1], sc);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+area_hist3_kernel(int nlon, int nlat, int kmax, int nb, int with_avort, const double* __restrict__ pv,
+                  const double* __restrict__ avort, const unsigned long long* __restrict__ ext,
+                  const double* __restrict__ da, int rows_per_block, double* __restrict__ hist) {
+    extern __shared__ double sh[];  // [3][2][nb]
+    const int k = blockIdx.y + 1, b = blockIdx.z;
+    const int nh = with_avort ? 3 : 2;
+    pv += (size_t)b * nlon * nlat * kmax;
+    if (avort) avort += (size_t)b * nlon * nlat * kmax;
+    ext += (size_t)b * 2 * kmax * 2;
+    hist += (size_t)b * 3 * kmax * 2 * nb;
+    for (int t = threadIdx.x; t < nh * 2 * nb; t += blockDim.x) sh[t] = 0.0;
+    __syncthreads();
+    const double pmax = ordered_to_f64(ext[k * 2 + 0]), pmin = ordered_to_f64(ext[k * 2 + 1]);
+    const double dqp = (pmax - pmin) / (double)(nb - 1);
+    const double smax = -pmin;                      // southern frame: q' = -pv, max' = -min
+    const double dqs = (smax - (-pmax)) / (double)(nb - 1);
+    double vmax = 0., dqv = 1.;
+    if (with_avort) {
+        vmax = ordered_to_f64(ext[(kmax + k) * 2 + 0]);
+        const double vmin = ordered_to_f64(ext[(kmax + k) * 2 + 1]);
+        dqv = (vmax - vmin) / (double)(nb - 1);
+    }
+    const int j0 = blockIdx.x * rows_per_block, j1 = min(nlat, j0 + rows_per_block);
+    const int run = 8;
+    const int runs_per_row = (nlon + run - 1) / run;
+    const int total = (j1 - j0) * runs_per_row;
+    const size_t lev = (size_t)k * nlat * nlon;
+    double* hN = sh;
+    double* hS = sh + 2 * nb;
+    double* hV = sh + 4 * nb;
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        const int j = j0 + t / runs_per_row;
+        const int i0 = (t % runs_per_row) * run, i1 = min(nlon, i0 + run);
+        const double daj = da[j];
+        int cn = -1, cs = -1, cv = -1;
+        double an = 0, qn = 0, as = 0, qs = 0, av = 0, qv = 0;
+        for (int i = i0; i < i1; ++i) {
+            const double q = pv[lev + (size_t)j * nlon + i];
+            int ind = max(1, min(nb, 1 + (int)((pmax - q) / dqp)));
+            if (ind != cn) { hist_flush(hN, nb, cn, an, qn); cn = ind; an = 0; qn = 0; }
+            an += daj; qn += daj * q;
+            const double qq = -q;
+            ind = max(1, min(nb, 1 + (int)((smax - qq) / dqs)));
+            if (ind != cs) { hist_flush(hS, nb, cs, as, qs); cs = ind; as = 0; qs = 0; }
+            as += daj; qs += daj * qq;
+            if (with_avort) {
+                const double w = avort[lev + (size_t)j * nlon + i];
+                ind = max(1, min(nb, 1 + (int)((vmax - w) / dqv)));
+                if (ind != cv) { hist_flush(hV, nb, cv, av, qv); cv = ind; av = 0; qv = 0; }
+                av += daj; qv += daj * w;
+            }
+        }
+        hist_flush(hN, nb, cn, an, qn);
+        hist_flush(hS, nb, cs, as, qs);
+        if (with_avort) hist_flush(hV, nb, cv, av, qv);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nh * 2 * nb; t += blockDim.x) {
+        const double x = sh[t];
+        if (x != 0.0) {
+            const int hsel = t / (2 * nb), r = t % (2 * nb);
+            atomicAdd(&hist[((size_t)hsel * kmax + k) * 2 * nb + r], x);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// merge hemispheric reference-state profiles into the global-latitude storage
+// (data_storage.py:32-62: north written to the last rows, south written flipped afterwards)
+//   qref_st[k][nlat] <- stored (normalised) qref ; qref_cu = ((qref_st*2)*omega)*sin(lat)
+// ---------------------------------------------------------------------------------------------
+__global__ void merge_refstates_kernel(int kmax, int nlat, int nd, int jd, int north_only, double qscale, double omega,
+                                       const double* __restrict__ sinlat, const double* __restrict__ qN,
+                                       const double* __restrict__ qS, const double* __restrict__ uN,
+                                       const double* __restrict__ uS, const double* __restrict__ tN,
+                                       const double* __restrict__ tS, double* __restrict__ qref_st,
+                                       double* __restrict__ qref_cu, double* __restrict__ uref_st,
+                                       double* __restrict__ ptref_st) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= kmax * nlat) return;
+    const int k = t / nlat, j = t % nlat;  // global row
+    double q, u = 0.0, th = 0.0;
+    // south covers rows [0, nd), north rows [nlat-nd, nlat); the equator row takes the southern value
+    if (north_only) {
+        q = (j >= nlat - nd) ? qN[(size_t)k * nd + (j - (nlat - nd))] / qscale : 0.0;
+        if (j >= nlat - jd) { u = uN[(size_t)k * jd + (j - (nlat - jd))]; th = tN[(size_t)k * jd + (j - (nlat - jd))]; }
+    } else {
+        if (j < nd) q = qS[(size_t)k * nd + (nd - 1 - j)] / qscale;
+        else q = qN[(size_t)k * nd + (j - (nlat - nd))] / qscale;
+        if (j < jd) { u = uS[(size_t)k * jd + (jd - 1 - j)]; th = tS[(size_t)k * jd + (jd - 1 - j)]; }
+        else if (j >= nlat - jd) { u = uN[(size_t)k * jd + (j - (nlat - jd))]; th = tN[(size_t)k * jd + (j - (nlat - jd))]; }
+    }
+    qref_st[t] = q;
+    qref_cu[t] = q * 2 * omega * sinlat[j];
+    uref_st[t] = u;
+    ptref_st[t] = th;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LWA + flux integrands + density-weighted vertical sums, one hemisphere, brute-force LWA.
+// One thread per (lon, hemispheric row); levels are walked sequentially so the vertical sums are
+// accumulated in the order of numpy's reduction (oopinterface.py:405-420).
+// ---------------------------------------------------------------------------------------------
+struct FusedFluxArgs {
+    int imax, nlat, kmax, nd, jb, jd, south, has_ncforce;
+    double a, om, dz, prefac, ab, rrh, ep42fac, dc, cosjb, cosjbm1;
+    const double *pv, *uu, *vv, *pt, *ncforce;
+    const double *qref_cu, *uref_st, *tref_st;  // [b][k][nlat]
+    const double *prof;                         // [b][4][kmax]
+    const double *cosphi, *sinphi, *aaw, *ep11a, *vw;
+    double *lwa, *out2d;
+};
+
+__global__ void __launch_bounds__(256)
+fused_flux_bruteforce_kernel(FusedFluxArgs p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;  // hemispheric row 1..nd
+    const int b = blockIdx.z;
+    if (i >= p.imax || j > p.nd) return;
+    const int nd = p.nd, nlat = p.nlat, imax = p.imax, kmax = p.kmax, jb = p.jb;
+    const size_t plane = (size_t)nlat * imax;
+    const size_t f3 = (size_t)b * plane * kmax;
+    const double *pv = p.pv + f3, *uu = p.uu + f3, *vv = p.vv + f3, *pt = p.pt + f3;
+    const double* nc = p.has_ncforce ? p.ncforce + f3 : nullptr;
+    const double* qref = p.qref_cu + (size_t)b * kmax * nlat;
+    const double* uref = p.uref_st + (size_t)b * kmax * nlat;
+    const double* tref = p.tref_st + (size_t)b * kmax * nlat;
+    const double* tg = p.prof + (size_t)b * 4 * kmax + (p.south ? 0 : kmax);  // tn0 north / ts0 south
+    double* lwa = p.lwa + f3;
+    double* out = p.out2d + (size_t)b * O_COUNT * plane;
+    const double sg = p.south ? -1.0 : 1.0;  // sign of pv, v and qref in the hemispheric frame
+    auto grow = [&](int jj) -> int { return p.south ? (nd - jj) : (nd - 2 + jj); };  // 0-based global row
+    const int g = grow(j);
+    const int jstart = jb + 1, jend = nd - 1;
+    const bool in_range = (j >= jstart && j <= jend);
+    const bool brow = (jb >= 1) ? (j == jb) : (j == nd);  // boundary row jb, or its alias (i,nd,k-1) when jb = 0
+    const double cphi0 = p.cosphi[j];
+    double s_a1 = 0, s_a2 = 0, s_ua1 = 0, s_ua2 = 0, s_ep1 = 0, s_ep2 = 0, s_ep3 = 0, s_nc = 0, s_u = 0, ep4 = 0;
+    const size_t o2 = (size_t)g * imax + i;
+    lwa[o2] = 0.0;
+    lwa[(size_t)(kmax - 1) * plane + o2] = 0.0;
+    for (int k = 2; k <= kmax; ++k) {  // 1-based level
+        const size_t lev = (size_t)(k - 1) * plane;
+        const double w = p.vw[k - 1];
+        s_u = s_u + uu[lev + o2] * w * p.dc;
+        if (k == kmax) break;
+        double a1 = 0, a2 = 0, ncf = 0, u2 = 0, e1 = 0, e2 = 0, e3 = 0, x_ua1 = 0;
+        if (in_range) {
+            const double qr = sg * qref[(size_t)(k - 1) * nlat + g];
+            const double ur = uref[(size_t)(k - 1) * nlat + g];
+            for (int jj = 1; jj < j; ++jj) {
+                const size_t gg = lev + (size_t)grow(jj) * imax + i;
+                const double qe = sg * pv[gg] - qr;
+                if (qe > 0.) {
+                    const double aa = p.aaw[jj];
+                    const double ue = uu[gg] * cphi0 - ur * p.cosphi[jj];
+                    a1 = a1 + qe * aa;
+                    if (nc) ncf = ncf + nc[gg] * aa;
+                    u2 = u2 + qe * ue * p.ab;
+                }
+            }
+            for (int jj = j; jj <= nd; ++jj) {
+                const size_t gg = lev + (size_t)grow(jj) * imax + i;
+                const double qe = sg * pv[gg] - qr;
+                if (qe <= 0.) {
+                    const double aa = p.aaw[jj];
+                    const double ue = uu[gg] * cphi0 - ur * p.cosphi[jj];
+                    a2 = a2 - qe * aa;
+                    if (nc) ncf = ncf - nc[gg] * aa;
+                    u2 = u2 - qe * ue * p.ab;
+                }
+            }
+            const size_t gc = lev + o2;
+            const double uu0 = uu[gc], vv0 = sg * vv[gc], pt0 = pt[gc];
+            const double tr = tref[(size_t)(k - 1) * nlat + g];
+            x_ua1 = ur * (a1 + a2);
+            e1 = -0.5 * ((uu0 - ur) * (uu0 - ur));
+            e1 = e1 + 0.5 * (vv0 * vv0);
+            double ep11 = 0.5 * ((pt0 - tr) * (pt0 - tr));
+            ep11 = ep11 * p.rrh * p.ep11a[k - 1];
+            ep11 = ep11 * 2. * p.dz / (tg[k] - tg[k - 2]);
+            e1 = e1 - ep11;
+            const double cosp = p.cosphi[j + 1], cosm = p.cosphi[j - 1], sin0 = p.sinphi[j];
+            e1 = e1 * cphi0;
+            const size_t gp = lev + (size_t)grow(j + 1) * imax + i, gm = lev + (size_t)grow(j - 1) * imax + i;
+            const double urp = uref[(size_t)(k - 1) * nlat + grow(j + 1)];
+            // uref(j-jb-1): for the first row this is the reference's out-of-bounds uref(0,k) == uref(jd,k-1)
+            const double urm = (j - jb - 1 >= 1) ? uref[(size_t)(k - 1) * nlat + grow(j - 1)]
+                                                 : uref[(size_t)(k - 2) * nlat + grow(nd)];
+            e2 = (uu[gp] - urp) * cosp * cosp * (sg * vv[gp]);
+            e3 = (uu[gm] - urm) * cosm * cosm * (sg * vv[gm]);
+            if (k == 2) {
+                const double ep41 = 2. * p.om * sin0 * cphi0 * p.dz / p.prefac;
+                const double ep42 = p.ep42fac * (sg * vv[plane + o2]) * (pt[plane + o2] - tref[nlat + g]) / (tg[2] - tg[0]);
+                double ep43 = (sg * vv[o2]) * (pt[o2] - tref[g]);
+                ep43 = 0.5 * ep43 / (tg[1] - tg[0]);
+                ep4 = ep41 * (ep42 + ep43);
+            }
+        }
+        lwa[lev + o2] = fabs(a1 + a2);
+        double wk = w;
+        if (brow) {  // compute_flux_dirinv.f90:173-178
+            const size_t r1 = lev + (size_t)grow(jb + 2) * imax + i, r0 = lev + (size_t)grow(jb + 1) * imax + i;
+            e2 = (uu[r1] - uref[(size_t)(k - 1) * nlat + grow(jb + 2)]) * p.cosjb * p.cosjb * (sg * vv[r1]);
+            e3 = (uu[r0] - uref[(size_t)(k - 1) * nlat + grow(jb + 1)]) * p.cosjbm1 * p.cosjbm1 * (sg * vv[r0]);
+            if (jb == 0) wk = (k >= 3) ? p.vw[k - 2] : 0.0;  // aliased into level k-1; level 1 is not averaged
+        }
+        s_a1 = s_a1 + a1 * w * p.dc;
+        s_a2 = s_a2 + a2 * w * p.dc;
+        s_ua1 = s_ua1 + x_ua1 * w * p.dc;
+        s_ua2 = s_ua2 + u2 * w * p.dc;
+        s_ep1 = s_ep1 + e1 * w * p.dc;
+        s_ep2 = s_ep2 + e2 * wk * p.dc;
+        s_ep3 = s_ep3 + e3 * wk * p.dc;
+        s_nc = s_nc + ncf * w * p.dc;
+    }
+    out[(size_t)O_ASTAR1 * plane + o2] = s_a1;
+    out[(size_t)O_ASTAR2 * plane + o2] = s_a2;
+    out[(size_t)O_LWA * plane + o2] = s_a1 + s_a2;
+    out[(size_t)O_UA1 * plane + o2] = s_ua1;
+    out[(size_t)O_UA2 * plane + o2] = s_ua2;
+    out[(size_t)O_EP1 * plane + o2] = s_ep1;
+    // southern hemisphere: ep2/ep3 swapped and negated, ncforce negated (oopinterface.py:790-792)
+    out[(size_t)O_EP2 * plane + o2] = p.south ? -s_ep3 : s_ep2;
+    out[(size_t)O_EP3 * plane + o2] = p.south ? -s_ep2 : s_ep3;
+    out[(size_t)O_EP4 * plane + o2] = ep4;
+    out[(size_t)O_NCF * plane + o2] = p.south ? -s_nc : s_nc;
+    out[(size_t)O_UBARO * plane + o2] = s_u;
+}
+
+// barotropic post-processing (oopinterface.py:906-944, :964-982; utilities.py:189-233)
+__global__ void __launch_bounds__(256)
+baro_post_kernel(int nlon, int nlat, int kmax, double a, double dphi, double dlambda, double dc,
+                 const double* __restrict__ clat, const double* __restrict__ vw, const double* __restrict__ uu,
+                 const double* __restrict__ vv, const double* __restrict__ uref_st, double* __restrict__ out2d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y, b = blockIdx.z;
+    if (i >= nlon) return;
+    const size_t plane = (size_t)nlat * nlon;
+    double* out = out2d + (size_t)b * O_COUNT * plane;
+    const size_t o = (size_t)j * nlon + i;
+    const double cl = clat[j];
+    out[(size_t)O_DIVEMF * plane + o] = (out[(size_t)O_EP2 * plane + o] - out[(size_t)O_EP3 * plane + o]) / (2 * a * dphi * cl);
+    auto zsum = [&](int ii) -> double {
+        const size_t oo = (size_t)j * nlon + ii;
+        return out[(size_t)O_UA1 * plane + oo] + out[(size_t)O_UA2 * plane + oo] + out[(size_t)O_EP1 * plane + oo];
+    };
+    const int ip = (i == nlon - 1) ? 0 : i + 1, im = (i == 0) ? nlon - 1 : i - 1;
+    double zd = zsum(ip) - zsum(im);
+    if (fabs(cl) > 1.e-5) zd = zd * (-1. / (a * cl * 2. * dlambda));
+    out[(size_t)O_CONV * plane + o] = zd;
+    out[(size_t)O_FLAMBDA * plane + o] = zsum(i);
+    // flux_vector_phi_baro = vertical average of -((u - uref) * v) * clat over levels index 1..kmax-1
+    const double* u3 = uu + (size_t)b * plane * kmax;
+    const double* v3 = vv + (size_t)b * plane * kmax;
+    const double* ur = uref_st + (size_t)b * kmax * nlat;
+    double s = 0.0;
+    for (int k = 1; k < kmax; ++k) {
+        const double x = -(((u3[(size_t)k * plane + o] - ur[(size_t)k * nlat + j]) * v3[(size_t)k * plane + o]) * cl);
+        s = s + x * vw[k] * dc;
+    }
+    out[(size_t)O_FPHI * plane + o] = s;
+}
+
+// small helpers -------------------------------------------------------------------------------
+static size_t push_tab(std::vector<double>& tab, const std::vector<double>& v) {
+    const size_t o = tab.size();
+    tab.insert(tab.end(), v.begin(), v.end());
+    return o;
+}
+
+}  // namespace falwa
+
+using namespace falwa;
+
+// ================================ C ABI, Section B =============================================
+extern "C" int falwa_b200_plan_create(falwa_plan** out, int kind, int nlon, int nlat, int nlev, int kmax, int jb,
+                                      int npart, int maxit, const double* plev_to_height_host,
+                                      const double* theta_factor_host, const double* clat_host,
+                                      const double* sinlat_host, double a, double omega, double dz, double h,
+                                      double rr, double cp, double tol, double rjac, double prefactor) {
+    if (!out || !plev_to_height_host || !theta_factor_host || !clat_host || !sinlat_host) return FALWA_ERR_NULL;
+    if ((kind != 0 && kind != 1) || nlon < 4 || nlat < 9 || (nlat % 2) != 1 || nlev < 2 || kmax < 4 || jb < 0)
+        return FALWA_ERR_ARG;
+    const int nd = nlat / 2 + 1;
+    if (kind == 0) jb = 0;
+    const int jd = nd - jb;
+    if (jd < 4) return FALWA_ERR_ARG;
+    falwa_plan* P = new falwa_plan();
+    P->kind = kind; P->nlon = nlon; P->nlat = nlat; P->nlev = nlev; P->kmax = kmax; P->jb = jb; P->nd = nd; P->jd = jd;
+    P->npart = npart > 0 ? npart : nlat; P->maxit = maxit;
+    P->a = a; P->omega = omega; P->dz = dz; P->h = h; P->rr = rr; P->cp = cp; P->tol = tol; P->rjac = rjac;
+    P->prefactor = prefactor;
+    const double pi = host_pi();
+    // oopinterface.py:164-165: np.deg2rad(180/(nlat-1)), np.deg2rad(360/nlon)
+    P->dphi = (180. / (double)(nlat - 1)) * (pi / 180.);
+    P->dlambda = (360. / (double)nlon) * (pi / 180.);
+    const double dphi = P->dphi, rkappa = rr / cp;
+    P->height.resize(kmax);
+    for (int k = 0; k < kmax; ++k) P->height[k] = (double)k * dz;
+    std::vector<double> tab;
+    P->o_fac = push_tab(tab, std::vector<double>(theta_factor_host, theta_factor_host + nlev));
+    P->o_clat = push_tab(tab, std::vector<double>(clat_host, clat_host + nlat));
+    P->o_sinlat = push_tab(tab, std::vector<double>(sinlat_host, sinlat_host + nlat));
+    // interpolation tables (scipy interp1d linear, extrapolating)
+    std::vector<double> whi(kmax), wlo(kmax);
+    std::vector<int> lo(kmax);
+    const double* x = plev_to_height_host;
+    for (int k = 0; k < kmax; ++k) {
+        const double xn = P->height[k];
+        int idx = 0;
+        while (idx < nlev && x[idx] < xn) ++idx;  // searchsorted(side='left')
+        idx = std::max(1, std::min(nlev - 1, idx));
+        lo[k] = idx - 1;
+        const double xl = x[idx - 1], xh = x[idx];
+        whi[k] = (xn - xl) / (xh - xl);
+        wlo[k] = (xh - xn) / (xh - xl);
+    }
+    P->o_whi = push_tab(tab, whi);
+    P->o_wlo = push_tab(tab, wlo);
+    {
+        std::vector<double> qg;
+        qgpv_tables_host(kind == 0 ? 0 : 1, nlat, kmax, P->height.data(), a, omega, h, qg);
+        P->o_qg = push_tab(tab, qg);
+    }
+    std::vector<double> alat, da;
+    host_alat_da(nd, nlat, a, dphi, P->dlambda, alat, da);
+    P->o_alat = push_tab(tab, alat);
+    P->o_da = push_tab(tab, da);
+    std::vector<double> cosmid(nd, 0.), norm(nd, 1.), vw(kmax);
+    for (int j = 1; j <= nd; ++j) {
+        cosmid[j - 1] = std::cos(dphi * ((double)j - 0.5));
+        const double s = std::sin(dphi * (double)(j - 1));
+        norm[j - 1] = (kind == 0) ? 2. * omega * s : s;
+    }
+    for (int k = 0; k < kmax; ++k) vw[k] = std::exp(-P->height[k] / h);
+    P->o_cosmid = push_tab(tab, cosmid);
+    P->o_norm = push_tab(tab, norm);
+    P->o_vw = push_tab(tab, vw);
+    std::vector<double> eref(kmax), ez(kmax);
+    for (int k = 1; k <= kmax; ++k) {
+        eref[k - 1] = std::exp(rkappa * (dz * (double)(k - 1)) / h);
+        ez[k - 1] = std::exp((dz * (double)(k - 1)) / h);
+    }
+    P->o_eref = push_tab(tab, eref);
+    P->o_ez = push_tab(tab, ez);
+    if (kind == 0) {  // NH18 SOR tables (compute_reference_states.f90:135-162, :188-190, :60-65)
+        std::vector<double> ajk(nd, 0.), bjk(nd, 0.), fact(nd, 0.), cosj(nd), cor(nd), cosw(nd), c1(nd, 0.), c2(nd, 1.);
+        for (int j = 1; j <= nd; ++j) {
+            const double phi0 = dphi * (double)(j - 1);
+            cosj[j - 1] = std::cos(phi0);
+            cor[j - 1] = 2. * omega * std::sin(phi0);
+            cosw[j - 1] = std::cos(dphi * (double)(j + nd - 2) - 0.5 * pi);
+            if (j >= 2 && j <= nd - 1) {
+                const double phip = ((double)j - 0.5) * dphi, phim = ((double)j - 1.5) * dphi;
+                ajk[j - 1] = 1. / (std::sin(phip) * std::cos(phip));
+                bjk[j - 1] = 1. / (std::sin(phim) * std::cos(phim));
+                fact[j - 1] = 4. * omega * omega * h * a * a * std::sin(phi0) * dphi * dphi / (dz * dz * rr * std::cos(phi0));
+                c1[j - 1] = dz * rr * std::cos(phi0) * std::exp(-(dz * (double)(kmax - 2)) * rkappa / h);
+                c2[j - 1] = 2. * omega * std::sin(phi0) * dphi * h * a;
+            }
+        }
+        P->o_ajk = push_tab(tab, ajk); P->o_bjk = push_tab(tab, bjk); P->o_fact = push_tab(tab, fact);
+        P->o_cosj = push_tab(tab, cosj); P->o_cor = push_tab(tab, cor); P->o_cosw = push_tab(tab, cosw);
+        P->o_uzc1 = push_tab(tab, c1); P->o_uzc2 = push_tab(tab, c2);
+    } else {  // NHN22 tables; latitude step of these routines is pi/(jmax-1)
+        const int n = jd - 2;
+        const double dp = pi / (double)(nlat - 1);
+        std::vector<double> ajk(n), bjk(n), fact(n), tc(n), td(n), cosrow(jd), sinrow(jd), sinnd(nd);
+        for (int jj = jb + 2; jj <= nd - 1; ++jj) {
+            const int i = jj - jb - 2;
+            const double phi0 = (double)(jj - 1) * dp, phip = ((double)jj - 0.5) * dp, phim = ((double)jj - 1.5) * dp;
+            ajk[i] = 1. / (std::sin(phip) * std::cos(phip));
+            bjk[i] = 1. / (std::sin(phim) * std::cos(phim));
+            fact[i] = 4. * omega * omega * h * a * a * std::sin(phi0) * dp * dp / (dz * dz * rr * std::cos(phi0));
+            const double phi0b = (double)(jj - 1) * dphi;  // compute_qref_and_fawa_first uses the dphi argument
+            tc[i] = -dz * rr * std::cos(phi0b) * std::exp(-(dz * (double)(kmax - 2)) * rkappa / h);
+            td[i] = 4. * omega * std::sin(phi0b) * dphi * h * a;
+        }
+        for (int j = 1; j <= jd; ++j) {
+            cosrow[j - 1] = std::cos(dp * (double)(j + jb - 1));
+            sinrow[j - 1] = std::sin(dp * (double)(j - 1 + jb));
+        }
+        for (int j = 1; j <= nd; ++j) sinnd[j - 1] = std::sin(dp * (double)(j - 1));
+        P->o_najk = push_tab(tab, ajk); P->o_nbjk = push_tab(tab, bjk); P->o_nfact = push_tab(tab, fact);
+        P->o_topcoef = push_tab(tab, tc); P->o_topden = push_tab(tab, td);
+        P->o_cosrow = push_tab(tab, cosrow); P->o_sinrow = push_tab(tab, sinrow); P->o_sinnd = push_tab(tab, sinnd);
+    }
+    {  // flux tables (compute_flux_dirinv.f90: dp = pi/(jmax-1), northern-hemisphere branch)
+        const double dp = pi / (double)(nlat - 1);
+        const int nt = nd + 2;
+        std::vector<double> cosphi(nt), sinphi(nt), aaw(nt), ep11a(kmax, 0.);
+        for (int jj = 0; jj <= nd + 1; ++jj) {
+            const double phi1 = dp * (double)(jj - 1);
+            cosphi[jj] = std::cos(phi1);
+            sinphi[jj] = std::sin(phi1);
+            aaw[jj] = a * dp * std::cos(phi1);
+        }
+        for (int k = 2; k <= kmax - 1; ++k) ep11a[k - 1] = std::exp(-rkappa * (dz * (double)(k - 1)) / h);
+        P->o_cosphi = push_tab(tab, cosphi); P->o_sinphi = push_tab(tab, sinphi); P->o_aaw = push_tab(tab, aaw);
+        P->o_ep11a = push_tab(tab, ep11a);
+    }
+    P->ntab = tab.size();
+    cudaError_t e = cudaMalloc((void**)&P->d_tab, tab.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&P->d_lo, kmax * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(P->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(P->d_lo, lo.data(), kmax * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {  // keep stream-ordered scratch cached between calls
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
+    if (e != cudaSuccess) {
+        if (P->d_tab) cudaFree(P->d_tab);
+        if (P->d_lo) cudaFree(P->d_lo);
+        delete P;
+        return (int)e;
+    }
+    *out = P;
+    return 0;
+}
+
+extern "C" int falwa_b200_plan_destroy(falwa_plan* P) {
+    if (!P) return 0;
+    if (P->d_tab) cudaFree(P->d_tab);
+    if (P->d_lo) cudaFree(P->d_lo);
+    delete P;
+    return 0;
+}
+
+// hemispheric cos-weighted mean theta per pressure level: means [batch][2][nlev] (0 = south, 1 = north)
+extern "C" int falwa_b200_theta_hemispheric_means(const falwa_plan* P, int batch, const double* t_in, double* means,
+                                                  void* stream) {
+    if (!P || !t_in || !means) return FALWA_ERR_NULL;
+    if (batch < 1) return FALWA_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceScratch<double> rowmean;
+    int rc = rowmean.alloc((size_t)batch * P->nlev * P->nlat, st);
+    if (rc) return rc;
+    return theta_means_launch(P->nlon, P->nlat, P->nlev, P->jd, batch, t_in, P->d_tab + P->o_fac, P->d_tab + P->o_clat,
+                              rowmean.d, means, st);
+}
+
+// vertical interpolation + QGPV.  profiles_host [batch][4][kmax] = t0_s, t0_n, stat_s, stat_n at `height`.
+extern "C" int falwa_b200_interpolate_fields(const falwa_plan* P, int batch, const double* u_in, const double* v_in,
+                                             const double* t_in, int already_on_height_grid,
+                                             const double* profiles_host, double* u, double* v, double* theta,
+                                             double* avort, double* qgpv, void* stream) {
+    if (!P || !u_in || !v_in || !t_in || !profiles_host || !u || !v || !theta || !avort || !qgpv) return FALWA_ERR_NULL;
+    if (batch < 1) return FALWA_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const double* d = P->d_tab;
+    int rc;
+    if (!already_on_height_grid) {
+        if ((rc = interp_launch(P->nlon, P->nlat, P->nlev, P->kmax, batch, u_in, v_in, t_in, P->d_lo, d + P->o_whi,
+                                d + P->o_wlo, d + P->o_fac, u, v, theta, st)))
+            return rc;
+    }
+    DeviceScratch<double> prof;
+    if ((rc = prof.alloc((size_t)batch * 4 * P->kmax, st))) return rc;
+    FALWA_CUDA_TRY(cudaMemcpyAsync(prof.d, profiles_host, sizeof(double) * (size_t)batch * 4 * P->kmax,
+                                   cudaMemcpyHostToDevice, st));
+    const int jdsplit = (P->kind == 0) ? P->nlat : P->nd;  // NHN22: rows j <= equator use the southern profile
+    return qgpv_launch(P->kind == 0 ? 0 : 1, P->nlon, P->nlat, P->kmax, jdsplit, batch, u, v, theta, d + P->o_qg, prof.d,
+                       qgpv, avort, st);
+}
+
+// reference states of both hemispheres -> global-latitude storage [batch][kmax][nlat]
+//   qref_st: stored (normalised) qref; qref_cu: qref in s^-1; uref_st; ptref_st.
+//   num_of_iter_host [batch][2] (NH18 SOR iterations north, south; 0 for NHN22).  Synchronises.
+extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const double* qgpv, const double* u,
+                                           const double* theta, const double* avort, const double* profiles_host,
+                                           int north_only, double* qref_st, double* qref_cu, double* uref_st,
+                                           double* ptref_st, int* num_of_iter_host, void* stream) {
+    if (!P || !qgpv || !u || !theta || !avort || !profiles_host || !qref_st || !qref_cu || !uref_st || !ptref_st ||
+        !num_of_iter_host)
+        return FALWA_ERR_NULL;
+    if (batch < 1) return FALWA_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const double* d = P->d_tab;
+    const int nlon = P->nlon, nlat = P->nlat, kmax = P->kmax, nd = P->nd, jd = P->jd, jb = P->jb;
+    const int nb = (P->kind == 0) ? P->npart : nlat;  // NHN22 ignores npart
+    const double pi = host_pi(), rkappa = P->rr / P->cp;
+    const size_t njk = (size_t)nd * kmax, njd = (size_t)jd * kmax;
+    int rc;
+    DeviceScratch<double> zm, hist, prof, work;
+    DeviceScratch<unsigned long long> ext;
+    DeviceScratch<int> nit;
+    if ((rc = zm.alloc((size_t)batch * 3 * kmax * nlat, st))) return rc;
+    if ((rc = hist.alloc((size_t)batch * 3 * kmax * 2 * nb, st, true))) return rc;
+    if ((rc = ext.alloc((size_t)batch * 2 * kmax * 2, st))) return rc;
+    if ((rc = nit.alloc((size_t)batch * 2, st, true))) return rc;
+    // per (b, hemisphere): qref, cref, cbar, ubar, tbar [njk each]; uref, tref [njd]; fjk [njk]; tb[kmax]; uz[nd]
+    const size_t per = 6 * njk + 2 * njd + kmax + nd;
+    const size_t ckoff = (size_t)batch * 2 * per;  // ckref per snapshot
+    if ((rc = work.alloc(ckoff + (size_t)batch * njk, st, true))) return rc;
+    init_ext_kernel<<<ceil_div((long long)batch * 2 * kmax * 2, 128), 128, 0, st>>>(ext.d, batch * 2 * kmax * 2);
+    zonal_stats_kernel<<<dim3(nlat, kmax, batch), 256, 0, st>>>(nlon, nlat, kmax, qgpv, u, theta, avort, zm.d, ext.d,
+                                                                P->kind == 0 ? 1 : 3);
+    FALWA_LAUNCH_CHECK();
+    {
+        int slabs = std::max(1, std::min(nlat, (148 * 4 + (kmax - 3)) / (kmax - 2) / std::max(1, std::min(batch, 4))));
+        const int rows = ceil_div(nlat, slabs);
+        slabs = ceil_div(nlat, rows);
+        const int nh = (P->kind == 0) ? 2 : 3;
+        const size_t smem = sizeof(double) * nh * 2 * nb;
+        if (smem > 48 * 1024)
+            FALWA_CUDA_TRY(cudaFuncSetAttribute(area_hist3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        area_hist3_kernel<<<dim3(slabs, kmax - 2, batch), 256, smem, st>>>(nlon, nlat, kmax, nb, P->kind != 0, qgpv, avort,
+                                                                          ext.d, d + P->o_da, rows, hist.d);
+        FALWA_LAUNCH_CHECK();
+    }
+    // host-built per-problem tables
+    std::vector<double> htab;
+    std::vector<size_t> o_spec((size_t)batch * 2), o_amp((size_t)batch * 2);
+    for (int b = 0; b < batch; ++b)
+        for (int hs = 0; hs < 2; ++hs) {
+            // hs 0 = north uses stat_n (row 3), hs 1 = south uses stat_s (row 2)
+            const double* stat = profiles_host + ((size_t)b * 4 + (hs == 0 ? 3 : 2)) * kmax;
+            if (P->kind == 0) {
+                std::vector<double> amp(kmax, 0.), amm(kmax, 0.);
+                for (int k = 2; k <= kmax - 1; ++k) {
+                    const double zk = P->dz * (double)(k - 1), zkp = P->dz * (double)k, zkm = P->dz * (double)(k - 2);
+                    const double zp = 0.5 * (zkp + zk), zmm = 0.5 * (zkm + zk);
+                    const double statp = 0.5 * (stat[k] + stat[k - 1]), statm = 0.5 * (stat[k - 2] + stat[k - 1]);
+                    amp[k - 1] = std::exp(-zp / P->h) * std::exp(rkappa * zp / P->h) / statp;
+                    amm[k - 1] = std::exp(-zmm / P->h) * std::exp(rkappa * zmm / P->h) / statm;
+                }
+                o_amp[(size_t)b * 2 + hs] = push_tab(htab, amp);
+                push_tab(htab, amm);
+            } else {
+                std::vector<double> spec;
+                const int er = vertical_operator_spectrum(kmax, stat, P->dz, P->h, rkappa, spec);
+                if (er) return FALWA_ERR_UNSUPPORTED;
+                o_spec[(size_t)b * 2 + hs] = push_tab(htab, spec);
+            }
+        }
+    const size_t o_prof = push_tab(htab, std::vector<double>(profiles_host, profiles_host + (size_t)batch * 4 * kmax));
+    DeviceTable HT;
+    if ((rc = HT.upload(htab, st))) return rc;
+    FALWA_CUDA_TRY(cudaMemsetAsync(uref_st, 0, sizeof(double) * (size_t)batch * kmax * nlat, st));
+    // ---- per (snapshot, hemisphere) profile kernels ---------------------------------------------
+    auto W = [&](int b, int hs, int which) -> double* {  // which: 0 qref 1 cref 2 cbar 3 ubar 4 tbar 5 fjk
+        return work.d + ((size_t)b * 2 + hs) * per + (size_t)which * njk;
+    };
+    auto WU = [&](int b, int hs) { return work.d + ((size_t)b * 2 + hs) * per + 6 * njk; };
+    auto WT = [&](int b, int hs) { return work.d + ((size_t)b * 2 + hs) * per + 6 * njk + njd; };
+    auto WTB = [&](int b, int hs) { return work.d + ((size_t)b * 2 + hs) * per + 6 * njk + 2 * njd; };
+    auto WUZ = [&](int b, int hs) { return work.d + ((size_t)b * 2 + hs) * per + 6 * njk + 2 * njd + kmax; };
+    for (int b = 0; b < batch; ++b) {
+        const double* zmb = zm.d + (size_t)b * 3 * kmax * nlat;
+        const unsigned long long* extb = ext.d + (size_t)b * 2 * kmax * 2;
+        const double* histb = hist.d + (size_t)b * 3 * kmax * 2 * nb;
+        double* ckref = work.d + ckoff + (size_t)b * njk;
+        if (P->kind != 0) {
+            qref_invert_kernel<<<kmax - 2, 256, sizeof(double) * 2 * nb, st>>>(
+                kmax, nb, nd, nd, histb + (size_t)2 * kmax * 2 * nb, extb + (size_t)kmax * 2, 1.0, d + P->o_alat, nullptr,
+                ckref, 0);
+            FALWA_LAUNCH_CHECK();
+        }
+        for (int hs = 0; hs < 2; ++hs) {
+            const double sgn = hs == 0 ? 1.0 : -1.0;
+            const int flip = hs == 0 ? 0 : nlat;
+            qref_invert_kernel<<<kmax - 2, 256, sizeof(double) * 2 * nb, st>>>(
+                kmax, nb, nd, nd, histb + (size_t)hs * kmax * 2 * nb, extb, sgn, d + P->o_alat, W(b, hs, 0), W(b, hs, 1), 1);
+            FALWA_LAUNCH_CHECK();
+            cbar_normalise_kernel<<<ceil_div(kmax, 64), 64, 0, st>>>(kmax, nd, zmb, nlat, sgn, flip, nd - 1, d + P->o_cosmid,
+                                                                     d + P->o_norm, P->a, P->dphi, pi, W(b, hs, 0),
+                                                                     W(b, hs, 1), W(b, hs, 2), nullptr);
+            extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, nd, nlat, nd - 1, flip, 1.0,
+                                                                   zmb + (size_t)1 * kmax * nlat, W(b, hs, 3));
+            extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, nd, nlat, nd - 1, flip, 1.0,
+                                                                   zmb + (size_t)2 * kmax * nlat, W(b, hs, 4));
+            FALWA_LAUNCH_CHECK();
+            if (P->kind == 0) {
+                tb_mean_kernel<<<ceil_div(kmax, 64), 64, 0, st>>>(kmax, nd, W(b, hs, 4), d + P->o_cosw, WTB(b, hs));
+                sor_uz_kernel<<<ceil_div(nd, 128), 128, 0, st>>>(nd, kmax, d + P->o_uzc1, d + P->o_uzc2, W(b, hs, 4),
+                                                                 WUZ(b, hs));
+                FALWA_LAUNCH_CHECK();
+            }
+        }
+    }
+    // ---- batched solves --------------------------------------------------------------------------
+    const int nprob = batch * 2;
+    if (P->kind == 0) {
+        std::vector<SorArgs> probs(nprob);
+        for (int b = 0; b < batch; ++b)
+            for (int hs = 0; hs < 2; ++hs) {
+                SorArgs& p = probs[(size_t)b * 2 + hs];
+                p.jd = nd; p.kmax = kmax; p.maxits = P->maxit;
+                p.om = P->omega; p.a = P->a; p.dphi = P->dphi; p.dz = P->dz; p.eps = P->tol; p.rjac = P->rjac; p.pi = pi;
+                p.h = P->h; p.r = P->rr;
+                p.ajk = d + P->o_ajk; p.bjk = d + P->o_bjk; p.fact = d + P->o_fact; p.uz = WUZ(b, hs);
+                p.cosj = d + P->o_cosj; p.cor = d + P->o_cor;
+                p.amp = HT.d + o_amp[(size_t)b * 2 + hs]; p.amm = p.amp + kmax; p.ez = d + P->o_ez; p.eref = d + P->o_eref;
+                p.qref = W(b, hs, 0); p.ubar = W(b, hs, 3); p.tbar = W(b, hs, 4); p.cref = W(b, hs, 1); p.cbar = W(b, hs, 2);
+                p.tb = WTB(b, hs); p.u = WU(b, hs); p.tref = WT(b, hs); p.fjk = W(b, hs, 5);
+                p.num_of_iter = nit.d + (size_t)b * 2 + hs;
+                p.u_in_smem = (sizeof(double) * njk <= 200 * 1024);
+            }
+        DeviceScratch<SorArgs> dp;
+        if ((rc = dp.alloc(nprob, st))) return rc;
+        FALWA_CUDA_TRY(cudaMemcpyAsync(dp.d, probs.data(), sizeof(SorArgs) * nprob, cudaMemcpyHostToDevice, st));
+        FALWA_CUDA_TRY(cudaFuncSetAttribute(sor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        const size_t smem = probs[0].u_in_smem ? sizeof(double) * njk : 0;
+        sor_kernel<<<nprob, 1024, smem, st>>>(dp.d);
+        FALWA_LAUNCH_CHECK();
+    } else {
+        const int n = jd - 2, m = kmax - 2;
+        DeviceScratch<double> sw;
+        const size_t per_s = 2 * (size_t)m * n + (size_t)n * m + (size_t)kmax * n + njk;  // g, gh, cp, pjk, qref_out
+        if ((rc = sw.alloc((size_t)nprob * per_s, st))) return rc;
+        std::vector<SpectralProblem> sp(nprob);
+        std::vector<SweepArgs> wp(nprob);
+        for (int b = 0; b < batch; ++b)
+            for (int hs = 0; hs < 2; ++hs) {
+                const size_t q = (size_t)b * 2 + hs;
+                double* base = sw.d + q * per_s;
+                SpectralProblem& s = sp[q];
+                s.qref = W(b, hs, 0); s.ckref = work.d + ckoff + (size_t)b * njk; s.tbar = W(b, hs, 4);
+                s.spec = HT.d + o_spec[q];
+                s.g = base; s.gh = base + (size_t)m * n; s.cp = base + 2 * (size_t)m * n; s.pjk = base + 3 * (size_t)m * n;
+                SweepArgs& w = wp[q];
+                w.n = n; w.jd = jd; w.nd = nd; w.kmax = kmax; w.jb = jb;
+                w.a = P->a; w.om = P->omega; w.dz = P->dz; w.h = P->h; w.rr = P->rr; w.dp = pi / (double)(nlat - 1); w.pi = pi;
+                w.sjk = nullptr; w.tjk = nullptr; w.ckref = s.ckref;
+                w.tb = HT.d + o_prof + ((size_t)b * 4 + 1) * kmax;  // tn0 for both hemispheres
+                w.qoc = W(b, hs, 0);
+                w.cosrow = d + P->o_cosrow; w.sinrow = d + P->o_sinrow; w.sinnd = d + P->o_sinnd; w.eref = d + P->o_eref;
+                w.tref = WT(b, hs); w.qref = base + 3 * (size_t)m * n + (size_t)kmax * n; w.u = WU(b, hs); w.pjk = s.pjk;
+                w.u1top = 0.0; w.u1off = P->omega * P->a * std::cos(w.dp * (double)jb);
+            }
+        SpectralCommon c;
+        c.n = n; c.m = m; c.nd = nd; c.kmax = kmax; c.jb = jb;
+        c.ajk = d + P->o_najk; c.bjk = d + P->o_nbjk; c.fact = d + P->o_nfact; c.topcoef = d + P->o_topcoef;
+        c.topden = d + P->o_topden;
+        c.fcoef = -0.5 * P->a * (pi / (double)(nlat - 1));
+        c.u1coef = 2. * pi * P->a;
+        c.u1off = P->omega * P->a * std::cos((pi / (double)(nlat - 1)) * (double)jb);
+        DeviceScratch<SpectralProblem> dsp;
+        DeviceScratch<SweepArgs> dwp;
+        if ((rc = dsp.alloc(nprob, st))) return rc;
+        if ((rc = dwp.alloc(nprob, st))) return rc;
+        FALWA_CUDA_TRY(cudaMemcpyAsync(dsp.d, sp.data(), sizeof(SpectralProblem) * nprob, cudaMemcpyHostToDevice, st));
+        FALWA_CUDA_TRY(cudaMemcpyAsync(dwp.d, wp.data(), sizeof(SweepArgs) * nprob, cudaMemcpyHostToDevice, st));
+        nhn22_spectral_solve_kernel<<<nprob, 512, 0, st>>>(c, dsp.d);
+        FALWA_LAUNCH_CHECK();
+        sweep_post_kernel<<<nprob, 512, 0, st>>>(dwp.d);
+        FALWA_LAUNCH_CHECK();
+        // dsp/dwp/sw are stream-ordered: freed after the kernels that use them
+        for (int b = 0; b < batch; ++b) {
+            merge_refstates_kernel<<<ceil_div((long long)kmax * nlat, 256), 256, 0, st>>>(
+                kmax, nlat, nd, jd, north_only, 2. * P->omega, P->omega, d + P->o_sinlat, W(b, 0, 0), W(b, 1, 0), WU(b, 0), WU(b, 1),
+                WT(b, 0), WT(b, 1), qref_st + (size_t)b * kmax * nlat, qref_cu + (size_t)b * kmax * nlat,
+                uref_st + (size_t)b * kmax * nlat, ptref_st + (size_t)b * kmax * nlat);
+            FALWA_LAUNCH_CHECK();
+        }
+    }
+    if (P->kind == 0) {
+        for (int b = 0; b < batch; ++b) {
+            merge_refstates_kernel<<<ceil_div((long long)kmax * nlat, 256), 256, 0, st>>>(
+                kmax, nlat, nd, nd, north_only, 1.0, P->omega, d + P->o_sinlat, W(b, 0, 0), W(b, 1, 0), WU(b, 0), WU(b, 1), WT(b, 0),
+                WT(b, 1), qref_st + (size_t)b * kmax * nlat, qref_cu + (size_t)b * kmax * nlat,
+                uref_st + (size_t)b * kmax * nlat, ptref_st + (size_t)b * kmax * nlat);
+            FALWA_LAUNCH_CHECK();
+        }
+    }
+    FALWA_CUDA_TRY(cudaMemcpyAsync(num_of_iter_host, nit.d, sizeof(int) * nprob, cudaMemcpyDeviceToHost, st));
+    FALWA_CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// LWA and barotropic fluxes of both hemispheres.
+//   lwa [batch][kmax][nlat][nlon]; out2d [batch][15][nlat][nlon] (slot order: enum Out2D / falwa_b200.h)
+//   ncforce may be NULL (treated as zeros).  method: 0 = automatic, 1 = brute force.
+extern "C" int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* P, int batch, const double* qgpv,
+                                                    const double* u, const double* v, const double* theta,
+                                                    const double* ncforce, const double* profiles_host,
+                                                    const double* qref_cu, const double* uref_st,
+                                                    const double* ptref_st, int north_only, double* lwa,
+                                                    double* out2d, int method, void* stream) {
+    (void)method;
+    if (!P || !qgpv || !u || !v || !theta || !profiles_host || !qref_cu || !uref_st || !ptref_st || !lwa || !out2d)
+        return FALWA_ERR_NULL;
+    if (batch < 1) return FALWA_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const double* d = P->d_tab;
+    const double pi = host_pi(), dp = pi / (double)(P->nlat - 1);
+    int rc;
+    DeviceScratch<double> prof;
+    if ((rc = prof.alloc((size_t)batch * 4 * P->kmax, st))) return rc;
+    FALWA_CUDA_TRY(cudaMemcpyAsync(prof.d, profiles_host, sizeof(double) * (size_t)batch * 4 * P->kmax,
+                                   cudaMemcpyHostToDevice, st));
+    FusedFluxArgs p;
+    p.imax = P->nlon; p.nlat = P->nlat; p.kmax = P->kmax; p.nd = P->nd; p.jb = P->jb; p.jd = P->jd;
+    p.has_ncforce = ncforce != nullptr;
+    p.a = P->a; p.om = P->omega; p.dz = P->dz; p.prefac = P->prefactor; p.ab = P->a * dp; p.rrh = P->rr / P->h;
+    p.ep42fac = std::exp(-P->dz / P->h); p.dc = P->dz / P->prefactor;
+    p.cosjb = std::cos(dp * (double)P->jb); p.cosjbm1 = std::cos(dp * (double)(P->jb - 1));
+    p.pv = qgpv; p.uu = u; p.vv = v; p.pt = theta; p.ncforce = ncforce;
+    p.qref_cu = qref_cu; p.uref_st = uref_st; p.tref_st = ptref_st; p.prof = prof.d;
+    p.cosphi = d + P->o_cosphi; p.sinphi = d + P->o_sinphi; p.aaw = d + P->o_aaw; p.ep11a = d + P->o_ep11a; p.vw = d + P->o_vw;
+    p.lwa = lwa; p.out2d = out2d;
+    dim3 block(32, 8);
+    dim3 grid(ceil_div(P->nlon, 32), ceil_div(P->nd, 8), batch);
+    if (north_only) {  // rows the northern launch does not cover stay zero
+        FALWA_CUDA_TRY(cudaMemsetAsync(lwa, 0, sizeof(double) * (size_t)batch * P->kmax * P->nlat * P->nlon, st));
+        FALWA_CUDA_TRY(cudaMemsetAsync(out2d, 0, sizeof(double) * (size_t)batch * O_COUNT * P->nlat * P->nlon, st));
+    }
+    for (int south = 0; south < (north_only ? 1 : 2); ++south) {  // north first, south second: equator row = south
+        p.south = south;
+        fused_flux_bruteforce_kernel<<<grid, block, 0, st>>>(p);
+        FALWA_LAUNCH_CHECK();
+    }
+    baro_post_kernel<<<dim3(ceil_div(P->nlon, 256), P->nlat, batch), 256, 0, st>>>(
+        P->nlon, P->nlat, P->kmax, P->a, P->dphi, P->dlambda, p.dc, d + P->o_clat, d + P->o_vw, u, v, uref_st, out2d);
+    FALWA_LAUNCH_CHECK();
+    return 0;
+}

@@ -24,10 +24,9 @@ struct QgpvTables {
     const double* ep;
     const double* e0;
     const double* height;
-    // t0[2][kmax], stat[2][kmax]: row 0 = south (rows j <= jd), row 1 = north
-    const double* t0;
-    const double* stat;
 };
+// Per-snapshot profiles live in a separate device array prof[batch][4][kmax]:
+//   row 0 = t0 south (rows j <= jd), 1 = t0 north, 2 = static stability south, 3 = north.
 
 // mode 0: NH18  — pv receives (altp - altm), finished by nh18_finish_kernel (needs the zonal-mean avort)
 // mode 1: NHN22 — pv = avort + e0 * ((altp - altm) * f / dh)
@@ -35,7 +34,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 avort_pv_kernel(int nlon, int nlat, int kmax, int jd, int kchunk, const double* __restrict__ u,
                 const double* __restrict__ v, const double* __restrict__ th, QgpvTables tb,
-                double* __restrict__ avort, double* __restrict__ pv, size_t batch_stride) {
+                const double* __restrict__ prof, double* __restrict__ avort, double* __restrict__ pv,
+                size_t batch_stride) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;  // 0-based row
     const int nchunks = (kmax + kchunk - 1) / kchunk;
@@ -52,6 +52,8 @@ avort_pv_kernel(int nlon, int nlat, int kmax, int jd, int kchunk, const double* 
     const int im = (i == 0) ? nlon - 1 : i - 1;
     const double av1 = tb.av1[j], den = tb.den[j], cp = tb.cosp[j], cm = tb.cosm[j];
     const int hemi = (j + 1 <= jd) ? 0 : 1;
+    const double* t0 = prof + (size_t)b * 4 * kmax + hemi * kmax;
+    const double* stat = t0 + 2 * kmax;
     const size_t col = (size_t)j * nlon + i;
     // rolling theta registers: tm = theta(k-1), tp = theta(k+1)
     double tm = (k0 >= 1) ? th[(size_t)(k0 - 1) * plane + col] : 0.0;
@@ -67,8 +69,8 @@ avort_pv_kernel(int nlon, int nlat, int kmax, int jd, int kchunk, const double* 
         }
         double q = 0.0;
         if (k >= 1 && k <= kmax - 2) {
-            const double altp = tb.ep[k + 1] * (tp - tb.t0[hemi * kmax + k + 1]) / tb.stat[hemi * kmax + k + 1];
-            const double altm = tb.ep[k - 1] * (tm - tb.t0[hemi * kmax + k - 1]) / tb.stat[hemi * kmax + k - 1];
+            const double altp = tb.ep[k + 1] * (tp - t0[k + 1]) / stat[k + 1];
+            const double altm = tb.ep[k - 1] * (tm - t0[k - 1]) / stat[k - 1];
             if (MODE == 0) {
                 q = altp - altm;
             } else {
@@ -122,8 +124,7 @@ nh18_finish_kernel(int nlon, int nlat, int kmax, const double* __restrict__ avor
     }
 }
 
-static int build_qgpv_tables(int nlat, int kmax, bool deg_lat, const double* height, const double* ts0,
-                             const double* tn0, const double* stats, const double* statn, double aa, double omega,
+static int build_qgpv_tables(int nlat, int kmax, bool deg_lat, const double* height, double aa, double omega,
                              double hh, std::vector<double>& h) {
     const double pi = host_pi();
     const double dphi = pi / (double)(nlat - 1);
@@ -134,9 +135,9 @@ static int build_qgpv_tables(int nlat, int kmax, bool deg_lat, const double* hei
         }
         return -0.5 * pi + pi * (double)jm1 / (double)(nlat - 1);  // compute_qgpv_direct_inv.f90:30-32
     };
-    h.assign((size_t)4 * nlat + 3 * kmax + 4 * kmax, 0.0);
+    h.assign((size_t)4 * nlat + 3 * kmax, 0.0);
     double *av1 = h.data(), *den = av1 + nlat, *cosp = den + nlat, *cosm = cosp + nlat;
-    double *ep = cosm + nlat, *e0 = ep + kmax, *hg = e0 + kmax, *t0 = hg + kmax, *st = t0 + 2 * kmax;
+    double *ep = cosm + nlat, *e0 = ep + kmax, *hg = e0 + kmax;
     for (int j = 1; j <= nlat; ++j) {
         const double phi0 = lat(j - 1), phim = lat(j - 2), phip = lat(j);
         av1[j - 1] = 2. * omega * std::sin(phi0);
@@ -148,8 +149,6 @@ static int build_qgpv_tables(int nlat, int kmax, bool deg_lat, const double* hei
         ep[k] = std::exp(-height[k] / hh);
         e0[k] = std::exp(height[k] / hh);
         hg[k] = height[k];
-        t0[k] = ts0[k]; t0[kmax + k] = tn0[k];
-        st[k] = stats[k]; st[kmax + k] = statn[k];
     }
     return 0;
 }
@@ -157,7 +156,7 @@ static int build_qgpv_tables(int nlat, int kmax, bool deg_lat, const double* hei
 static QgpvTables view_tables(const double* d, int nlat, int kmax) {
     QgpvTables t;
     t.av1 = d; t.den = d + nlat; t.cosp = d + 2 * nlat; t.cosm = d + 3 * nlat;
-    t.ep = d + 4 * nlat; t.e0 = t.ep + kmax; t.height = t.e0 + kmax; t.t0 = t.height + kmax; t.stat = t.t0 + 2 * kmax;
+    t.ep = d + 4 * nlat; t.e0 = t.ep + kmax; t.height = t.e0 + kmax;
     return t;
 }
 
@@ -171,16 +170,17 @@ static int pick_kchunk(int nlon, int nlat, int kmax, int batch) {
 
 // Shared driver: mode 0 = NH18 (global t0/stat), mode 1 = NHN22 (hemispheric, split at row jd).
 int qgpv_launch(int mode, int nlon, int nlat, int kmax, int jd, int batch, const double* u, const double* v,
-                const double* th, const double* d_tables, double* pv, double* avort, cudaStream_t st) {
+                const double* th, const double* d_tables, const double* d_prof, double* pv, double* avort,
+                cudaStream_t st) {
     const QgpvTables tb = view_tables(d_tables, nlat, kmax);
     const size_t bstride = (size_t)nlon * nlat * kmax;
     const int kchunk = pick_kchunk(nlon, nlat, kmax, batch);
     dim3 block(32, 8);
     dim3 grid(ceil_div(nlon, 32), ceil_div(nlat, 8), ceil_div(kmax, kchunk) * batch);
     if (mode == 0)
-        avort_pv_kernel<0><<<grid, block, 0, st>>>(nlon, nlat, kmax, jd, kchunk, u, v, th, tb, avort, pv, bstride);
+        avort_pv_kernel<0><<<grid, block, 0, st>>>(nlon, nlat, kmax, jd, kchunk, u, v, th, tb, d_prof, avort, pv, bstride);
     else
-        avort_pv_kernel<1><<<grid, block, 0, st>>>(nlon, nlat, kmax, jd, kchunk, u, v, th, tb, avort, pv, bstride);
+        avort_pv_kernel<1><<<grid, block, 0, st>>>(nlon, nlat, kmax, jd, kchunk, u, v, th, tb, d_prof, avort, pv, bstride);
     FALWA_LAUNCH_CHECK();
     polar_rows_kernel<<<dim3(kmax, 2, batch), 256, 0, st>>>(nlon, nlat, kmax, mode == 1, avort, pv, bstride);
     FALWA_LAUNCH_CHECK();
@@ -191,24 +191,26 @@ int qgpv_launch(int mode, int nlon, int nlat, int kmax, int jd, int batch, const
     return 0;
 }
 
-int qgpv_tables_host(int mode, int nlat, int kmax, const double* height, const double* ts0, const double* tn0,
-                     const double* stats, const double* statn, double aa, double omega, double hh,
+int qgpv_tables_host(int mode, int nlat, int kmax, const double* height, double aa, double omega, double hh,
                      std::vector<double>& h) {
-    return build_qgpv_tables(nlat, kmax, mode == 0, height, ts0, tn0, stats, statn, aa, omega, hh, h);
+    return build_qgpv_tables(nlat, kmax, mode == 0, height, aa, omega, hh, h);
 }
 
+size_t qgpv_tables_size(int nlat, int kmax) { return (size_t)4 * nlat + 3 * kmax; }
+
 // ---------------------------------------------------------------------------------------------
-// Vertical interpolation plev -> uniform pseudo-height (scipy interp1d "linear", extrapolating):
-//   idx = clip(searchsorted(x, x_new), 1, n-1); slope = (y_hi-y_lo)/(x_hi-x_lo);
-//   y = slope*(x_new-x_lo) + y_lo.
+// Vertical interpolation plev -> uniform pseudo-height, scipy.interpolate.interp1d(kind="linear",
+// fill_value="extrapolate") as implemented by the SciPy of this image (1.18, _call_linear):
+//   idx = clip(searchsorted(x, x_new), 1, n-1); lo = idx-1; hi = idx
+//   y = ((x_new-x_lo)/(x_hi-x_lo)) * y_hi + ((x_hi-x_new)/(x_hi-x_lo)) * y_lo
 // T is turned into potential temperature with the per-level factor exp(kappa z_p / H) first
 // (oopinterface.py:127-128).  One thread per (lon, lat) column; each input level is read once.
-// Tables (host): lo[kmax] (as doubles), dx[kmax] = x_hi-x_lo, dxn[kmax] = x_new-x_lo, fac[nlev].
+// Tables (host): lo[kmax], whi[kmax], wlo[kmax], fac[nlev].
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 interp_kernel(int nlon, int nlat, int nlev, int kmax, const double* __restrict__ uin,
               const double* __restrict__ vin, const double* __restrict__ tin, const int* __restrict__ lo,
-              const double* __restrict__ dx, const double* __restrict__ dxn, const double* __restrict__ fac,
+              const double* __restrict__ whi, const double* __restrict__ wlo, const double* __restrict__ fac,
               double* __restrict__ uo, double* __restrict__ vo, double* __restrict__ to, size_t in_stride,
               size_t out_stride) {
     const size_t plane = (size_t)nlon * nlat;
@@ -217,12 +219,12 @@ interp_kernel(int nlon, int nlat, int nlev, int kmax, const double* __restrict__
     const int b = blockIdx.y;
     uin += (size_t)b * in_stride; vin += (size_t)b * in_stride; tin += (size_t)b * in_stride;
     uo += (size_t)b * out_stride; vo += (size_t)b * out_stride; to += (size_t)b * out_stride;
-    int cur = -1;
+    int cur = -2;
     double u0 = 0, u1 = 0, v0 = 0, v1 = 0, t0 = 0, t1 = 0;
     for (int k = 0; k < kmax; ++k) {
         const int l = lo[k];
         if (l != cur) {
-            if (l == cur + 1 && cur >= 0) {
+            if (l == cur + 1) {
                 u0 = u1; v0 = v1; t0 = t1;
             } else {
                 u0 = ld_stream(&uin[(size_t)l * plane + col]);
@@ -234,11 +236,10 @@ interp_kernel(int nlon, int nlat, int nlev, int kmax, const double* __restrict__
             t1 = ld_stream(&tin[(size_t)(l + 1) * plane + col]) * fac[l + 1];
             cur = l;
         }
-        const double ddx = dx[k], ddn = dxn[k];
-        const double su = (u1 - u0) / ddx, sv = (v1 - v0) / ddx, stt = (t1 - t0) / ddx;
-        uo[(size_t)k * plane + col] = su * ddn + u0;
-        vo[(size_t)k * plane + col] = sv * ddn + v0;
-        to[(size_t)k * plane + col] = stt * ddn + t0;
+        const double a1 = whi[k], a0 = wlo[k];
+        st_stream(&uo[(size_t)k * plane + col], a1 * u1 + a0 * u0);
+        st_stream(&vo[(size_t)k * plane + col], a1 * v1 + a0 * v0);
+        to[(size_t)k * plane + col] = a1 * t1 + a0 * t0;
     }
 }
 
@@ -275,6 +276,26 @@ theta_hemi_kernel(int nlat, int nlev, int jd, const double* __restrict__ rowmean
     if (threadIdx.x == 0) out[((size_t)b * 2 + hemi) * nlev + l] = s / c;
 }
 
+int interp_launch(int nlon, int nlat, int nlev, int kmax, int batch, const double* uin, const double* vin,
+                  const double* tin, const int* lo, const double* whi, const double* wlo, const double* fac, double* uo,
+                  double* vo, double* to, cudaStream_t st) {
+    const size_t plane = (size_t)nlon * nlat;
+    interp_kernel<<<dim3(ceil_div((long long)plane, 256), batch), 256, 0, st>>>(
+        nlon, nlat, nlev, kmax, uin, vin, tin, lo, whi, wlo, fac, uo, vo, to, plane * nlev, plane * kmax);
+    FALWA_LAUNCH_CHECK();
+    return 0;
+}
+
+int theta_means_launch(int nlon, int nlat, int nlev, int jd, int batch, const double* tin, const double* fac,
+                       const double* clat, double* rowmean, double* out, cudaStream_t st) {
+    theta_rowmean_kernel<<<dim3(nlat, nlev, batch), 256, 0, st>>>(nlon, nlat, nlev, tin, fac, clat, rowmean,
+                                                                  (size_t)nlon * nlat * nlev);
+    FALWA_LAUNCH_CHECK();
+    theta_hemi_kernel<<<dim3(nlev, 2, batch), 128, 0, st>>>(nlat, nlev, jd, rowmean, clat, out);
+    FALWA_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace falwa
 
 using namespace falwa;
@@ -289,11 +310,13 @@ extern "C" int falwa_b200_compute_qgpv(int nlon, int nlat, int kmax, const doubl
     if (nlon < 3 || nlat < 3 || kmax < 3) return FALWA_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<double> h;
-    qgpv_tables_host(0, nlat, kmax, height_host, t0_host, t0_host, stat_host, stat_host, aa, omega, hh, h);
+    qgpv_tables_host(0, nlat, kmax, height_host, aa, omega, hh, h);
+    const size_t o_prof = h.size();
+    for (const double* src : {t0_host, t0_host, stat_host, stat_host}) h.insert(h.end(), src, src + kmax);
     DeviceTable tb;
     int rc = tb.upload(h, st);
     if (rc) return rc;
-    return qgpv_launch(0, nlon, nlat, kmax, nlat, 1, ut, vt, theta, tb.d, pv, avort, st);
+    return qgpv_launch(0, nlon, nlat, kmax, nlat, 1, ut, vt, theta, tb.d, tb.d + o_prof, pv, avort, st);
 }
 
 extern "C" int falwa_b200_compute_qgpv_direct_inv(int nlon, int nlat, int kmax, int jd, const double* uq,
@@ -308,9 +331,11 @@ extern "C" int falwa_b200_compute_qgpv_direct_inv(int nlon, int nlat, int kmax, 
     if (nlon < 3 || nlat < 3 || kmax < 3 || jd < 0 || jd > nlat) return FALWA_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<double> h;
-    qgpv_tables_host(1, nlat, kmax, height_host, ts0_host, tn0_host, stats_host, statn_host, aa, omega, hh, h);
+    qgpv_tables_host(1, nlat, kmax, height_host, aa, omega, hh, h);
+    const size_t o_prof = h.size();
+    for (const double* src : {ts0_host, tn0_host, stats_host, statn_host}) h.insert(h.end(), src, src + kmax);
     DeviceTable tb;
     int rc = tb.upload(h, st);
     if (rc) return rc;
-    return qgpv_launch(1, nlon, nlat, kmax, jd, 1, uq, vq, tq, tb.d, pv, avort, st);
+    return qgpv_launch(1, nlon, nlat, kmax, jd, 1, uq, vq, tq, tb.d, tb.d + o_prof, pv, avort, st);
 }

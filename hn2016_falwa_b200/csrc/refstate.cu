@@ -29,6 +29,15 @@ __global__ void __launch_bounds__(256)
 zonal_stats_kernel(int nlon, int nlat, int kmax, const double* __restrict__ f0, const double* __restrict__ f1,
                    const double* __restrict__ f2, const double* __restrict__ f3, double* __restrict__ zm,
                    unsigned long long* __restrict__ ext, int ext_mask) {
+    {   // batch: blockIdx.z selects the snapshot (contiguous fields / zm / ext per snapshot)
+        const size_t fs = (size_t)blockIdx.z * nlon * nlat * kmax;
+        if (f0) f0 += fs;
+        if (f1) f1 += fs;
+        if (f2) f2 += fs;
+        if (f3) f3 += fs;
+        zm += (size_t)blockIdx.z * 3 * kmax * nlat;
+        if (ext) ext += (size_t)blockIdx.z * 2 * kmax * 2;
+    }
     // f0..f2: fields whose zonal mean is wanted (may be null); extrema are taken of f0 (ext_mask&1)
     // and f3 (ext_mask&2).
     __shared__ double red[33];
@@ -252,7 +261,8 @@ struct SorArgs {
 };
 
 __global__ void __launch_bounds__(1024)
-sor_kernel(SorArgs p) {
+sor_kernel(const SorArgs* __restrict__ probs) {
+    const SorArgs p = probs[blockIdx.x];
     extern __shared__ double sh[];
     __shared__ double red[33];
     __shared__ double s_anormf;
@@ -474,22 +484,32 @@ struct SweepArgs {
     double u1off;
 };
 
+// p_{k+1} = S_k p_k + T_k  (upward_sweep.f90:19-34); thread-per-row keeps the reference's summation order
 __global__ void __launch_bounds__(1024)
-upward_sweep_kernel(SweepArgs p) {
-    const int n = p.n, jd = p.jd, nd = p.nd, kmax = p.kmax;
+sweep_matvec_kernel(int n, int kmax, const double* __restrict__ sjk, const double* __restrict__ tjk,
+                    double* __restrict__ pjk) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < n; i += nt) p.pjk[i] = 0.0;
+    for (int i = tid; i < n; i += nt) pjk[i] = 0.0;
     __syncthreads();
-    for (int k = 0; k < kmax - 1; ++k) {  // p_{k+1} = S_k p_k + T_k
-        const double* S = p.sjk + (size_t)k * n * n;
-        const double* pk = p.pjk + (size_t)k * n;
+    for (int k = 0; k < kmax - 1; ++k) {
+        const double* S = sjk + (size_t)k * n * n;
+        const double* pk = pjk + (size_t)k * n;
         for (int i = tid; i < n; i += nt) {
             double y = 0.0;
             for (int kk = 0; kk < n; ++kk) y = y + S[(size_t)kk * n + i] * pk[kk];
-            p.pjk[(size_t)(k + 1) * n + i] = y + p.tjk[(size_t)k * n + i];
+            pjk[(size_t)(k + 1) * n + i] = y + tjk[(size_t)k * n + i];
         }
         __syncthreads();
     }
+}
+
+// upward_sweep.f90:36-91 given p_k: u, corner values, /cos, tref marching, qref * sin(lat).
+// One CTA per (snapshot, hemisphere) problem.
+__global__ void __launch_bounds__(512)
+sweep_post_kernel(const SweepArgs* __restrict__ probs) {
+    const SweepArgs p = probs[blockIdx.x];
+    const int n = p.n, jd = p.jd, nd = p.nd, kmax = p.kmax;
+    const int tid = threadIdx.x, nt = blockDim.x;
     // recover u, corners, /cos, extrapolated last row (:36-57)
     for (int t = tid; t < jd * kmax; t += nt) {
         const int k = t / jd, j = t % jd;  // 0-based
@@ -678,7 +698,10 @@ extern "C" int falwa_b200_compute_reference_states(const double* pv, const doubl
     p.u_in_smem = need <= 200 * 1024;
     const size_t smem = p.u_in_smem ? need : 0;
     FALWA_CUDA_TRY(cudaFuncSetAttribute(sor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-    sor_kernel<<<1, 1024, smem, st>>>(p);
+    DeviceScratch<SorArgs> dp;
+    if ((rc = dp.alloc(1, st))) return rc;
+    FALWA_CUDA_TRY(cudaMemcpyAsync(dp.d, &p, sizeof(SorArgs), cudaMemcpyHostToDevice, st));
+    sor_kernel<<<1, 1024, smem, st>>>(dp.d);
     FALWA_LAUNCH_CHECK();
     FALWA_CUDA_TRY(cudaMemcpyAsync(num_of_iter_host, nit.d, sizeof(int), cudaMemcpyDeviceToHost, st));
     FALWA_CUDA_TRY(cudaStreamSynchronize(st));
@@ -843,7 +866,12 @@ extern "C" int falwa_b200_upward_sweep(int jmax, int kmax, int nd, int jb, int j
     p.tref = tref; p.qref = qref; p.u = u; p.pjk = pjk.d;
     p.u1top = 0.0; p.u1off = om * a * std::cos(dp * (double)jb);
     FALWA_CUDA_TRY(cudaMemsetAsync(tref, 0, sizeof(double) * (size_t)jd * kmax, st));
-    upward_sweep_kernel<<<1, 1024, 0, st>>>(p);
+    sweep_matvec_kernel<<<1, 1024, 0, st>>>(n, kmax, sjk, tjk, pjk.d);
+    FALWA_LAUNCH_CHECK();
+    DeviceScratch<SweepArgs> dprob;
+    if ((rc = dprob.alloc(1, st))) return rc;
+    FALWA_CUDA_TRY(cudaMemcpyAsync(dprob.d, &p, sizeof(SweepArgs), cudaMemcpyHostToDevice, st));
+    sweep_post_kernel<<<1, 512, 0, st>>>(dprob.d);
     FALWA_LAUNCH_CHECK();
     return 0;
 }

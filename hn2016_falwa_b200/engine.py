@@ -1,0 +1,208 @@
+"""Batched, device-resident QGField engine: the host side of Section B of include/falwa_b200.h.
+
+One ``QGBatch`` holds B independent snapshots on one GPU (fields [B][level][lat][lon], fp64) and runs the
+three stages of the reference pipeline on all of them per call:
+
+    interpolate_fields  ->  compute_reference_states  ->  compute_lwa_and_barotropic_fluxes
+    (oopinterface.py:467-535)  (:550-615, :1604-1674, :1774-1888)   (:716-982)
+
+``QGFieldNH18`` / ``QGFieldNHN22`` (oopinterface.py of this package) are a batch of one; ``QGDataset`` shards
+its snapshots over batches (and over GPUs, one process per GPU).  PyTorch is used for device memory, streams
+and host<->device copies only; every number is produced by the kernels of libfalwa_b200.so, except the
+static-stability smoothing spline (SciPy FITPACK on 2 x nlev numbers per snapshot), which is the
+same host call the reference makes.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+from scipy.interpolate import UnivariateSpline
+
+from . import _lib
+from ._lib import c_d, c_dp, c_i, check, dptr, hptr, stream_ptr
+from .constant import P_GROUND
+
+OUT2D = {  # slot order of falwa_b200.h (enum FALWA_OUT2D_*)
+    "astar1_baro": 0, "astar2_baro": 1, "lwa_baro": 2, "adv_flux_f1": 3, "adv_flux_f2": 4, "adv_flux_f3": 5,
+    "ep2baro": 6, "ep3baro": 7, "meridional_heat_flux": 8, "ncforce_baro": 9, "u_baro": 10,
+    "convergence_zonal_advective_flux": 11, "divergence_eddy_momentum_flux": 12, "flux_vector_lambda_baro": 13,
+    "flux_vector_phi_baro": 14}
+N_OUT2D = 15
+
+_registered = False
+
+
+def _register():
+    global _registered
+    if _registered:
+        return
+    _lib.register("falwa_b200_plan_create", [c_dp] + [c_i] * 8 + [c_dp] * 4 + [c_d] * 9)
+    _lib.register("falwa_b200_plan_destroy", [c_dp])
+    _lib.register("falwa_b200_theta_hemispheric_means", [c_dp, c_i, c_dp, c_dp, c_dp])
+    _lib.register("falwa_b200_interpolate_fields", [c_dp, c_i, c_dp, c_dp, c_dp, c_i, c_dp] + [c_dp] * 5 + [c_dp])
+    _lib.register("falwa_b200_reference_states", [c_dp, c_i] + [c_dp] * 5 + [c_i] + [c_dp] * 4 + [c_dp, c_dp])
+    _lib.register("falwa_b200_lwa_and_barotropic_fluxes",
+                  [c_dp, c_i] + [c_dp] * 9 + [c_i, c_dp, c_dp, c_i, c_dp])
+    _registered = True
+
+
+class Plan:
+    """Grid-dependent device tables (falwa_b200_plan_create)."""
+
+    def __init__(self, kind, xlon, ylat, plev, kmax, dz, jb, npart, maxit, tol, rjac, scale_height, cp,
+                 dry_gas_constant, omega, planet_radius, on_height_grid=False):
+        _lib.require_cuda()
+        _register()
+        self.lib = _lib.load()
+        self.kind = kind
+        self.nlon, self.nlat, self.nlev, self.kmax = int(xlon.size), int(ylat.size), int(plev.size), int(kmax)
+        self.jb = int(jb) if kind == 1 else 0
+        self.nd = self.nlat // 2 + 1
+        self.jd = self.nd - self.jb
+        self.dz, self.h = float(dz), float(scale_height)
+        self.height = np.array([i * dz for i in range(kmax)])                      # oopinterface.py:121
+        self.plev_to_height = -scale_height * np.log(np.asarray(plev, float) / P_GROUND)   # :120
+        self.theta_factor = np.exp(dry_gas_constant / cp * self.plev_to_height / scale_height)  # :127-128
+        self.clat = np.abs(np.cos(np.deg2rad(ylat)))                               # :342
+        self.sinlat = np.sin(np.deg2rad(ylat))                                     # data_storage.py:175-176
+        self.prefactor = sum([math.exp(-k * dz / scale_height) * dz for k in range(1, kmax - 1)])  # :270
+        if on_height_grid:  # data_on_evenly_spaced_pseudoheight_grid: no interpolation tables needed
+            p2h = np.ascontiguousarray(self.height)
+        else:
+            p2h = np.ascontiguousarray(self.plev_to_height)
+        self._keep = (p2h, np.ascontiguousarray(self.theta_factor), np.ascontiguousarray(self.clat),
+                      np.ascontiguousarray(self.sinlat))
+        handle = ctypes.c_void_p()
+        check(self.lib.falwa_b200_plan_create(
+            ctypes.cast(ctypes.byref(handle), ctypes.c_void_p), kind, self.nlon, self.nlat,
+            p2h.size, self.kmax, self.jb, int(npart) if npart is not None else 0, int(maxit), hptr(self._keep[0]),
+            hptr(self._keep[1]), hptr(self._keep[2]), hptr(self._keep[3]), float(planet_radius), float(omega),
+            float(dz), float(scale_height), float(dry_gas_constant), float(cp), float(tol), float(rjac),
+            float(self.prefactor)), "plan_create")
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.falwa_b200_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:  # interpreter shutdown
+            pass
+
+
+class QGBatch:
+    """B snapshots on the current CUDA device.  Inputs: u, v, t as [B][nlev][nlat][nlon] float64
+    (NumPy -> copied from pinned memory, or CUDA tensors -> used as is), latitude ascending, pressure descending."""
+
+    def __init__(self, plan, u, v, t, on_height_grid=False, northern_hemisphere_results_only=False):
+        self.plan = plan
+        self.lib = plan.lib
+        self.on_height_grid = on_height_grid
+        self.north_only = int(bool(northern_hemisphere_results_only))
+        self.u_in, self.v_in, self.t_in = (self._to_device(x) for x in (u, v, t))
+        self.B = int(self.u_in.shape[0])
+        exp = (self.B, plan.nlev if not on_height_grid else plan.kmax, plan.nlat, plan.nlon)
+        for name, x in (("u", self.u_in), ("v", self.v_in), ("t", self.t_in)):
+            if tuple(x.shape) != exp:
+                raise TypeError(f"Incorrect dimension of {name}_field. Expected dimension: {exp}")
+        self.profiles = None          # host [B][4][kmax]: t0_s, t0_n, stat_s, stat_n
+        self.u = self.v = self.theta = self.avort = self.qgpv = None
+        self.qref_st = self.qref_cu = self.uref = self.ptref = None
+        self.num_of_iter = None
+        self.lwa = self.out2d = None
+
+    @staticmethod
+    def _to_device(x):
+        if isinstance(x, torch.Tensor):
+            assert x.is_cuda and x.dtype == torch.float64
+            return x.contiguous()
+        a = np.ascontiguousarray(x, dtype=np.float64)
+        return torch.from_numpy(a).pin_memory().cuda(non_blocking=True)
+
+    def _new(self, *shape):
+        return torch.empty(shape, dtype=torch.float64, device=self.u_in.device)
+
+    # ---- stage 1 -------------------------------------------------------------------------------
+    def hemispheric_theta_means(self):
+        """[B][2][nlev] cos-weighted hemispheric means of potential temperature (device reduction)."""
+        p = self.plan
+        means = self._new(self.B, 2, self.t_in.shape[1])
+        check(self.lib.falwa_b200_theta_hemispheric_means(p.handle, self.B, dptr(self.t_in), dptr(means),
+                                                          stream_ptr()), "theta_hemispheric_means")
+        return means.cpu().numpy()
+
+    def static_stability_profiles(self):
+        """oopinterface.py:241-261 and :530-531: smoothing splines of the hemispheric-mean theta(z) and their
+        derivatives, evaluated on the height grid.  Returns [B][4][kmax] (t0_s, t0_n, stat_s, stat_n)."""
+        p = self.plan
+        means = self.hemispheric_theta_means()
+        x = p.height if self.on_height_grid else p.plev_to_height
+        prof = np.empty((self.B, 4, p.kmax))
+        for b in range(self.B):
+            us = UnivariateSpline(x=x, y=means[b, 0])
+            un = UnivariateSpline(x=x, y=means[b, 1])
+            prof[b, 0], prof[b, 1] = us(p.height), un(p.height)
+            prof[b, 2], prof[b, 3] = us.derivative()(p.height), un.derivative()(p.height)
+        return prof
+
+    def interpolate_fields(self):
+        p = self.plan
+        prof = self.static_stability_profiles()
+        if p.kind == 0:  # NH18 uses the average of the two hemispheres everywhere (oopinterface.py:1567-1580)
+            t0 = 0.5 * (prof[:, 0] + prof[:, 1])
+            st = 0.5 * (prof[:, 2] + prof[:, 3])
+            prof = np.stack([t0, t0, st, st], axis=1)
+        self.profiles = np.ascontiguousarray(prof)
+        shape = (self.B, p.kmax, p.nlat, p.nlon)
+        if self.on_height_grid:
+            self.u, self.v = self.u_in, self.v_in
+            fac = torch.from_numpy(p.theta_factor).to(self.t_in.device)
+            self.theta = (self.t_in * fac[None, :, None, None]).contiguous()
+        else:
+            self.u, self.v, self.theta = self._new(*shape), self._new(*shape), self._new(*shape)
+        self.avort, self.qgpv = self._new(*shape), self._new(*shape)
+        check(self.lib.falwa_b200_interpolate_fields(
+            p.handle, self.B, dptr(self.u_in), dptr(self.v_in), dptr(self.t_in), int(self.on_height_grid),
+            hptr(self.profiles), dptr(self.u), dptr(self.v), dptr(self.theta), dptr(self.avort), dptr(self.qgpv),
+            stream_ptr()), "interpolate_fields")
+
+    # ---- stage 2 -------------------------------------------------------------------------------
+    def compute_reference_states(self):
+        p = self.plan
+        if self.qgpv is None:
+            raise ValueError("QGField.interpolate_fields has to be called before QGField.compute_reference_states.")
+        shape = (self.B, p.kmax, p.nlat)
+        self.qref_st, self.qref_cu, self.uref, self.ptref = (self._new(*shape) for _ in range(4))
+        nit = np.zeros((self.B, 2), dtype=np.int32)
+        check(self.lib.falwa_b200_reference_states(
+            p.handle, self.B, dptr(self.qgpv), dptr(self.u), dptr(self.theta), dptr(self.avort), hptr(self.profiles),
+            self.north_only, dptr(self.qref_st), dptr(self.qref_cu), dptr(self.uref), dptr(self.ptref),
+            nit.ctypes.data_as(ctypes.c_void_p), stream_ptr()), "reference_states")
+        self.num_of_iter = nit
+
+    # ---- stage 3 -------------------------------------------------------------------------------
+    def compute_lwa_and_barotropic_fluxes(self, ncforce=None, method=0):
+        p = self.plan
+        if self.qref_cu is None:
+            raise ValueError("Reference states have not been computed yet.")
+        nc = None
+        if ncforce is not None:
+            nc = self._to_device(ncforce)
+            assert tuple(nc.shape) == tuple(self.theta.shape)
+        self.lwa = self._new(self.B, p.kmax, p.nlat, p.nlon)
+        self.out2d = self._new(self.B, N_OUT2D, p.nlat, p.nlon)
+        check(self.lib.falwa_b200_lwa_and_barotropic_fluxes(
+            p.handle, self.B, dptr(self.qgpv), dptr(self.u), dptr(self.v), dptr(self.theta), dptr(nc),
+            hptr(self.profiles), dptr(self.qref_cu), dptr(self.uref), dptr(self.ptref), self.north_only,
+            dptr(self.lwa), dptr(self.out2d), int(method), stream_ptr()), "lwa_and_barotropic_fluxes")
+
+    def out(self, name):
+        """2-D output `name` as a [B][nlat][nlon] device view."""
+        return self.out2d[:, OUT2D[name]]
+
+    def run(self, ncforce=None, method=0):
+        self.interpolate_fields()
+        self.compute_reference_states()
+        self.compute_lwa_and_barotropic_fluxes(ncforce=ncforce, method=method)
+        return self

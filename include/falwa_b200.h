@@ -125,6 +125,76 @@ int falwa_b200_compute_lwa_only_nhn22(const double* pv, const double* uu, const 
                                       double* astarbaro, double* ubaro, double* astar1, double* astar2,
                                       int method, void* stream);
 
+/* ======================================================================================
+ * Section B — fused, batched, device-resident pipeline (what QGFieldNH18 / QGFieldNHN22 /
+ * QGDataset of hn2016_falwa_b200 call).  A plan holds the grid-dependent tables on the device.
+ * All 3-D fields are [batch][level][lat south->north][lon]; reference-state profiles are
+ * [batch][kmax][nlat]; the southern hemisphere is handled by index arithmetic and sign factors
+ * instead of the reference's flipped/negated copies (oopinterface.py:764-792, :1794-1806).
+ * ====================================================================================== */
+typedef struct falwa_plan falwa_plan;
+
+/* kind: 0 = QGFieldNH18 (SOR reference state, jb forced to 0), 1 = QGFieldNHN22 (direct inversion).
+ * Host tables supplied by the caller so that they are bit-identical to the reference's NumPy values:
+ *   plev_to_height_host[nlev] = -H log(plev/1000)        (oopinterface.py:120)
+ *   theta_factor_host[nlev]   = exp(R/cp * z_p / H)       (oopinterface.py:127-128)
+ *   clat_host[nlat]           = |cos(deg2rad(ylat))|      (oopinterface.py:342)
+ *   sinlat_host[nlat]         = sin(deg2rad(ylat))        (data_storage.py:175-176)
+ * npart <= 0 means nlat.  prefactor: oopinterface.py:263-270. */
+int falwa_b200_plan_create(falwa_plan** plan, int kind, int nlon, int nlat, int nlev, int kmax, int jb,
+                           int npart, int maxit, const double* plev_to_height_host,
+                           const double* theta_factor_host, const double* clat_host,
+                           const double* sinlat_host, double a, double omega, double dz, double h, double rr,
+                           double cp, double tol, double rjac, double prefactor);
+int falwa_b200_plan_destroy(falwa_plan* plan);
+
+/* Hemispheric cos-weighted mean potential temperature on the input pressure levels — the input of the
+ * host-side static-stability spline (replaces the NumPy reductions of oopinterface.py:250-256).
+ * t_in: temperature [batch][nlev][nlat][nlon]; means: [batch][2][nlev] (0 = south, 1 = north). */
+int falwa_b200_theta_hemispheric_means(const falwa_plan* plan, int batch, const double* t_in, double* means,
+                                       void* stream);
+
+/* interpolate_fields (oopinterface.py:467-535): vertical interpolation of u, v, theta (theta = T * factor)
+ * onto the uniform pseudo-height grid, absolute vorticity and QGPV.
+ * profiles_host [batch][4][kmax] = t0_s, t0_n, stat_s, stat_n evaluated at the height grid (for NH18 pass
+ * the hemispheric averages in both slots).  If already_on_height_grid != 0 the interpolation is skipped
+ * and u, v, theta must already hold the fields on the height grid. */
+int falwa_b200_interpolate_fields(const falwa_plan* plan, int batch, const double* u_in, const double* v_in,
+                                  const double* t_in, int already_on_height_grid, const double* profiles_host,
+                                  double* u, double* v, double* theta, double* avort, double* qgpv,
+                                  void* stream);
+
+/* compute_reference_states (oopinterface.py:550-615, :1604-1674, :1774-1888), both hemispheres, merged
+ * into global-latitude storage like data_storage.py:32-62 (north first, south second).
+ *   qref_st: qref as the reference stores it (qref/f); qref_cu: qref in s^-1 (data_storage.py:170-179).
+ *   num_of_iter_host [batch][2]: NH18 SOR iteration counts (north, south); 0 for NHN22.
+ * north_only != 0 computes the northern hemisphere only.  Synchronises the stream before returning. */
+int falwa_b200_reference_states(const falwa_plan* plan, int batch, const double* qgpv, const double* u,
+                                const double* theta, const double* avort, const double* profiles_host,
+                                int north_only, double* qref_st, double* qref_cu, double* uref_st,
+                                double* ptref_st, int* num_of_iter_host, void* stream);
+
+/* compute_lwa_and_barotropic_fluxes (oopinterface.py:716-982), both hemispheres.
+ *   lwa   [batch][kmax][nlat][nlon]
+ *   out2d [batch][FALWA_OUT2D_COUNT][nlat][nlon], slots below.
+ * ncforce may be NULL (zeros).  method: 0 = automatic, 1 = O(nd^2) brute-force LWA. */
+enum {
+    FALWA_OUT2D_ASTAR1_BARO = 0, FALWA_OUT2D_ASTAR2_BARO = 1, FALWA_OUT2D_LWA_BARO = 2,
+    FALWA_OUT2D_ADV_FLUX_F1 = 3, FALWA_OUT2D_ADV_FLUX_F2 = 4, FALWA_OUT2D_ADV_FLUX_F3 = 5,
+    FALWA_OUT2D_EP2_BARO = 6, FALWA_OUT2D_EP3_BARO = 7, FALWA_OUT2D_MERIDIONAL_HEAT_FLUX = 8,
+    FALWA_OUT2D_NCFORCE_BARO = 9, FALWA_OUT2D_U_BARO = 10, FALWA_OUT2D_CONVERGENCE_ZONAL_ADVECTIVE_FLUX = 11,
+    FALWA_OUT2D_DIVERGENCE_EDDY_MOMENTUM_FLUX = 12, FALWA_OUT2D_FLUX_VECTOR_LAMBDA_BARO = 13,
+    FALWA_OUT2D_FLUX_VECTOR_PHI_BARO = 14, FALWA_OUT2D_COUNT = 15
+};
+int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* plan, int batch, const double* qgpv, const double* u,
+                                         const double* v, const double* theta, const double* ncforce,
+                                         const double* profiles_host, const double* qref_cu,
+                                         const double* uref_st, const double* ptref_st, int north_only,
+                                         double* lwa, double* out2d, int method, void* stream);
+
+/* Host-only test hook: eigen-decomposition of a symmetric tridiagonal matrix (used by the NHN22 solve). */
+int falwa_b200_debug_symtridiag_eig(int m, double* d, const double* e, double* z);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,132 @@
+"""GPU parity tests of the product path — QGFieldNH18 / QGFieldNHN22 (device-resident, Section B of the C ABI)
+against the CPU oracle pipeline, on the reference repo's ERA-Interim snapshot (BASELINE.json configs 1, 2) and a
+seeded synthetic snapshot.  rtol 1e-8 as stated by BASELINE.json's north_star; the atol of each field is 1e-9 of
+that field's maximum magnitude unless a tighter one is given (values that are differences of large sums)."""
+import numpy as np
+import pytest
+
+from oracle import pipeline, testdata
+from tests.parity import compare
+
+pytestmark = pytest.mark.gpu
+
+TOL = dict(qgpv=(1e-10, 1e-17), interpolated_u=(1e-13, 1e-13), interpolated_v=(1e-13, 1e-13),
+           interpolated_theta=(1e-13, 0.0), ptref=(1e-9, 0.0))
+
+
+def _inputs(name):
+    if name == "era":
+        return testdata.load_era_snapshot()
+    return testdata.synthetic_snapshot(nlon=96, nlat=49, seed=3)
+
+
+@pytest.fixture(scope="module", params=["era", "synthetic"])
+def case(request):
+    return request.param, _inputs(request.param)
+
+
+def _cls(kind):
+    from hn2016_falwa_b200.oopinterface import QGFieldNH18, QGFieldNHN22
+    return QGFieldNH18 if kind == "nh18" else QGFieldNHN22
+
+
+def _check_all(tag, f, want):
+    for name in pipeline.USER_FIELDS:
+        rtol, atol = TOL.get(name, (1e-8, 1e-9 * float(np.abs(want[name]).max())))
+        compare(f"{tag}/{name}", getattr(f, name), want[name], rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("kind", ["nh18", "nhn22"])
+def test_qgfield_pipeline_matches_oracle(case, kind):
+    name, inputs = case
+    want = pipeline.run_qgfield(kind, *inputs)
+    f = _cls(kind)(*inputs)
+    tup = f.interpolate_fields()
+    assert tup.QGPV.shape == want["qgpv"].shape
+    ss_want = want["static_stability"]
+    if kind == "nh18":
+        compare(f"{name}/{kind}/static_stability", f.static_stability, ss_want, rtol=1e-9)
+    else:
+        compare(f"{name}/{kind}/static_stability_s", f.static_stability[0], ss_want[0], rtol=1e-9)
+        compare(f"{name}/{kind}/static_stability_n", f.static_stability[1], ss_want[1], rtol=1e-9)
+    ref = f.compute_reference_states()
+    assert ref.Qref.shape == want["qref"].shape
+    out = f.compute_lwa_and_barotropic_fluxes(method=1)
+    assert out.lwa.shape == want["lwa"].shape
+    if kind == "nh18":
+        assert tuple(f._batch.num_of_iter[0]) == tuple(want["num_of_iter"])
+    _check_all(f"{name}/{kind}/product", f, want)
+    # structural assertions of the reference's own tests (tests/test_oopinterface.py:410-452)
+    np.testing.assert_array_equal(f.flux_vector_lambda_baro, f.adv_flux_f1 + f.adv_flux_f2 + f.adv_flux_f3)
+
+
+def test_golden_fixture_nhn22_era():
+    """Product path against the committed fixture generated from the reference's own unmodified Python."""
+    import os
+    g = np.load(os.path.join(testdata.GOLDEN_DIR, "qgfield_nhn22_era_interim.npz"))
+    f = _cls("nhn22")(*testdata.load_era_snapshot())
+    f.interpolate_fields(return_named_tuple=False)
+    f.compute_reference_states(return_named_tuple=False)
+    f.compute_lwa_and_barotropic_fluxes(return_named_tuple=False)
+    stride, levels = int(g["lon_stride"]), list(g["levels_3d"])
+    for name in pipeline.USER_FIELDS:
+        a = np.asarray(getattr(f, name))
+        a = a[levels][:, :, ::stride] if a.ndim == 3 else (a[:, ::stride] if a.shape[-1] > 200 else a)
+        rtol, atol = TOL.get(name, (1e-8, 1e-9 * float(np.abs(g[name]).max())))
+        compare(f"golden/nhn22/{name}", a, g[name], rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("kind", ["nh18", "nhn22"])
+def test_batched_equals_single(kind):
+    """Config 4 in miniature: a batch of snapshots through the engine == each snapshot on its own."""
+    from hn2016_falwa_b200 import engine
+    snaps = [testdata.synthetic_snapshot(nlon=96, nlat=49, seed=11, t_index=t) for t in range(3)]
+    xlon, ylat, plev = snaps[0][:3]
+    u = np.stack([s[3] for s in snaps]); v = np.stack([s[4] for s in snaps]); t = np.stack([s[5] for s in snaps])
+    cls = _cls(kind)
+    f0 = cls(xlon, ylat, plev, u[0], v[0], t[0])
+    batch = engine.QGBatch(f0._plan, u, v, t).run(method=1)
+    for b in range(3):
+        f = cls(xlon, ylat, plev, u[b], v[b], t[b])
+        f.interpolate_fields(False); f.compute_reference_states(False); f.compute_lwa_and_barotropic_fluxes(False, method=1)
+        np.testing.assert_array_equal(batch.qgpv[b].cpu().numpy(), f.qgpv)
+        np.testing.assert_allclose(batch.uref[b].cpu().numpy(), f.uref, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(batch.out("lwa_baro")[b].cpu().numpy(), f.lwa_baro, rtol=1e-10, atol=1e-12)
+
+
+def test_northern_hemisphere_results_only_and_errors():
+    inputs = testdata.synthetic_snapshot(nlon=96, nlat=49, seed=3)
+    xlon, ylat, plev, u, v, t = inputs
+    cls = _cls("nh18")
+    f = cls(xlon, ylat, plev, u, v, t, northern_hemisphere_results_only=True)
+    with pytest.raises(ValueError):
+        f.compute_reference_states()            # interpolate_fields not called yet
+    f.interpolate_fields(False)
+    with pytest.raises(ValueError):
+        f.compute_lwa_and_barotropic_fluxes()   # reference states missing
+    q, ur, pt = f.compute_reference_states()
+    assert q.shape == (49, 25) and ur.shape == (49, 25)
+    out = f.compute_lwa_and_barotropic_fluxes()
+    assert out.lwa.shape == (49, 25, 96) and out.lwa_baro.shape == (25, 96)
+    full = cls(xlon, ylat, plev, u, v, t)
+    full.interpolate_fields(False); full.compute_reference_states(False); full.compute_lwa_and_barotropic_fluxes(False)
+    np.testing.assert_allclose(out.lwa_baro[1:], full.lwa_baro[25:], rtol=1e-10, atol=1e-12)
+    # bad kmax raises like the reference (tests/test_oopinterface.py:219-227)
+    with pytest.raises(ValueError):
+        cls(xlon, ylat, plev, u, v, t, kmax=1000)
+    with pytest.raises(TypeError):
+        cls(xlon, ylat[::-1], plev, u, v, t)
+    # non-convergence: raise by default, warn when asked to, then compute_lwa_only works (:195-216)
+    g = cls(xlon, ylat, plev, u, v, t, maxit=5)
+    g.interpolate_fields(False)
+    with pytest.raises(ValueError):
+        g.compute_reference_states()
+    g = cls(xlon, ylat, plev, u, v, t, maxit=5, raise_error_for_nonconvergence=False)
+    g.interpolate_fields(False)
+    with pytest.warns(UserWarning):
+        g.compute_reference_states()
+    assert g.nonconvergent_uref
+    with pytest.raises(ValueError):
+        g.compute_lwa_and_barotropic_fluxes()
+    g.compute_lwa_only()
+    assert g.lwa.shape == (49, 49, 96) and np.isfinite(g.lwa_baro).all()
