@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — snapshots/s of the full QGFieldNHN22 pipeline at ERA5 0.25° (BASELINE.json configs[2]).
+
+One "step" = interpolate_fields + compute_reference_states + compute_lwa_and_barotropic_fluxes (both
+hemispheres, default jb=5, kmax=49) over one batch of synthetic snapshots per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--grid 0.25|1.5] [--impl b200|reference]
+
+  value      snapshots/s with the batch already resident in HBM (CUDA events on the launching stream, barrier +
+             synchronize on both sides, max over ranks).  Inputs of one step are B x 0.92 GB >> 126 MB L2.
+  e2e        the same pipeline through hn2016_falwa_b200.engine.HostStream: pinned HOST inputs, H2D and D2H copies
+             (reference states, the 2-D flux fields and 3-D LWA) inside the timed region.
+  roofline   the kernel with the largest share of the step, timed live with CUDA events inside the library
+             (falwa_b200_profile_*), against MEASURED_PEAKS.json's HBM copy bandwidth.
+  cpu_baseline / --impl reference
+             the CPU oracle (C++/NumPy restatement of the reference's Fortran/Python path; the reference's own
+             Fortran cannot be compiled in this image) on the host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GRIDS = {"0.25": (1440, 721), "1.5": (240, 121)}
+KMAX, NLEV = 49, 37
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU every 100 ms while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.err = index, [], set(), False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    bits = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    bits = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for b, name in self.REASONS.items():
+                    if bits & b:
+                        self.reasons.add(name)
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+            time.sleep(0.1)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": self.err or "no samples"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def make_batch(nlon, nlat, batch, seed):
+    """One seeded synthetic snapshot (hn2016_falwa_b200.synthetic) + zonally rotated copies of it: B distinct
+    snapshots [B][nlev][nlat][nlon] without B x 8 s of host trigonometry."""
+    from hn2016_falwa_b200.synthetic import synthetic_snapshot
+    xlon, ylat, plev, u, v, t = synthetic_snapshot(nlon=nlon, nlat=nlat, seed=seed)
+    shifts = [(b * 37 * nlon) // 360 for b in range(batch)]
+    return xlon, ylat, plev, u, v, t, shifts
+
+
+def algorithmic_bytes(nlon, nlat, nd, kmax, nlev, has_avort=True):
+    """Compulsory bytes per snapshot of each kernel, fp64."""
+    f3, f3in, f2 = 8.0 * nlon * nlat * kmax, 8.0 * nlon * nlat * nlev, 8.0 * nlon * nlat
+    hemi3, hemi2 = 8.0 * nlon * nd * kmax, 8.0 * nlon * nd
+    return {
+        "theta_rowmean_kernel": f3in,
+        "interp_kernel": 3 * f3in + 3 * f3,
+        "avort_pv_kernel": 3 * f3 + 2 * f3,
+        "zonal_stats_kernel": 4 * f3,
+        "area_hist3_kernel": 2 * f3,
+        "fused_flux_bruteforce_kernel": 4 * hemi3 + hemi3 + 11 * hemi2,     # per hemisphere launch
+        "lwa_scan_kernel": 2 * hemi3 + 3 * hemi3,                              # per hemisphere launch
+        "flux_column_kernel": 6 * f3 + f3 + 12 * f2,
+        "baro_post_kernel": 2 * f3 + 8 * f2,
+        "pipeline": 3 * f3in + 4 * f3 + f3 + 12 * f2,                         # 3056.6 MB at 0.25°
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle pipeline on the host cores (reported baseline; see module docstring)
+# ------------------------------------------------------------------------------------------------
+def _cpu_one(args):
+    nlon, nlat, seed, threads = args
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    from oracle import pipeline
+    from hn2016_falwa_b200.synthetic import synthetic_snapshot
+    inp = synthetic_snapshot(nlon=nlon, nlat=nlat, seed=seed)
+    t0 = time.perf_counter()
+    pipeline.run_qgfield("nhn22", *inp)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_rate(nlon, nlat, snapshots, workers):
+    """snapshots/s of the CPU oracle: `workers` processes x (cores // workers) OpenMP threads."""
+    import multiprocessing as mp
+    import subprocess
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    cores = os.cpu_count() or 1
+    workers = max(1, min(workers, cores, snapshots))
+    threads = max(1, cores // workers)
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(workers) as pool:
+        per = pool.map(_cpu_one, [(nlon, nlat, 1234 + i, threads) for i in range(snapshots)])
+    wall = time.perf_counter() - t0
+    # the rate counts only the pipeline time of the slowest worker chain (input synthesis excluded)
+    busy = max(sum(per[i::workers]) for i in range(workers))
+    return snapshots / busy, cores, workers, threads, wall
+
+
+def run_reference(args, nlon, nlat, rank, world):
+    if rank != 0:
+        return
+    workers = 2 if nlon > 1000 else min(8, os.cpu_count() or 1)
+    per_step = workers if nlon > 1000 else 4 * workers
+    for _ in range(min(args.warmup, 0)):
+        pass  # nothing to warm up on the CPU arm beyond building the oracle library
+    rates, t_all = [], time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        rate, cores, workers, threads, wall = cpu_reference_rate(nlon, nlat, per_step, workers)
+        rates.append(rate)
+    value = float(np.mean(rates))
+    sample = f"{per_step} synthetic {nlon}x{nlat} snapshot(s) per step, {workers} processes x {threads} OpenMP threads"
+    line = {
+        "impl": "reference", "metric": "snapshots/sec, QGFieldNHN22 full pipeline", "value": value,
+        "unit": "snapshots/s", "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": args.warmup,
+        "ms_per_step": 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"QGFieldNHN22 {nlon}x{nlat}x{NLEV}plev->kmax{KMAX}, jb=5, both hemispheres",
+                   "snapshots_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": "snapshots/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "snapshots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU oracle (C++/NumPy restatement, fp64); the reference's Fortran cannot be built in this image",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, nlon, nlat, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from hn2016_falwa_b200 import _lib, engine
+    from hn2016_falwa_b200.oopinterface import QGFieldNHN22
+
+    _lib.require_cuda()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = args.batch
+    xlon, ylat, plev, u, v, t, shifts = make_batch(nlon, nlat, B, seed=1234 + rank)
+    # plan via the public class (validates the grid exactly like the reference's constructor)
+    f0 = QGFieldNHN22(xlon, ylat, plev, u, v, t)
+    plan = f0._plan
+    del f0
+    hu, hv, ht = (engine.HostStream.pinned((B,) + u.shape) for _ in range(3))
+    for b, s in enumerate(shifts):
+        hu[b].copy_(torch.from_numpy(np.roll(u, s, axis=-1)))
+        hv[b].copy_(torch.from_numpy(np.roll(v, s, axis=-1)))
+        ht[b].copy_(torch.from_numpy(np.roll(t, s, axis=-1)))
+    du, dv, dt_ = hu.cuda(), hv.cuda(), ht.cuda()
+    torch.cuda.synchronize()
+
+    def step():
+        return engine.QGBatch(plan, du, dv, dt_).run(method=args.method)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.result()
+    tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end: pinned host inputs -> results in pinned host memory ---------------------
+    hs = engine.HostStream(plan, chunk=args.chunk, want_lwa3d=True, method=args.method)
+    out = hs.alloc_outputs(B)
+    hs.run(hu, hv, ht, out=out)   # warm-up (allocator, pinned output pages)
+    barrier()
+    w0 = torch.cuda.Event(enable_timing=True); w1 = torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    w0.record()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        hs.run(hu, hv, ht, out=out)
+    w1.record()
+    barrier()
+    e2e_s = max(time.perf_counter() - t0, w0.elapsed_time(w1) / 1e3)
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * B * e2e_steps / float(te.item()), "unit": "snapshots/s",
+           "h2d_bytes_per_step": int(hs.h2d_bytes), "d2h_bytes_per_step": int(hs.d2h_bytes),
+           "chunk": args.chunk, "steps": e2e_steps}
+
+    # ---- per-kernel shares (CUDA events inside the library) and the roofline of the top kernel --
+    roofline, kernels = None, {}
+    if rank == 0:
+        _lib.profile_enable(True)
+        psteps = max(1, min(args.steps, 2))
+        for _ in range(psteps):
+            step()
+        prof = _lib.profile_read()
+        _lib.profile_enable(False)
+        total = sum(ms_ for _, ms_ in prof.values()) or 1.0
+        kernels = {k: {"launches_per_step": n / psteps, "ms_per_step": m / psteps, "share": m / total}
+                   for k, (n, m) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+        top = next(iter(kernels))
+        ab = algorithmic_bytes(nlon, nlat, plan.nd, KMAX, NLEV)
+        peak, which = peaks()
+        n_launch, top_ms = prof[top]
+        per_launch_ms = top_ms / n_launch
+        bytes_step = ab.get(top, 0.0) * B * (n_launch / psteps if top in ("fused_flux_bruteforce_kernel",
+                                                                          "lwa_scan_kernel") else 1)
+        bytes_launch = bytes_step / (n_launch / psteps)
+        achieved = bytes_launch / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(f"{top}@{nlon}x{nlat}xB{B}")
+        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": which,
+                    "algorithmic_bytes_per_launch": bytes_launch, "ms_per_launch": per_launch_ms,
+                    "pipeline_frac": (ab["pipeline"] * B * args.steps / (ms * 1e-3) / 1e9) / peak}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            snaps = 1 if nlon > 1000 else 8
+            rate, cores, workers, threads, wall = cpu_reference_rate(nlon, nlat, snaps, workers=1 if nlon > 1000 else 8)
+            cpu = {"value": rate, "unit": "snapshots/s", "cores": cores, "kind": "port",
+                   "sample": f"{snaps} synthetic {nlon}x{nlat} snapshot(s), {workers} process(es) x {threads} OpenMP "
+                             f"threads, {wall:.1f} s wall"}
+        line = {
+            "metric": "snapshots/sec, QGFieldNHN22 full pipeline", "value": value, "unit": "snapshots/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"QGFieldNHN22 {nlon}x{nlat}x{NLEV}plev->kmax{KMAX}, jb=5, both hemispheres",
+                       "snapshots_per_step_per_gpu": B, "l2": "inputs of one step exceed L2 (B x 0.92 GB at 0.25 deg)",
+                       "lwa_method": args.method},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu, "kernels": kernels,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4, help="snapshots per step per GPU")
+    ap.add_argument("--chunk", type=int, default=1, help="snapshots per H2D/D2H chunk of the end-to-end run")
+    ap.add_argument("--grid", default="0.25", choices=sorted(GRIDS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--method", type=int, default=0, help="LWA algorithm: 0 automatic, 1 brute force")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    nlon, nlat = GRIDS[args.grid]
+    if args.impl == "reference":
+        run_reference(args, nlon, nlat, rank, world)
+    else:
+        run_b200(args, nlon, nlat, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

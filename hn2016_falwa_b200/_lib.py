@@ -49,8 +49,34 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = c_i
+    lib.falwa_b200_launch_count.restype = ctypes.c_longlong
+    lib.falwa_b200_launch_count.argtypes = []
+    lib.falwa_b200_profile_enable.argtypes = [c_i]
+    lib.falwa_b200_profile_enable.restype = c_i
+    lib.falwa_b200_profile_read.argtypes = [ctypes.c_char_p, c_i]
+    lib.falwa_b200_profile_read.restype = c_i
     _lib = lib
     return lib
+
+
+def launch_count():
+    """Number of CUDA kernels this library has launched so far in this process."""
+    return int(load().falwa_b200_launch_count())
+
+
+def profile_enable(on=True):
+    check(load().falwa_b200_profile_enable(int(bool(on))), "profile_enable")
+
+
+def profile_read():
+    """-> {kernel_name: (launches, total_ms)} since profile_enable(True); synchronises the device."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(load().falwa_b200_profile_read(buf, len(buf)), "profile_read")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.split()
+        out[name] = (int(n), float(ms))
+    return out
 
 
 def register(name, argtypes):

@@ -15,9 +15,50 @@
 
 #define FALWA_LAUNCH_CHECK() FALWA_CUDA_TRY(cudaGetLastError())
 
+// Launch accounting + optional per-kernel CUDA-event timing (falwa_b200_profile_* in the C ABI).
+// `FALWA_KERNEL("name", stream);` directly before a launch counts it and, when profiling is on,
+// brackets everything up to the end of the enclosing scope with two events on that stream.
+#define FALWA_CAT2(a, b) a##b
+#define FALWA_CAT(a, b) FALWA_CAT2(a, b)
+#define FALWA_KERNEL(name, st) falwa::KernelScope FALWA_CAT(_falwa_ks_, __LINE__)(name, st)
+
 namespace falwa {
 
 constexpr int kWarp = 32;
+
+struct ProfileRecord {
+    const char* name;
+    cudaEvent_t e0, e1;
+};
+struct ProfileState {
+    bool enabled = false;
+    long long launches = 0;
+    std::vector<ProfileRecord> recs;
+};
+inline ProfileState& profile_state() {
+    static ProfileState s;
+    return s;
+}
+struct KernelScope {
+    cudaStream_t st;
+    cudaEvent_t e1 = nullptr;
+    KernelScope(const char* name, cudaStream_t stream) : st(stream) {
+        ProfileState& P = profile_state();
+        ++P.launches;
+        if (P.enabled) {
+            ProfileRecord r;
+            r.name = name;
+            cudaEventCreate(&r.e0);
+            cudaEventCreate(&r.e1);
+            cudaEventRecord(r.e0, st);
+            e1 = r.e1;
+            P.recs.push_back(r);
+        }
+    }
+    ~KernelScope() {
+        if (e1) cudaEventRecord(e1, st);
+    }
+};
 
 // Streaming (read-once) global load: do not pollute L1.
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }

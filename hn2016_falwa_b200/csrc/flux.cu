@@ -215,12 +215,12 @@ extern "C" int falwa_b200_compute_flux_dirinv_nshem(
     const int nrows = p.jend - p.jstart + 1;
     dim3 block(32, 8);
     dim3 grid(ceil_div(imax, 32), ceil_div(nrows, 8), kmax - 2);
-    flux_bruteforce_kernel<<<grid, block, 0, st>>>(p);
+    { FALWA_KERNEL("flux_bruteforce_kernel", st); flux_bruteforce_kernel<<<grid, block, 0, st>>>(p); }
     FALWA_LAUNCH_CHECK();
     {  // boundary row jb: executed for either value of is_nhem, like the reference
         const double pi = host_pi(), dp = pi / (double)(jmax - 1);
-        flux_boundary_row_kernel<<<dim3(ceil_div(imax, 128), kmax - 2), 128, 0, st>>>(p, std::cos(dp * (double)jb),
-                                                                                     std::cos(dp * (double)(jb - 1)));
+        { FALWA_KERNEL("flux_boundary_row_kernel", st); flux_boundary_row_kernel<<<dim3(ceil_div(imax, 128), kmax - 2), 128, 0, st>>>(p, std::cos(dp * (double)jb),
+                                                                                     std::cos(dp * (double)(jb - 1))); }
         FALWA_LAUNCH_CHECK();
     }
     return 0;
@@ -257,11 +257,11 @@ extern "C" int falwa_b200_compute_lwa_only_nhn22(const double* pv, const double*
     const int nrows = p.jend - p.jstart + 1;
     dim3 block(32, 8);
     dim3 grid(ceil_div(imax, 32), ceil_div(nrows, 8), kmax - 2);
-    flux_bruteforce_kernel<<<grid, block, 0, st>>>(p);
+    { FALWA_KERNEL("flux_bruteforce_kernel", st); flux_bruteforce_kernel<<<grid, block, 0, st>>>(p); }
     FALWA_LAUNCH_CHECK();
-    lwa_only_column_kernel<<<dim3(ceil_div(imax, 128), nd), 128, 0, st>>>(imax, jmax, kmax, nd, p.jstart, p.jend, p.joff,
+    { FALWA_KERNEL("lwa_only_column_kernel", st); lwa_only_column_kernel<<<dim3(ceil_div(imax, 128), nd), 128, 0, st>>>(imax, jmax, kmax, nd, p.jstart, p.jend, p.joff,
                                                                         astar1, astar2, uu, T.d + o_w, dz / prefac,
-                                                                        astarbaro, ubaro);
+                                                                        astarbaro, ubaro); }
     FALWA_LAUNCH_CHECK();
     return 0;
 }

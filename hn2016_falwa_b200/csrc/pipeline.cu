@@ -547,9 +547,9 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
     const size_t per = 6 * njk + 2 * njd + kmax + nd;
     const size_t ckoff = (size_t)batch * 2 * per;  // ckref per snapshot
     if ((rc = work.alloc(ckoff + (size_t)batch * njk, st, true))) return rc;
-    init_ext_kernel<<<ceil_div((long long)batch * 2 * kmax * 2, 128), 128, 0, st>>>(ext.d, batch * 2 * kmax * 2);
-    zonal_stats_kernel<<<dim3(nlat, kmax, batch), 256, 0, st>>>(nlon, nlat, kmax, qgpv, u, theta, avort, zm.d, ext.d,
-                                                                P->kind == 0 ? 1 : 3);
+    { FALWA_KERNEL("init_ext_kernel", st); init_ext_kernel<<<ceil_div((long long)batch * 2 * kmax * 2, 128), 128, 0, st>>>(ext.d, batch * 2 * kmax * 2); }
+    { FALWA_KERNEL("zonal_stats_kernel", st); zonal_stats_kernel<<<dim3(nlat, kmax, batch), 256, 0, st>>>(nlon, nlat, kmax, qgpv, u, theta, avort, zm.d, ext.d,
+                                                                P->kind == 0 ? 1 : 3); }
     FALWA_LAUNCH_CHECK();
     {
         int slabs = std::max(1, std::min(nlat, (148 * 4 + (kmax - 3)) / (kmax - 2) / std::max(1, std::min(batch, 4))));
@@ -559,8 +559,8 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
         const size_t smem = sizeof(double) * nh * 2 * nb;
         if (smem > 48 * 1024)
             FALWA_CUDA_TRY(cudaFuncSetAttribute(area_hist3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        area_hist3_kernel<<<dim3(slabs, kmax - 2, batch), 256, smem, st>>>(nlon, nlat, kmax, nb, P->kind != 0, qgpv, avort,
-                                                                          ext.d, d + P->o_da, rows, hist.d);
+        { FALWA_KERNEL("area_hist3_kernel", st); area_hist3_kernel<<<dim3(slabs, kmax - 2, batch), 256, smem, st>>>(nlon, nlat, kmax, nb, P->kind != 0, qgpv, avort,
+                                                                          ext.d, d + P->o_da, rows, hist.d); }
         FALWA_LAUNCH_CHECK();
     }
     // host-built per-problem tables
@@ -606,29 +606,29 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
         const double* histb = hist.d + (size_t)b * 3 * kmax * 2 * nb;
         double* ckref = work.d + ckoff + (size_t)b * njk;
         if (P->kind != 0) {
-            qref_invert_kernel<<<kmax - 2, 256, sizeof(double) * 2 * nb, st>>>(
+            { FALWA_KERNEL("qref_invert_kernel", st); qref_invert_kernel<<<kmax - 2, 256, sizeof(double) * 2 * nb, st>>>(
                 kmax, nb, nd, nd, histb + (size_t)2 * kmax * 2 * nb, extb + (size_t)kmax * 2, 1.0, d + P->o_alat, nullptr,
-                ckref, 0);
+                ckref, 0); }
             FALWA_LAUNCH_CHECK();
         }
         for (int hs = 0; hs < 2; ++hs) {
             const double sgn = hs == 0 ? 1.0 : -1.0;
             const int flip = hs == 0 ? 0 : nlat;
-            qref_invert_kernel<<<kmax - 2, 256, sizeof(double) * 2 * nb, st>>>(
-                kmax, nb, nd, nd, histb + (size_t)hs * kmax * 2 * nb, extb, sgn, d + P->o_alat, W(b, hs, 0), W(b, hs, 1), 1);
+            { FALWA_KERNEL("qref_invert_kernel", st); qref_invert_kernel<<<kmax - 2, 256, sizeof(double) * 2 * nb, st>>>(
+                kmax, nb, nd, nd, histb + (size_t)hs * kmax * 2 * nb, extb, sgn, d + P->o_alat, W(b, hs, 0), W(b, hs, 1), 1); }
             FALWA_LAUNCH_CHECK();
-            cbar_normalise_kernel<<<ceil_div(kmax, 64), 64, 0, st>>>(kmax, nd, zmb, nlat, sgn, flip, nd - 1, d + P->o_cosmid,
+            { FALWA_KERNEL("cbar_normalise_kernel", st); cbar_normalise_kernel<<<ceil_div(kmax, 64), 64, 0, st>>>(kmax, nd, zmb, nlat, sgn, flip, nd - 1, d + P->o_cosmid,
                                                                      d + P->o_norm, P->a, P->dphi, pi, W(b, hs, 0),
-                                                                     W(b, hs, 1), W(b, hs, 2), nullptr);
-            extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, nd, nlat, nd - 1, flip, 1.0,
-                                                                   zmb + (size_t)1 * kmax * nlat, W(b, hs, 3));
-            extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, nd, nlat, nd - 1, flip, 1.0,
-                                                                   zmb + (size_t)2 * kmax * nlat, W(b, hs, 4));
+                                                                     W(b, hs, 1), W(b, hs, 2), nullptr); }
+            { FALWA_KERNEL("extract_rows_kernel", st); extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, nd, nlat, nd - 1, flip, 1.0,
+                                                                   zmb + (size_t)1 * kmax * nlat, W(b, hs, 3)); }
+            { FALWA_KERNEL("extract_rows_kernel", st); extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, nd, nlat, nd - 1, flip, 1.0,
+                                                                   zmb + (size_t)2 * kmax * nlat, W(b, hs, 4)); }
             FALWA_LAUNCH_CHECK();
             if (P->kind == 0) {
-                tb_mean_kernel<<<ceil_div(kmax, 64), 64, 0, st>>>(kmax, nd, W(b, hs, 4), d + P->o_cosw, WTB(b, hs));
-                sor_uz_kernel<<<ceil_div(nd, 128), 128, 0, st>>>(nd, kmax, d + P->o_uzc1, d + P->o_uzc2, W(b, hs, 4),
-                                                                 WUZ(b, hs));
+                { FALWA_KERNEL("tb_mean_kernel", st); tb_mean_kernel<<<ceil_div(kmax, 64), 64, 0, st>>>(kmax, nd, W(b, hs, 4), d + P->o_cosw, WTB(b, hs)); }
+                { FALWA_KERNEL("sor_uz_kernel", st); sor_uz_kernel<<<ceil_div(nd, 128), 128, 0, st>>>(nd, kmax, d + P->o_uzc1, d + P->o_uzc2, W(b, hs, 4),
+                                                                 WUZ(b, hs)); }
                 FALWA_LAUNCH_CHECK();
             }
         }
@@ -656,7 +656,7 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
         FALWA_CUDA_TRY(cudaMemcpyAsync(dp.d, probs.data(), sizeof(SorArgs) * nprob, cudaMemcpyHostToDevice, st));
         FALWA_CUDA_TRY(cudaFuncSetAttribute(sor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
         const size_t smem = probs[0].u_in_smem ? sizeof(double) * njk : 0;
-        sor_kernel<<<nprob, 1024, smem, st>>>(dp.d);
+        { FALWA_KERNEL("sor_kernel", st); sor_kernel<<<nprob, 1024, smem, st>>>(dp.d); }
         FALWA_LAUNCH_CHECK();
     } else {
         const int n = jd - 2, m = kmax - 2;
@@ -696,25 +696,25 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
         if ((rc = dwp.alloc(nprob, st))) return rc;
         FALWA_CUDA_TRY(cudaMemcpyAsync(dsp.d, sp.data(), sizeof(SpectralProblem) * nprob, cudaMemcpyHostToDevice, st));
         FALWA_CUDA_TRY(cudaMemcpyAsync(dwp.d, wp.data(), sizeof(SweepArgs) * nprob, cudaMemcpyHostToDevice, st));
-        nhn22_spectral_solve_kernel<<<nprob, 512, 0, st>>>(c, dsp.d);
+        { FALWA_KERNEL("nhn22_spectral_solve_kernel", st); nhn22_spectral_solve_kernel<<<nprob, 512, 0, st>>>(c, dsp.d); }
         FALWA_LAUNCH_CHECK();
-        sweep_post_kernel<<<nprob, 512, 0, st>>>(dwp.d);
+        { FALWA_KERNEL("sweep_post_kernel", st); sweep_post_kernel<<<nprob, 512, 0, st>>>(dwp.d); }
         FALWA_LAUNCH_CHECK();
         // dsp/dwp/sw are stream-ordered: freed after the kernels that use them
         for (int b = 0; b < batch; ++b) {
-            merge_refstates_kernel<<<ceil_div((long long)kmax * nlat, 256), 256, 0, st>>>(
+            { FALWA_KERNEL("merge_refstates_kernel", st); merge_refstates_kernel<<<ceil_div((long long)kmax * nlat, 256), 256, 0, st>>>(
                 kmax, nlat, nd, jd, north_only, 2. * P->omega, P->omega, d + P->o_sinlat, W(b, 0, 0), W(b, 1, 0), WU(b, 0), WU(b, 1),
                 WT(b, 0), WT(b, 1), qref_st + (size_t)b * kmax * nlat, qref_cu + (size_t)b * kmax * nlat,
-                uref_st + (size_t)b * kmax * nlat, ptref_st + (size_t)b * kmax * nlat);
+                uref_st + (size_t)b * kmax * nlat, ptref_st + (size_t)b * kmax * nlat); }
             FALWA_LAUNCH_CHECK();
         }
     }
     if (P->kind == 0) {
         for (int b = 0; b < batch; ++b) {
-            merge_refstates_kernel<<<ceil_div((long long)kmax * nlat, 256), 256, 0, st>>>(
+            { FALWA_KERNEL("merge_refstates_kernel", st); merge_refstates_kernel<<<ceil_div((long long)kmax * nlat, 256), 256, 0, st>>>(
                 kmax, nlat, nd, nd, north_only, 1.0, P->omega, d + P->o_sinlat, W(b, 0, 0), W(b, 1, 0), WU(b, 0), WU(b, 1), WT(b, 0),
                 WT(b, 1), qref_st + (size_t)b * kmax * nlat, qref_cu + (size_t)b * kmax * nlat,
-                uref_st + (size_t)b * kmax * nlat, ptref_st + (size_t)b * kmax * nlat);
+                uref_st + (size_t)b * kmax * nlat, ptref_st + (size_t)b * kmax * nlat); }
             FALWA_LAUNCH_CHECK();
         }
     }
@@ -762,11 +762,11 @@ extern "C" int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* P, int bat
     }
     for (int south = 0; south < (north_only ? 1 : 2); ++south) {  // north first, south second: equator row = south
         p.south = south;
-        fused_flux_bruteforce_kernel<<<grid, block, 0, st>>>(p);
+        { FALWA_KERNEL("fused_flux_bruteforce_kernel", st); fused_flux_bruteforce_kernel<<<grid, block, 0, st>>>(p); }
         FALWA_LAUNCH_CHECK();
     }
-    baro_post_kernel<<<dim3(ceil_div(P->nlon, 256), P->nlat, batch), 256, 0, st>>>(
-        P->nlon, P->nlat, P->kmax, P->a, P->dphi, P->dlambda, p.dc, d + P->o_clat, d + P->o_vw, u, v, uref_st, out2d);
+    { FALWA_KERNEL("baro_post_kernel", st); baro_post_kernel<<<dim3(ceil_div(P->nlon, 256), P->nlat, batch), 256, 0, st>>>(
+        P->nlon, P->nlat, P->kmax, P->a, P->dphi, P->dlambda, p.dc, d + P->o_clat, d + P->o_vw, u, v, uref_st, out2d); }
     FALWA_LAUNCH_CHECK();
     return 0;
 }

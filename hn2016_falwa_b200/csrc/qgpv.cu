@@ -177,15 +177,18 @@ int qgpv_launch(int mode, int nlon, int nlat, int kmax, int jd, int batch, const
     const int kchunk = pick_kchunk(nlon, nlat, kmax, batch);
     dim3 block(32, 8);
     dim3 grid(ceil_div(nlon, 32), ceil_div(nlat, 8), ceil_div(kmax, kchunk) * batch);
-    if (mode == 0)
-        avort_pv_kernel<0><<<grid, block, 0, st>>>(nlon, nlat, kmax, jd, kchunk, u, v, th, tb, d_prof, avort, pv, bstride);
-    else
-        avort_pv_kernel<1><<<grid, block, 0, st>>>(nlon, nlat, kmax, jd, kchunk, u, v, th, tb, d_prof, avort, pv, bstride);
+    {
+        FALWA_KERNEL("avort_pv_kernel", st);
+        if (mode == 0)
+            avort_pv_kernel<0><<<grid, block, 0, st>>>(nlon, nlat, kmax, jd, kchunk, u, v, th, tb, d_prof, avort, pv, bstride);
+        else
+            avort_pv_kernel<1><<<grid, block, 0, st>>>(nlon, nlat, kmax, jd, kchunk, u, v, th, tb, d_prof, avort, pv, bstride);
+    }
     FALWA_LAUNCH_CHECK();
-    polar_rows_kernel<<<dim3(kmax, 2, batch), 256, 0, st>>>(nlon, nlat, kmax, mode == 1, avort, pv, bstride);
+    { FALWA_KERNEL("polar_rows_kernel", st); polar_rows_kernel<<<dim3(kmax, 2, batch), 256, 0, st>>>(nlon, nlat, kmax, mode == 1, avort, pv, bstride); }
     FALWA_LAUNCH_CHECK();
     if (mode == 0) {
-        nh18_finish_kernel<<<dim3(nlat, kmax - 2, batch), 256, 0, st>>>(nlon, nlat, kmax, avort, pv, tb, bstride);
+        { FALWA_KERNEL("nh18_finish_kernel", st); nh18_finish_kernel<<<dim3(nlat, kmax - 2, batch), 256, 0, st>>>(nlon, nlat, kmax, avort, pv, tb, bstride); }
         FALWA_LAUNCH_CHECK();
     }
     return 0;
@@ -280,18 +283,18 @@ int interp_launch(int nlon, int nlat, int nlev, int kmax, int batch, const doubl
                   const double* tin, const int* lo, const double* whi, const double* wlo, const double* fac, double* uo,
                   double* vo, double* to, cudaStream_t st) {
     const size_t plane = (size_t)nlon * nlat;
-    interp_kernel<<<dim3(ceil_div((long long)plane, 256), batch), 256, 0, st>>>(
-        nlon, nlat, nlev, kmax, uin, vin, tin, lo, whi, wlo, fac, uo, vo, to, plane * nlev, plane * kmax);
+    { FALWA_KERNEL("interp_kernel", st); interp_kernel<<<dim3(ceil_div((long long)plane, 256), batch), 256, 0, st>>>(
+        nlon, nlat, nlev, kmax, uin, vin, tin, lo, whi, wlo, fac, uo, vo, to, plane * nlev, plane * kmax); }
     FALWA_LAUNCH_CHECK();
     return 0;
 }
 
 int theta_means_launch(int nlon, int nlat, int nlev, int jd, int batch, const double* tin, const double* fac,
                        const double* clat, double* rowmean, double* out, cudaStream_t st) {
-    theta_rowmean_kernel<<<dim3(nlat, nlev, batch), 256, 0, st>>>(nlon, nlat, nlev, tin, fac, clat, rowmean,
-                                                                  (size_t)nlon * nlat * nlev);
+    { FALWA_KERNEL("theta_rowmean_kernel", st); theta_rowmean_kernel<<<dim3(nlat, nlev, batch), 256, 0, st>>>(nlon, nlat, nlev, tin, fac, clat, rowmean,
+                                                                  (size_t)nlon * nlat * nlev); }
     FALWA_LAUNCH_CHECK();
-    theta_hemi_kernel<<<dim3(nlev, 2, batch), 128, 0, st>>>(nlat, nlev, jd, rowmean, clat, out);
+    { FALWA_KERNEL("theta_hemi_kernel", st); theta_hemi_kernel<<<dim3(nlev, 2, batch), 128, 0, st>>>(nlat, nlev, jd, rowmean, clat, out); }
     FALWA_LAUNCH_CHECK();
     return 0;
 }

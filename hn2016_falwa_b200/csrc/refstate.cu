@@ -585,8 +585,8 @@ static int launch_hist(int nlon, int nlat, int kmax, int nb, const double* fld, 
     int rows = ceil_div(nlat, slabs);
     slabs = ceil_div(nlat, rows);
     const size_t smem = sizeof(double) * 2 * nb;
-    area_hist_kernel<<<dim3(slabs, kmax - 2), kHistThreads, smem, st>>>(nlon, nlat, kmax, nb, fld, ext, sgn, d_da,
-                                                                       rows, hist, bins);
+    { FALWA_KERNEL("area_hist_kernel", st); area_hist_kernel<<<dim3(slabs, kmax - 2), kHistThreads, smem, st>>>(nlon, nlat, kmax, nb, fld, ext, sgn, d_da,
+                                                                       rows, hist, bins); }
     FALWA_LAUNCH_CHECK();
     return 0;
 }
@@ -660,18 +660,18 @@ extern "C" int falwa_b200_compute_reference_states(const double* pv, const doubl
            *fjk = prof.d + 4 * njk;
     FALWA_CUDA_TRY(cudaMemsetAsync(qref, 0, sizeof(double) * njk, st));
     FALWA_CUDA_TRY(cudaMemsetAsync(tref, 0, sizeof(double) * njk, st));
-    init_ext_kernel<<<ceil_div(2 * kmax * 2, 128), 128, 0, st>>>(ext.d, 2 * kmax * 2);
-    zonal_stats_kernel<<<dim3(nlat, kmax), 256, 0, st>>>(nlon, nlat, kmax, pv, uu, pt, nullptr, zm.d, ext.d, 1);
+    { FALWA_KERNEL("init_ext_kernel", st); init_ext_kernel<<<ceil_div(2 * kmax * 2, 128), 128, 0, st>>>(ext.d, 2 * kmax * 2); }
+    { FALWA_KERNEL("zonal_stats_kernel", st); zonal_stats_kernel<<<dim3(nlat, kmax), 256, 0, st>>>(nlon, nlat, kmax, pv, uu, pt, nullptr, zm.d, ext.d, 1); }
     FALWA_LAUNCH_CHECK();
-    extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, jd, nlat, jd - 1, 0, 1.0, zm.d + (size_t)1 * kmax * nlat, ubar);
-    extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, jd, nlat, jd - 1, 0, 1.0, zm.d + (size_t)2 * kmax * nlat, tbar);
-    tb_mean_kernel<<<ceil_div(kmax, 64), 64, 0, st>>>(kmax, jd, tbar, d + o_cosw, tb.d);
+    { FALWA_KERNEL("extract_rows_kernel", st); extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, jd, nlat, jd - 1, 0, 1.0, zm.d + (size_t)1 * kmax * nlat, ubar); }
+    { FALWA_KERNEL("extract_rows_kernel", st); extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, jd, nlat, jd - 1, 0, 1.0, zm.d + (size_t)2 * kmax * nlat, tbar); }
+    { FALWA_KERNEL("tb_mean_kernel", st); tb_mean_kernel<<<ceil_div(kmax, 64), 64, 0, st>>>(kmax, jd, tbar, d + o_cosw, tb.d); }
     if ((rc = launch_hist(nlon, nlat, kmax, npart, pv, ext.d, 1.0, d + o_da, hist.d, bins, st))) return rc;
-    qref_invert_kernel<<<kmax - 2, 256, sizeof(double) * 2 * npart, st>>>(kmax, npart, jd, jd, hist.d, ext.d, 1.0,
-                                                                           d + o_alat, qref, cref, 1);
+    { FALWA_KERNEL("qref_invert_kernel", st); qref_invert_kernel<<<kmax - 2, 256, sizeof(double) * 2 * npart, st>>>(kmax, npart, jd, jd, hist.d, ext.d, 1.0,
+                                                                           d + o_alat, qref, cref, 1); }
     FALWA_LAUNCH_CHECK();
-    cbar_normalise_kernel<<<ceil_div(kmax, 64), 64, 0, st>>>(kmax, jd, zm.d, nlat, 1.0, 0, jd - 1, d + o_cosmid,
-                                                             d + o_norm, a, dphi, pi, qref, cref, cbar, nullptr);
+    { FALWA_KERNEL("cbar_normalise_kernel", st); cbar_normalise_kernel<<<ceil_div(kmax, 64), 64, 0, st>>>(kmax, jd, zm.d, nlat, 1.0, 0, jd - 1, d + o_cosmid,
+                                                             d + o_norm, a, dphi, pi, qref, cref, cbar, nullptr); }
     FALWA_LAUNCH_CHECK();
     // uz(j) = c1(j) * (tbar(j+1,kmax-1) - tbar(j-1,kmax-1)) / c2(j)   (:188-190)
     DeviceTable C;
@@ -684,7 +684,7 @@ extern "C" int falwa_b200_compute_reference_states(const double* pv, const doubl
             both[jd + j - 1] = 2. * om * std::sin(phi0) * dphi * h * a;
         }
         if ((rc = C.upload(both, st))) return rc;
-        sor_uz_kernel<<<ceil_div(jd, 128), 128, 0, st>>>(jd, kmax, C.d, C.d + jd, tbar, uzdev.d);
+        { FALWA_KERNEL("sor_uz_kernel", st); sor_uz_kernel<<<ceil_div(jd, 128), 128, 0, st>>>(jd, kmax, C.d, C.d + jd, tbar, uzdev.d); }
         FALWA_LAUNCH_CHECK();
     }
     SorArgs p;
@@ -701,7 +701,7 @@ extern "C" int falwa_b200_compute_reference_states(const double* pv, const doubl
     DeviceScratch<SorArgs> dp;
     if ((rc = dp.alloc(1, st))) return rc;
     FALWA_CUDA_TRY(cudaMemcpyAsync(dp.d, &p, sizeof(SorArgs), cudaMemcpyHostToDevice, st));
-    sor_kernel<<<1, 1024, smem, st>>>(dp.d);
+    { FALWA_KERNEL("sor_kernel", st); sor_kernel<<<1, 1024, smem, st>>>(dp.d); }
     FALWA_LAUNCH_CHECK();
     FALWA_CUDA_TRY(cudaMemcpyAsync(num_of_iter_host, nit.d, sizeof(int), cudaMemcpyDeviceToHost, st));
     FALWA_CUDA_TRY(cudaStreamSynchronize(st));
@@ -755,27 +755,27 @@ extern "C" int falwa_b200_compute_qref_and_fawa_first(const double* pv, const do
     FALWA_CUDA_TRY(cudaMemsetAsync(ckref, 0, sizeof(double) * njk, st));
     FALWA_CUDA_TRY(cudaMemsetAsync(tjk, 0, sizeof(double) * (size_t)n * (kmax - 1), st));
     FALWA_CUDA_TRY(cudaMemsetAsync(sjk, 0, sizeof(double) * (size_t)n * n * (kmax - 1), st));
-    init_ext_kernel<<<ceil_div(2 * kmax * 2, 128), 128, 0, st>>>(ext.d, 2 * kmax * 2);
-    zonal_stats_kernel<<<dim3(jmax, kmax), 256, 0, st>>>(imax, jmax, kmax, pv, uu, pt, vort, zm.d, ext.d, 3);
+    { FALWA_KERNEL("init_ext_kernel", st); init_ext_kernel<<<ceil_div(2 * kmax * 2, 128), 128, 0, st>>>(ext.d, 2 * kmax * 2); }
+    { FALWA_KERNEL("zonal_stats_kernel", st); zonal_stats_kernel<<<dim3(jmax, kmax), 256, 0, st>>>(imax, jmax, kmax, pv, uu, pt, vort, zm.d, ext.d, 3); }
     FALWA_LAUNCH_CHECK();
-    extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, nd, jmax, nd - 1, 0, 1.0, zm.d + (size_t)1 * kmax * jmax, ubar);
-    extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, nd, jmax, nd - 1, 0, 1.0, zm.d + (size_t)2 * kmax * jmax, tbar);
+    { FALWA_KERNEL("extract_rows_kernel", st); extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, nd, jmax, nd - 1, 0, 1.0, zm.d + (size_t)1 * kmax * jmax, ubar); }
+    { FALWA_KERNEL("extract_rows_kernel", st); extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, nd, jmax, nd - 1, 0, 1.0, zm.d + (size_t)2 * kmax * jmax, tbar); }
     // QGPV area analysis -> qref, cref
     if ((rc = launch_hist(imax, jmax, kmax, nnd, pv, ext.d, 1.0, d + o_da, hist.d, bins_pv, st))) return rc;
-    qref_invert_kernel<<<kmax - 2, 256, sizeof(double) * 2 * nnd, st>>>(kmax, nnd, nd, nd, hist.d, ext.d, 1.0,
-                                                                         d + o_alat, qref, cref, 1);
+    { FALWA_KERNEL("qref_invert_kernel", st); qref_invert_kernel<<<kmax - 2, 256, sizeof(double) * 2 * nnd, st>>>(kmax, nnd, nd, nd, hist.d, ext.d, 1.0,
+                                                                         d + o_alat, qref, cref, 1); }
     FALWA_LAUNCH_CHECK();
     // absolute-vorticity area analysis -> ckref
     if ((rc = launch_hist(imax, jmax, kmax, nnd, vort, ext.d + (size_t)kmax * 2, 1.0, d + o_da, hist.d, bins_vort, st)))
         return rc;
-    qref_invert_kernel<<<kmax - 2, 256, sizeof(double) * 2 * nnd, st>>>(kmax, nnd, nd, nd, hist.d,
+    { FALWA_KERNEL("qref_invert_kernel", st); qref_invert_kernel<<<kmax - 2, 256, sizeof(double) * 2 * nnd, st>>>(kmax, nnd, nd, nd, hist.d,
                                                                          ext.d + (size_t)kmax * 2, 1.0, d + o_alat,
-                                                                         nullptr, ckref, 0);
+                                                                         nullptr, ckref, 0); }
     FALWA_LAUNCH_CHECK();
-    cbar_normalise_kernel<<<ceil_div(kmax, 64), 64, 0, st>>>(kmax, nd, zm.d, jmax, 1.0, 0, nd - 1, d + o_cosmid,
-                                                             d + o_norm, a, dphi, pi, qref, cref, cbar, fawa);
+    { FALWA_KERNEL("cbar_normalise_kernel", st); cbar_normalise_kernel<<<ceil_div(kmax, 64), 64, 0, st>>>(kmax, nd, zm.d, jmax, 1.0, 0, nd - 1, d + o_cosmid,
+                                                             d + o_norm, a, dphi, pi, qref, cref, cbar, fawa); }
     FALWA_LAUNCH_CHECK();
-    nhn22_top_bc_kernel<<<ceil_div(n, 128), 128, 0, st>>>(n, nd, kmax, jb, tbar, d + o_coef, d + o_den, tjk, sjk);
+    { FALWA_KERNEL("nhn22_top_bc_kernel", st); nhn22_top_bc_kernel<<<ceil_div(n, 128), 128, 0, st>>>(n, nd, kmax, jb, tbar, d + o_coef, d + o_den, tjk, sjk); }
     FALWA_LAUNCH_CHECK();
     return 0;
 }
@@ -812,9 +812,9 @@ extern "C" int falwa_b200_matrix_b4_inversion(int k, int jmax, int kmax, int nd,
     if (rc) return rc;
     const double fcoef = -0.5 * a * dp;
     const double u1coef = 2. * pi * a, u1off = om * a * std::cos(dp * (double)jb);
-    b4_kernel<<<ceil_div((long long)n * n, 256), 256, 0, st>>>(n, k, nd, jb, T.d, T.d + n, T.d + 2 * n, T.d + 3 * n, fcoef,
+    { FALWA_KERNEL("b4_kernel", st); b4_kernel<<<ceil_div((long long)n * n, 256), 256, 0, st>>>(n, k, nd, jb, T.d, T.d + n, T.d + 2 * n, T.d + 3 * n, fcoef,
                                                               u1coef, u1off, qref, ckref, sjk + (size_t)(k - 1) * n * n,
-                                                              qjj, djj, cjj, rj);
+                                                              qjj, djj, cjj, rj); }
     FALWA_LAUNCH_CHECK();
     return 0;
 }
@@ -826,10 +826,10 @@ extern "C" int falwa_b200_matrix_after_inversion(int k, int kmax, int jd, const 
     if (k < 2 || k > kmax - 1 || jd < 4) return FALWA_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int n = jd - 2;
-    after_s_kernel<<<ceil_div((long long)n * n, 256), 256, 0, st>>>(n, qjj, djj, sjk + (size_t)(k - 2) * n * n);
+    { FALWA_KERNEL("after_s_kernel", st); after_s_kernel<<<ceil_div((long long)n * n, 256), 256, 0, st>>>(n, qjj, djj, sjk + (size_t)(k - 2) * n * n); }
     FALWA_LAUNCH_CHECK();
-    after_t_kernel<<<1, 512, sizeof(double) * n, st>>>(n, qjj, cjj, rj, tjk + (size_t)(k - 1) * n,
-                                                        tjk + (size_t)(k - 2) * n);
+    { FALWA_KERNEL("after_t_kernel", st); after_t_kernel<<<1, 512, sizeof(double) * n, st>>>(n, qjj, cjj, rj, tjk + (size_t)(k - 1) * n,
+                                                        tjk + (size_t)(k - 2) * n); }
     FALWA_LAUNCH_CHECK();
     return 0;
 }
@@ -866,12 +866,12 @@ extern "C" int falwa_b200_upward_sweep(int jmax, int kmax, int nd, int jb, int j
     p.tref = tref; p.qref = qref; p.u = u; p.pjk = pjk.d;
     p.u1top = 0.0; p.u1off = om * a * std::cos(dp * (double)jb);
     FALWA_CUDA_TRY(cudaMemsetAsync(tref, 0, sizeof(double) * (size_t)jd * kmax, st));
-    sweep_matvec_kernel<<<1, 1024, 0, st>>>(n, kmax, sjk, tjk, pjk.d);
+    { FALWA_KERNEL("sweep_matvec_kernel", st); sweep_matvec_kernel<<<1, 1024, 0, st>>>(n, kmax, sjk, tjk, pjk.d); }
     FALWA_LAUNCH_CHECK();
     DeviceScratch<SweepArgs> dprob;
     if ((rc = dprob.alloc(1, st))) return rc;
     FALWA_CUDA_TRY(cudaMemcpyAsync(dprob.d, &p, sizeof(SweepArgs), cudaMemcpyHostToDevice, st));
-    sweep_post_kernel<<<1, 512, 0, st>>>(dprob.d);
+    { FALWA_KERNEL("sweep_post_kernel", st); sweep_post_kernel<<<1, 512, 0, st>>>(dprob.d); }
     FALWA_LAUNCH_CHECK();
     return 0;
 }

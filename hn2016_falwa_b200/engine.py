@@ -206,3 +206,90 @@ class QGBatch:
         self.compute_reference_states()
         self.compute_lwa_and_barotropic_fluxes(ncforce=ncforce, method=method)
         return self
+
+
+class HostStream:
+    """Streams host-resident snapshots through one GPU in chunks: pinned host -> device copy, the three stages,
+    device -> pinned host copy of the results, with the copies of neighbouring chunks overlapping the kernels
+    (separate copy-in / compute / copy-out streams, two input slots).  This is what ``QGDataset`` uses for a shard
+    of time steps and what bench.py times as the end-to-end number.
+
+    Results (per snapshot, the return values of the reference's ``compute_reference_states`` and
+    ``compute_lwa_and_barotropic_fluxes``, oopinterface.py:550-615, :796-962):
+      qref, uref, ptref [N][kmax][nlat];  the 2-D fields of ``OUT2D`` [N][15][nlat][nlon];  lwa [N][kmax][nlat][nlon]
+      (optional, ``want_lwa3d``).
+    """
+
+    def __init__(self, plan, chunk=1, want_lwa3d=True, method=0, on_height_grid=False):
+        self.plan, self.chunk, self.want_lwa3d, self.method = plan, int(chunk), want_lwa3d, method
+        self.on_height_grid = on_height_grid
+        self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        nl = plan.kmax if on_height_grid else plan.nlev
+        shape = (self.chunk, nl, plan.nlat, plan.nlon)
+        self.slots = [tuple(torch.empty(shape, dtype=torch.float64, device="cuda") for _ in range(3)) for _ in range(2)]
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_free = [torch.cuda.Event() for _ in range(2)]
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    @staticmethod
+    def pinned(shape):
+        return torch.empty(shape, dtype=torch.float64).pin_memory()
+
+    def alloc_outputs(self, n):
+        p = self.plan
+        out = dict(qref=self.pinned((n, p.kmax, p.nlat)), uref=self.pinned((n, p.kmax, p.nlat)),
+                   ptref=self.pinned((n, p.kmax, p.nlat)), out2d=self.pinned((n, N_OUT2D, p.nlat, p.nlon)),
+                   num_of_iter=np.zeros((n, 2), dtype=np.int32))
+        if self.want_lwa3d:
+            out["lwa"] = self.pinned((n, p.kmax, p.nlat, p.nlon))
+        return out
+
+    def _h2d(self, slot, host, lo, hi):
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.ev_free[slot])
+            for dst, src in zip(self.slots[slot], host):
+                dst[:hi - lo].copy_(src[lo:hi], non_blocking=True)
+                self.h2d_bytes += (hi - lo) * dst[0].numel() * 8
+            self.ev_in[slot].record(self.s_in)
+
+    def run(self, u, v, t, out=None):
+        """u, v, t: pinned float64 host tensors [N][nlev][nlat][nlon] (NumPy arrays are staged through pinned
+        memory first).  Returns the dict of pinned host result tensors (``out`` is reused when given)."""
+        host = []
+        for x in (u, v, t):
+            if not isinstance(x, torch.Tensor):
+                x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+            if not x.is_pinned():
+                x = x.pin_memory()
+            host.append(x)
+        n = int(host[0].shape[0])
+        if out is None:
+            out = self.alloc_outputs(n)
+        self.h2d_bytes = self.d2h_bytes = 0
+        main = torch.cuda.current_stream()
+        for e in self.ev_free:
+            e.record(main)
+        bounds = [(lo, min(n, lo + self.chunk)) for lo in range(0, n, self.chunk)]
+        self._h2d(0, host, *bounds[0])
+        for c, (lo, hi) in enumerate(bounds):
+            slot = c & 1
+            if c + 1 < len(bounds):
+                self._h2d(slot ^ 1, host, *bounds[c + 1])
+            main.wait_event(self.ev_in[slot])
+            b = QGBatch(self.plan, *(x[:hi - lo] for x in self.slots[slot]), on_height_grid=self.on_height_grid)
+            b.run(method=self.method)
+            self.ev_free[slot].record(main)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(done)
+                pairs = [("qref", b.qref_cu), ("uref", b.uref), ("ptref", b.ptref), ("out2d", b.out2d)]
+                if self.want_lwa3d:
+                    pairs.append(("lwa", b.lwa))
+                for name, dev in pairs:
+                    dev.record_stream(self.s_out)
+                    out[name][lo:hi].copy_(dev, non_blocking=True)
+                    self.d2h_bytes += dev.numel() * 8
+            out["num_of_iter"][lo:hi] = b.num_of_iter
+        self.s_out.synchronize()
+        return out

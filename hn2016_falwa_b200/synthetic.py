@@ -1,0 +1,40 @@
+"""Seeded synthetic u/v/T snapshots at any grid size: ERA5 0.25° (1440x721) and ERA-Interim
+1.5° (240x121) shapes for benchmarks and tests.  Pure NumPy input generation; no reference or oracle code."""
+import numpy as np
+
+ERA_PLEV = np.array([1000, 975, 950, 925, 900, 875, 850, 825, 800, 775, 750, 700, 650, 600, 550, 500, 450, 400,
+                     350, 300, 250, 225, 200, 175, 150, 125, 100, 70, 50, 30, 20, 10, 7, 5, 3, 2, 1], dtype=np.float64)
+
+
+def synthetic_snapshot(nlon=240, nlat=121, plev=ERA_PLEV, seed=1234, t_index=0):
+    """Seeded analytic snapshot: a Gaussian jet per hemisphere, six Rossby-like waves per
+    hemisphere in u, v, T, and a statically stable T(p) profile (dθ/dz > 0 everywhere).
+
+    Returns xlon, ylat, plev, u, v, t with fields of shape (nlev, nlat, nlon), float64."""
+    rng = np.random.default_rng(seed + t_index)
+    xlon = np.linspace(0.0, 360.0, nlon, endpoint=False)
+    ylat = np.linspace(-90.0, 90.0, nlat, endpoint=True)
+    lam = np.deg2rad(xlon)[None, None, :]
+    phi = ylat[None, :, None]
+    p = plev[:, None, None]
+    zp = -7000.0 * np.log(p / 1000.0)
+    # temperature: troposphere lapse 6.5 K/km to 11 km (min 210 K), slowly warming stratosphere,
+    # plus a pole-to-equator gradient decaying with height
+    t_prof = np.maximum(288.0 - 6.5e-3 * zp, 212.0) + np.maximum(zp - 20000.0, 0.0) * 1.2e-3
+    t = t_prof + 25.0 * (np.cos(np.deg2rad(phi)) ** 2 - 0.5) * np.exp(-zp / 12000.0)
+    vert = np.exp(-((zp - 10500.0) / 9000.0) ** 2)
+    u = np.zeros((plev.size, nlat, nlon))
+    v = np.zeros_like(u)
+    for sgn in (1.0, -1.0):
+        env = np.exp(-((phi - sgn * 45.0) / 15.0) ** 2)
+        u = u + 40.0 * env * vert
+        for m in range(1, 7):
+            amp = rng.uniform(2.0, 10.0)
+            ph0 = rng.uniform(0.0, 2 * np.pi) + 2 * np.pi * t_index / (4.0 * 5.0 * m)
+            tilt = rng.uniform(-0.5, 0.5)
+            wave = np.cos(m * lam + ph0 + tilt * np.deg2rad(phi - sgn * 45.0) * 4.0)
+            wave_s = np.sin(m * lam + ph0 + tilt * np.deg2rad(phi - sgn * 45.0) * 4.0)
+            u = u + 0.5 * amp * env * vert * wave
+            v = v + amp * env * vert * wave_s
+            t = t + 0.3 * amp * env * np.exp(-zp / 15000.0) * wave
+    return xlon, ylat, plev.copy(), u, v, t

@@ -192,6 +192,13 @@ int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* plan, int batch, cons
                                          const double* uref_st, const double* ptref_st, int north_only,
                                          double* lwa, double* out2d, int method, void* stream);
 
+/* Diagnostics used by bench.py (not on the data path): number of kernels launched by this library so far;
+ * optional per-kernel timing with CUDA events on the launching stream.  profile_read synchronises the device
+ * and writes one line "kernel_name launches total_ms" per kernel into buf, then clears the records. */
+long long falwa_b200_launch_count(void);
+int falwa_b200_profile_enable(int on);
+int falwa_b200_profile_read(char* buf, int buflen);
+
 /* Host-only test hook: eigen-decomposition of a symmetric tridiagonal matrix (used by the NHN22 solve). */
 int falwa_b200_debug_symtridiag_eig(int m, double* d, const double* e, double* z);
 
