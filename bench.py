@@ -104,9 +104,9 @@ def algorithmic_bytes(nlon, nlat, nd, kmax, nlev, has_avort=True):
         "avort_pv_kernel": 3 * f3 + 2 * f3,
         "zonal_stats_kernel": 4 * f3,
         "area_hist3_kernel": 2 * f3,
-        "fused_flux_bruteforce_kernel": 4 * hemi3 + hemi3 + 11 * hemi2,     # per hemisphere launch
-        "lwa_scan_kernel": 2 * hemi3 + 3 * hemi3,                              # per hemisphere launch
-        "flux_column_kernel": 6 * f3 + f3 + 12 * f2,
+        "fused_flux_bruteforce_kernel": 2 * (4 * hemi3 + hemi3 + 11 * hemi2),
+        "lwa_scan_kernel": 2 * (2 * hemi3 + 3 * hemi3),                        # read pv, u; write a1, a2, ua2
+        "flux_column_kernel": 2 * (6 * hemi3 + hemi3 + 12 * hemi2),            # read a1,a2,ua2,u,v,theta; write lwa + 2-D
         "baro_post_kernel": 2 * f3 + 8 * f2,
         "pipeline": 3 * f3in + 4 * f3 + f3 + 12 * f2,                         # 3056.6 MB at 0.25°
     }
@@ -266,9 +266,7 @@ def run_b200(args, nlon, nlat, rank, world, local_rank):
         peak, which = peaks()
         n_launch, top_ms = prof[top]
         per_launch_ms = top_ms / n_launch
-        bytes_step = ab.get(top, 0.0) * B * (n_launch / psteps if top in ("fused_flux_bruteforce_kernel",
-                                                                          "lwa_scan_kernel") else 1)
-        bytes_launch = bytes_step / (n_launch / psteps)
+        bytes_launch = ab.get(top, 0.0) * B / (n_launch / psteps)   # table entries are per snapshot, all launches
         achieved = bytes_launch / (per_launch_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")

@@ -2,6 +2,7 @@
 #include "version.cu"
 #include "qgpv.cu"
 #include "refstate.cu"
+#include "flux_scan.cu"
 #include "flux.cu"
 #include "nhn22_solve.cu"
 #include "pipeline.cu"

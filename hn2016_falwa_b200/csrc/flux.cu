@@ -27,7 +27,10 @@ struct FluxArgs {
     unsigned long long* mask_count;
 };
 
-// one thread per (i, j) of one level; jj loop in the reference's order
+// one thread per (i, j) of one level; jj loop in the reference's order.
+// BRUTE = false: astar1 / astar2 (/ ua2 / ncforce3d) were already written by the interval-scan kernel
+// (flux_scan.cu) and only the pointwise flux terms are evaluated here.
+template <bool BRUTE>
 __global__ void __launch_bounds__(256)
 flux_bruteforce_kernel(FluxArgs p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -44,7 +47,12 @@ flux_bruteforce_kernel(FluxArgs p) {
         const double ur = p.uref[(size_t)(k - 1) * p.jd + (j - p.uoff - 1)];
         const double cphi0 = p.cosphi[j];
         double as_pos = 0., as_neg = 0., ncf = 0., u2 = 0.;
-        for (int jj = 1; jj < j; ++jj) {  // cyclonic candidates: qe > 0, jj < j
+        const size_t o = ((size_t)(k - 1) * p.nd + (j - 1)) * p.imax + i;
+        if (!BRUTE) {
+            as_neg = p.astar1[o];
+            as_pos = p.astar2[o];
+        }
+        for (int jj = 1; BRUTE && jj < j; ++jj) {  // cyclonic candidates: qe > 0, jj < j
             const double q = pvk[(size_t)(jj - 1) * p.imax];
             const double qe = q - qr;
             if (qe > 0.) {
@@ -56,7 +64,7 @@ flux_bruteforce_kernel(FluxArgs p) {
                 ++c1;
             }
         }
-        for (int jj = j; jj <= p.nd; ++jj) {  // anticyclonic candidates: qe <= 0, jj >= j
+        for (int jj = j; BRUTE && jj <= p.nd; ++jj) {  // anticyclonic candidates: qe <= 0, jj >= j
             const double q = pvk[(size_t)(jj - 1) * p.imax];
             const double qe = q - qr;
             if (qe <= 0.) {
@@ -70,11 +78,12 @@ flux_bruteforce_kernel(FluxArgs p) {
         }
         double a1, a2;
         if (p.is_nhem) { a2 = as_pos; a1 = as_neg; } else { a1 = as_pos; a2 = as_neg; }
-        const size_t o = ((size_t)(k - 1) * p.nd + (j - 1)) * p.imax + i;
-        p.astar1[o] = a1;
-        p.astar2[o] = a2;
-        if (p.ncforce3d) p.ncforce3d[o] = ncf;
-        if (p.ua2) p.ua2[o] = u2;
+        if (BRUTE) {
+            p.astar1[o] = a1;
+            p.astar2[o] = a2;
+            if (p.ncforce3d) p.ncforce3d[o] = ncf;
+            if (p.ua2) p.ua2[o] = u2;
+        }
         if (p.ua1) {
             const size_t g = lev + (size_t)(j + p.joff - 1) * p.imax + i;
             const double uu0 = p.uu[g], vv0 = p.vv[g], pt0 = p.pt[g];
@@ -105,7 +114,7 @@ flux_bruteforce_kernel(FluxArgs p) {
             }
         }
     }
-    if (p.mask_count) {
+    if (BRUTE && p.mask_count) {
         c1 = __reduce_add_sync(0xffffffffu, (unsigned)c1);
         c2 = __reduce_add_sync(0xffffffffu, (unsigned)c2);
         if ((threadIdx.x & 31) == 0 && (c1 | c2)) {
@@ -191,7 +200,6 @@ extern "C" int falwa_b200_compute_flux_dirinv_nshem(
     int nd, int jb, int jd, int is_nhem, double a, double om, double dz, double h, double rr, double cp, double prefac,
     double* astar1, double* astar2, double* ncforce3d, double* ua1, double* ua2, double* ep1, double* ep2, double* ep3,
     double* ep4, int64_t* mask_count, int method, void* stream) {
-    (void)method;
     if (!pv || !uu || !vv || !pt || !ncforce || !tn0_host || !qref || !uref || !tref || !astar1 || !astar2 ||
         !ncforce3d || !ua1 || !ua2 || !ep1 || !ep2 || !ep3 || !ep4)
         return FALWA_ERR_NULL;
@@ -215,7 +223,29 @@ extern "C" int falwa_b200_compute_flux_dirinv_nshem(
     const int nrows = p.jend - p.jstart + 1;
     dim3 block(32, 8);
     dim3 grid(ceil_div(imax, 32), ceil_div(nrows, 8), kmax - 2);
-    { FALWA_KERNEL("flux_bruteforce_kernel", st); flux_bruteforce_kernel<<<grid, block, 0, st>>>(p); }
+    const bool use_scan = (method != 1) && is_nhem && scan_supported(nd);
+    ScanTables tabs;
+    if (use_scan) {  // astar1, astar2, ua2, ncforce3d by the interval scan, the pointwise terms afterwards
+        if ((rc = tabs.alloc(1, nd, kmax, st))) return rc;
+        ThrArgs t{};
+        ScanArgs s{};
+        t.nd = nd; t.kmax = kmax; t.jstart = p.jstart; t.jend = p.jend; t.nhemi = 1;
+        t.qref = qref; t.q_batch = 0; t.q_kstride = nd; t.q_row0[0] = 0; t.q_rstep[0] = 1; t.q_sg[0] = 1.0;
+        t.uref = uref; t.u_batch = 0; t.u_kstride = jd; t.u_row0[0] = -p.uoff; t.u_rstep[0] = 1;
+        s.imax = imax; s.nd = nd; s.kmax = kmax; s.jstart = p.jstart; s.jend = p.jend; s.nhemi = 1;
+        s.pv = pv; s.uu = uu; s.nc = ncforce; s.in_batch = 0; s.in_plane = (size_t)jmax * imax;
+        s.a1 = astar1; s.a2 = astar2; s.u2 = ua2; s.ncf = ncforce3d;
+        s.out_batch = 0; s.out_plane = (size_t)nd * imax; s.out_pitch = imax;
+        s.fr[0].in_row0 = p.joff; s.fr[0].in_rstep = 1; s.fr[0].out_row0 = 0; s.fr[0].out_rstep = 1;
+        s.fr[0].skip_first_row = 0; s.fr[0].sg = 1.0;
+        s.cosphi = p.cosphi; s.ab = p.ab; s.mask_count = p.mask_count;
+        tabs.bind(t, s, 1, nd, kmax);
+        if ((rc = lwa_scan_launch(t, s, 1, st))) return rc;
+        { FALWA_KERNEL("flux_pointwise_kernel", st); flux_bruteforce_kernel<false><<<grid, block, 0, st>>>(p); }
+    } else {
+        FALWA_KERNEL("flux_bruteforce_kernel", st);
+        flux_bruteforce_kernel<true><<<grid, block, 0, st>>>(p);
+    }
     FALWA_LAUNCH_CHECK();
     {  // boundary row jb: executed for either value of is_nhem, like the reference
         const double pi = host_pi(), dp = pi / (double)(jmax - 1);
@@ -231,7 +261,6 @@ extern "C" int falwa_b200_compute_lwa_only_nhn22(const double* pv, const double*
                                                  double dz, double h, double rr, double cp, double prefac,
                                                  double* astarbaro, double* ubaro, double* astar1, double* astar2,
                                                  int method, void* stream) {
-    (void)method;
     if (!pv || !uu || !qref || !astarbaro || !ubaro || !astar1 || !astar2) return FALWA_ERR_NULL;
     if (imax < 1 || kmax < 4 || nd < 4 || jmax != 2 * nd - 1 || jb < 0) return FALWA_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -257,7 +286,27 @@ extern "C" int falwa_b200_compute_lwa_only_nhn22(const double* pv, const double*
     const int nrows = p.jend - p.jstart + 1;
     dim3 block(32, 8);
     dim3 grid(ceil_div(imax, 32), ceil_div(nrows, 8), kmax - 2);
-    { FALWA_KERNEL("flux_bruteforce_kernel", st); flux_bruteforce_kernel<<<grid, block, 0, st>>>(p); }
+    ScanTables tabs;
+    if ((method != 1) && is_nhem && scan_supported(nd)) {
+        if ((rc = tabs.alloc(1, nd, kmax, st))) return rc;
+        ThrArgs t{};
+        ScanArgs s{};
+        t.nd = nd; t.kmax = kmax; t.jstart = p.jstart; t.jend = p.jend; t.nhemi = 1;
+        t.qref = qref; t.q_batch = 0; t.q_kstride = nd; t.q_row0[0] = 0; t.q_rstep[0] = 1; t.q_sg[0] = 1.0;
+        t.uref = nullptr;
+        s.imax = imax; s.nd = nd; s.kmax = kmax; s.jstart = p.jstart; s.jend = p.jend; s.nhemi = 1;
+        s.pv = pv; s.uu = uu; s.nc = nullptr; s.in_batch = 0; s.in_plane = (size_t)jmax * imax;
+        s.a1 = astar1; s.a2 = astar2; s.u2 = nullptr; s.ncf = nullptr;
+        s.out_batch = 0; s.out_plane = (size_t)nd * imax; s.out_pitch = imax;
+        s.fr[0].in_row0 = p.joff; s.fr[0].in_rstep = 1; s.fr[0].out_row0 = 0; s.fr[0].out_rstep = 1;
+        s.fr[0].skip_first_row = 0; s.fr[0].sg = 1.0;
+        s.cosphi = p.cosphi; s.ab = p.ab; s.mask_count = nullptr;
+        tabs.bind(t, s, 1, nd, kmax);
+        if ((rc = lwa_scan_launch(t, s, 1, st))) return rc;
+    } else {
+        FALWA_KERNEL("flux_bruteforce_kernel", st);
+        flux_bruteforce_kernel<true><<<grid, block, 0, st>>>(p);
+    }
     FALWA_LAUNCH_CHECK();
     { FALWA_KERNEL("lwa_only_column_kernel", st); lwa_only_column_kernel<<<dim3(ceil_div(imax, 128), nd), 128, 0, st>>>(imax, jmax, kmax, nd, p.jstart, p.jend, p.joff,
                                                                         astar1, astar2, uu, T.d + o_w, dz / prefac,

@@ -152,7 +152,9 @@ __global__ void merge_refstates_kernel(int kmax, int nlat, int nd, int jd, int n
 // accumulated in the order of numpy's reduction (oopinterface.py:405-420).
 // ---------------------------------------------------------------------------------------------
 struct FusedFluxArgs {
-    int imax, nlat, kmax, nd, jb, jd, south, has_ncforce;
+    int imax, nlat, kmax, nd, jb, jd, nhemi, has_ncforce;
+    const double *sa1, *sa2, *su2, *snc;       // BRUTE = false: LWA pieces from the interval-scan kernel, [b][k][lat][lon]
+    const double *clat;                        // |cos(lat)| of the global rows
     double a, om, dz, prefac, ab, rrh, ep42fac, dc, cosjb, cosjbm1;
     const double *pv, *uu, *vv, *pt, *ncforce;
     const double *qref_cu, *uref_st, *tref_st;  // [b][k][nlat]
@@ -161,12 +163,19 @@ struct FusedFluxArgs {
     double *lwa, *out2d;
 };
 
+// BRUTE = true: the reference's O(nd^2) double loop inline (method 1).  BRUTE = false: a1 / a2 / ua2 / ncforce3d
+// come from lwa_scan_kernel (flux_scan.cu) and this kernel is a pure column walk ("flux_column").
+// blockIdx.z = snapshot * nhemi + hemisphere (0 = north, 1 = south).  When both hemispheres are computed the
+// southern one owns the equator row (the reference writes north first, south second: data_storage.py:42-62).
+template <bool BRUTE>
 __global__ void __launch_bounds__(256)
-fused_flux_bruteforce_kernel(FusedFluxArgs p) {
+fused_flux_kernel(FusedFluxArgs p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;  // hemispheric row 1..nd
-    const int b = blockIdx.z;
+    const int b = blockIdx.z / p.nhemi;
+    const bool south = (blockIdx.z % p.nhemi) == 1;
     if (i >= p.imax || j > p.nd) return;
+    if (j == 1 && p.nhemi == 2 && !south) return;
     const int nd = p.nd, nlat = p.nlat, imax = p.imax, kmax = p.kmax, jb = p.jb;
     const size_t plane = (size_t)nlat * imax;
     const size_t f3 = (size_t)b * plane * kmax;
@@ -175,17 +184,19 @@ fused_flux_bruteforce_kernel(FusedFluxArgs p) {
     const double* qref = p.qref_cu + (size_t)b * kmax * nlat;
     const double* uref = p.uref_st + (size_t)b * kmax * nlat;
     const double* tref = p.tref_st + (size_t)b * kmax * nlat;
-    const double* tg = p.prof + (size_t)b * 4 * kmax + (p.south ? 0 : kmax);  // tn0 north / ts0 south
+    const double* tg = p.prof + (size_t)b * 4 * kmax + (south ? 0 : kmax);  // tn0 north / ts0 south
     double* lwa = p.lwa + f3;
     double* out = p.out2d + (size_t)b * O_COUNT * plane;
-    const double sg = p.south ? -1.0 : 1.0;  // sign of pv, v and qref in the hemispheric frame
-    auto grow = [&](int jj) -> int { return p.south ? (nd - jj) : (nd - 2 + jj); };  // 0-based global row
+    const double sg = south ? -1.0 : 1.0;  // sign of pv, v and qref in the hemispheric frame
+    auto grow = [&](int jj) -> int { return south ? (nd - jj) : (nd - 2 + jj); };  // 0-based global row
     const int g = grow(j);
     const int jstart = jb + 1, jend = nd - 1;
     const bool in_range = (j >= jstart && j <= jend);
     const bool brow = (jb >= 1) ? (j == jb) : (j == nd);  // boundary row jb, or its alias (i,nd,k-1) when jb = 0
     const double cphi0 = p.cosphi[j];
     double s_a1 = 0, s_a2 = 0, s_ua1 = 0, s_ua2 = 0, s_ep1 = 0, s_ep2 = 0, s_ep3 = 0, s_nc = 0, s_u = 0, ep4 = 0;
+    double s_fphi = 0;
+    const double cl = p.clat[g];
     const size_t o2 = (size_t)g * imax + i;
     lwa[o2] = 0.0;
     lwa[(size_t)(kmax - 1) * plane + o2] = 0.0;
@@ -193,12 +204,22 @@ fused_flux_bruteforce_kernel(FusedFluxArgs p) {
         const size_t lev = (size_t)(k - 1) * plane;
         const double w = p.vw[k - 1];
         s_u = s_u + uu[lev + o2] * w * p.dc;
+        {   // flux_vector_phi_baro = vertical average of -((u - uref) * v) * clat  (oopinterface.py:964-982)
+            const double x = -(((uu[lev + o2] - uref[(size_t)(k - 1) * nlat + g]) * vv[lev + o2]) * cl);
+            s_fphi = s_fphi + x * w * p.dc;
+        }
         if (k == kmax) break;
         double a1 = 0, a2 = 0, ncf = 0, u2 = 0, e1 = 0, e2 = 0, e3 = 0, x_ua1 = 0;
         if (in_range) {
             const double qr = sg * qref[(size_t)(k - 1) * nlat + g];
             const double ur = uref[(size_t)(k - 1) * nlat + g];
-            for (int jj = 1; jj < j; ++jj) {
+            if (!BRUTE) {
+                a1 = p.sa1[f3 + lev + o2];
+                a2 = p.sa2[f3 + lev + o2];
+                u2 = p.su2[f3 + lev + o2];
+                if (nc) ncf = p.snc[f3 + lev + o2];
+            }
+            for (int jj = 1; BRUTE && jj < j; ++jj) {
                 const size_t gg = lev + (size_t)grow(jj) * imax + i;
                 const double qe = sg * pv[gg] - qr;
                 if (qe > 0.) {
@@ -209,7 +230,7 @@ fused_flux_bruteforce_kernel(FusedFluxArgs p) {
                     u2 = u2 + qe * ue * p.ab;
                 }
             }
-            for (int jj = j; jj <= nd; ++jj) {
+            for (int jj = j; BRUTE && jj <= nd; ++jj) {
                 const size_t gg = lev + (size_t)grow(jj) * imax + i;
                 const double qe = sg * pv[gg] - qr;
                 if (qe <= 0.) {
@@ -271,18 +292,18 @@ fused_flux_bruteforce_kernel(FusedFluxArgs p) {
     out[(size_t)O_UA2 * plane + o2] = s_ua2;
     out[(size_t)O_EP1 * plane + o2] = s_ep1;
     // southern hemisphere: ep2/ep3 swapped and negated, ncforce negated (oopinterface.py:790-792)
-    out[(size_t)O_EP2 * plane + o2] = p.south ? -s_ep3 : s_ep2;
-    out[(size_t)O_EP3 * plane + o2] = p.south ? -s_ep2 : s_ep3;
+    out[(size_t)O_EP2 * plane + o2] = south ? -s_ep3 : s_ep2;
+    out[(size_t)O_EP3 * plane + o2] = south ? -s_ep2 : s_ep3;
     out[(size_t)O_EP4 * plane + o2] = ep4;
-    out[(size_t)O_NCF * plane + o2] = p.south ? -s_nc : s_nc;
+    out[(size_t)O_NCF * plane + o2] = south ? -s_nc : s_nc;
     out[(size_t)O_UBARO * plane + o2] = s_u;
+    out[(size_t)O_FPHI * plane + o2] = s_fphi;
 }
 
 // barotropic post-processing (oopinterface.py:906-944, :964-982; utilities.py:189-233)
 __global__ void __launch_bounds__(256)
-baro_post_kernel(int nlon, int nlat, int kmax, double a, double dphi, double dlambda, double dc,
-                 const double* __restrict__ clat, const double* __restrict__ vw, const double* __restrict__ uu,
-                 const double* __restrict__ vv, const double* __restrict__ uref_st, double* __restrict__ out2d) {
+baro_post_kernel(int nlon, int nlat, double a, double dphi, double dlambda, const double* __restrict__ clat,
+                 double* __restrict__ out2d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y, b = blockIdx.z;
     if (i >= nlon) return;
@@ -300,16 +321,6 @@ baro_post_kernel(int nlon, int nlat, int kmax, double a, double dphi, double dla
     if (fabs(cl) > 1.e-5) zd = zd * (-1. / (a * cl * 2. * dlambda));
     out[(size_t)O_CONV * plane + o] = zd;
     out[(size_t)O_FLAMBDA * plane + o] = zsum(i);
-    // flux_vector_phi_baro = vertical average of -((u - uref) * v) * clat over levels index 1..kmax-1
-    const double* u3 = uu + (size_t)b * plane * kmax;
-    const double* v3 = vv + (size_t)b * plane * kmax;
-    const double* ur = uref_st + (size_t)b * kmax * nlat;
-    double s = 0.0;
-    for (int k = 1; k < kmax; ++k) {
-        const double x = -(((u3[(size_t)k * plane + o] - ur[(size_t)k * nlat + j]) * v3[(size_t)k * plane + o]) * cl);
-        s = s + x * vw[k] * dc;
-    }
-    out[(size_t)O_FPHI * plane + o] = s;
 }
 
 // small helpers -------------------------------------------------------------------------------
@@ -732,41 +743,81 @@ extern "C" int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* P, int bat
                                                     const double* qref_cu, const double* uref_st,
                                                     const double* ptref_st, int north_only, double* lwa,
                                                     double* out2d, int method, void* stream) {
-    (void)method;
     if (!P || !qgpv || !u || !v || !theta || !profiles_host || !qref_cu || !uref_st || !ptref_st || !lwa || !out2d)
         return FALWA_ERR_NULL;
     if (batch < 1) return FALWA_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const double* d = P->d_tab;
     const double pi = host_pi(), dp = pi / (double)(P->nlat - 1);
+    const int nlon = P->nlon, nlat = P->nlat, kmax = P->kmax, nd = P->nd, jb = P->jb;
+    const int nhemi = north_only ? 1 : 2;
+    const size_t f3 = (size_t)kmax * nlat * nlon;
     int rc;
-    DeviceScratch<double> prof;
-    if ((rc = prof.alloc((size_t)batch * 4 * P->kmax, st))) return rc;
-    FALWA_CUDA_TRY(cudaMemcpyAsync(prof.d, profiles_host, sizeof(double) * (size_t)batch * 4 * P->kmax,
+    DeviceScratch<double> prof, tmp;
+    if ((rc = prof.alloc((size_t)batch * 4 * kmax, st))) return rc;
+    FALWA_CUDA_TRY(cudaMemcpyAsync(prof.d, profiles_host, sizeof(double) * (size_t)batch * 4 * kmax,
                                    cudaMemcpyHostToDevice, st));
     FusedFluxArgs p;
-    p.imax = P->nlon; p.nlat = P->nlat; p.kmax = P->kmax; p.nd = P->nd; p.jb = P->jb; p.jd = P->jd;
+    p.imax = nlon; p.nlat = nlat; p.kmax = kmax; p.nd = nd; p.jb = jb; p.jd = P->jd; p.nhemi = nhemi;
     p.has_ncforce = ncforce != nullptr;
     p.a = P->a; p.om = P->omega; p.dz = P->dz; p.prefac = P->prefactor; p.ab = P->a * dp; p.rrh = P->rr / P->h;
     p.ep42fac = std::exp(-P->dz / P->h); p.dc = P->dz / P->prefactor;
-    p.cosjb = std::cos(dp * (double)P->jb); p.cosjbm1 = std::cos(dp * (double)(P->jb - 1));
+    p.cosjb = std::cos(dp * (double)jb); p.cosjbm1 = std::cos(dp * (double)(jb - 1));
     p.pv = qgpv; p.uu = u; p.vv = v; p.pt = theta; p.ncforce = ncforce;
     p.qref_cu = qref_cu; p.uref_st = uref_st; p.tref_st = ptref_st; p.prof = prof.d;
     p.cosphi = d + P->o_cosphi; p.sinphi = d + P->o_sinphi; p.aaw = d + P->o_aaw; p.ep11a = d + P->o_ep11a; p.vw = d + P->o_vw;
+    p.clat = d + P->o_clat;
+    p.sa1 = p.sa2 = p.su2 = p.snc = nullptr;
     p.lwa = lwa; p.out2d = out2d;
-    dim3 block(32, 8);
-    dim3 grid(ceil_div(P->nlon, 32), ceil_div(P->nd, 8), batch);
     if (north_only) {  // rows the northern launch does not cover stay zero
-        FALWA_CUDA_TRY(cudaMemsetAsync(lwa, 0, sizeof(double) * (size_t)batch * P->kmax * P->nlat * P->nlon, st));
-        FALWA_CUDA_TRY(cudaMemsetAsync(out2d, 0, sizeof(double) * (size_t)batch * O_COUNT * P->nlat * P->nlon, st));
+        FALWA_CUDA_TRY(cudaMemsetAsync(lwa, 0, sizeof(double) * (size_t)batch * f3, st));
+        FALWA_CUDA_TRY(cudaMemsetAsync(out2d, 0, sizeof(double) * (size_t)batch * O_COUNT * nlat * nlon, st));
     }
-    for (int south = 0; south < (north_only ? 1 : 2); ++south) {  // north first, south second: equator row = south
-        p.south = south;
-        { FALWA_KERNEL("fused_flux_bruteforce_kernel", st); fused_flux_bruteforce_kernel<<<grid, block, 0, st>>>(p); }
+    const bool use_scan = (method != 1) && scan_supported(nd);
+    ScanTables tabs;
+    if (use_scan) {
+        // LWA pieces a1, a2, ua2 (, ncforce3d) of every level by the interval scan, in the global frame
+        const int narr = ncforce ? 4 : 3, nprob = batch * nhemi;
+        if ((rc = tmp.alloc((size_t)narr * batch * f3, st))) return rc;
+        if ((rc = tabs.alloc(nprob, nd, kmax, st))) return rc;
+        ThrArgs t{};
+        ScanArgs s{};
+        t.nd = nd; t.kmax = kmax; t.jstart = jb + 1; t.jend = nd - 1; t.nhemi = nhemi;
+        t.qref = qref_cu; t.q_batch = (size_t)kmax * nlat; t.q_kstride = nlat;
+        t.uref = uref_st; t.u_batch = (size_t)kmax * nlat; t.u_kstride = nlat;
+        for (int h = 0; h < 2; ++h) {  // hemispheric row jj -> global row nd-2+jj (north) / nd-jj (south)
+            t.q_row0[h] = t.u_row0[h] = nd - 1;
+            t.q_rstep[h] = t.u_rstep[h] = h ? -1 : 1;
+            t.q_sg[h] = h ? -1.0 : 1.0;
+            s.fr[h].in_row0 = s.fr[h].out_row0 = nd - 1;
+            s.fr[h].in_rstep = s.fr[h].out_rstep = h ? -1 : 1;
+            s.fr[h].sg = h ? -1.0 : 1.0;
+            s.fr[h].skip_first_row = (nhemi == 2 && h == 0) ? 1 : 0;
+        }
+        s.imax = nlon; s.nd = nd; s.kmax = kmax; s.jstart = t.jstart; s.jend = t.jend; s.nhemi = nhemi;
+        s.pv = qgpv; s.uu = u; s.nc = ncforce; s.in_batch = f3; s.in_plane = (size_t)nlat * nlon;
+        s.a1 = tmp.d; s.a2 = tmp.d + (size_t)batch * f3; s.u2 = tmp.d + (size_t)2 * batch * f3;
+        s.ncf = ncforce ? tmp.d + (size_t)3 * batch * f3 : nullptr;
+        s.out_batch = f3; s.out_plane = (size_t)nlat * nlon; s.out_pitch = nlon;
+        s.cosphi = d + P->o_cosphi; s.ab = p.ab; s.mask_count = nullptr;
+        tabs.bind(t, s, nprob, nd, kmax);
+        if ((rc = lwa_scan_launch(t, s, nprob, st))) return rc;
+        p.sa1 = s.a1; p.sa2 = s.a2; p.su2 = s.u2; p.snc = s.ncf;
+    }
+    {
+        dim3 block(32, 8);
+        dim3 grid(ceil_div(nlon, 32), ceil_div(nd, 8), batch * nhemi);
+        if (use_scan) {
+            FALWA_KERNEL("flux_column_kernel", st);
+            fused_flux_kernel<false><<<grid, block, 0, st>>>(p);
+        } else {
+            FALWA_KERNEL("fused_flux_bruteforce_kernel", st);
+            fused_flux_kernel<true><<<grid, block, 0, st>>>(p);
+        }
         FALWA_LAUNCH_CHECK();
     }
     { FALWA_KERNEL("baro_post_kernel", st); baro_post_kernel<<<dim3(ceil_div(P->nlon, 256), P->nlat, batch), 256, 0, st>>>(
-        P->nlon, P->nlat, P->kmax, P->a, P->dphi, P->dlambda, p.dc, d + P->o_clat, d + P->o_vw, u, v, uref_st, out2d); }
+        P->nlon, P->nlat, P->a, P->dphi, P->dlambda, d + P->o_clat, out2d); }
     FALWA_LAUNCH_CHECK();
     return 0;
 }

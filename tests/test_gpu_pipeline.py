@@ -36,8 +36,9 @@ def _check_all(tag, f, want):
         compare(f"{tag}/{name}", getattr(f, name), want[name], rtol=rtol, atol=atol)
 
 
+@pytest.mark.parametrize("method", [0, 1], ids=["scan", "bruteforce"])
 @pytest.mark.parametrize("kind", ["nh18", "nhn22"])
-def test_qgfield_pipeline_matches_oracle(case, kind):
+def test_qgfield_pipeline_matches_oracle(case, kind, method):
     name, inputs = case
     want = pipeline.run_qgfield(kind, *inputs)
     f = _cls(kind)(*inputs)
@@ -51,11 +52,11 @@ def test_qgfield_pipeline_matches_oracle(case, kind):
         compare(f"{name}/{kind}/static_stability_n", f.static_stability[1], ss_want[1], rtol=1e-9)
     ref = f.compute_reference_states()
     assert ref.Qref.shape == want["qref"].shape
-    out = f.compute_lwa_and_barotropic_fluxes(method=1)
+    out = f.compute_lwa_and_barotropic_fluxes(method=method)
     assert out.lwa.shape == want["lwa"].shape
     if kind == "nh18":
         assert tuple(f._batch.num_of_iter[0]) == tuple(want["num_of_iter"])
-    _check_all(f"{name}/{kind}/product", f, want)
+    _check_all(f"{name}/{kind}/product{method}", f, want)
     # structural assertions of the reference's own tests (tests/test_oopinterface.py:410-452)
     np.testing.assert_array_equal(f.flux_vector_lambda_baro, f.adv_flux_f1 + f.adv_flux_f2 + f.adv_flux_f3)
 
