@@ -30,6 +30,12 @@ namespace falwa {
 constexpr int kScanCols = 8;    // longitudes (= warps) per CTA
 constexpr int kScanRMax = 13;   // thresholds per lane in the output phase (odd => conflict-free lane strides)
 constexpr int kScanMaxRows = 32 * kScanRMax;  // 416 hemispheric rows (0.25 deg: 361)
+constexpr int kScanCells = 1024;  // uniform PV grid that brackets the threshold search (cell -> range of thresholds)
+
+// cell of a PV value: monotone in q, so thresholds in lower (higher) cells are < (>) q
+__device__ __forceinline__ int scan_cell(double q, double lo, double inv) {
+    return min(max(__double2int_rz((q - lo) * inv), 0), kScanCells - 1);
+}
 
 struct ScanFrame {
     int in_row0, in_rstep;    // memory row of hemispheric row jj (1-based): in_row0 + in_rstep * (jj - 1)
@@ -51,6 +57,8 @@ struct ScanArgs {
     // per (problem = b * nhemi + h, level): tables of lwa_thresholds_kernel
     const double *thr, *urt;              // [nprob][kmax][nd]: thresholds (exception rows appended), uref alike
     const short *rowof, *nxt, *exc;       // [nprob][kmax][nd], [..][nd+2], [..][nd]
+    const short* cell;                    // [nprob][kmax][kScanCells+1]: #thresholds below each cell of a uniform grid
+    const double* srch;                   // [nprob][kmax][2]: grid origin, cells per unit
     const int* meta;                      // [nprob][kmax][4]: M, nexc
     unsigned long long* mask_count;       // optional: [0] anticyclonic pairs, [1] cyclonic pairs
 };
@@ -60,6 +68,7 @@ struct ThrArgs {
     const double* qref; size_t q_batch; int q_kstride; int q_row0[2], q_rstep[2]; double q_sg[2];
     const double* uref; size_t u_batch; int u_kstride; int u_row0[2], u_rstep[2];  // uref may be null (-> 0)
     double *thr, *urt; short *rowof, *nxt, *exc; int* meta;
+    short* cell; double* srch;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -77,6 +86,7 @@ lwa_thresholds_kernel(ThrArgs p) {
     unsigned char* keepA = (unsigned char*)(s_exc + nd);  // [nd+1]
     unsigned char* keepB = keepA + nd + 1;                // [nd+1]
     __shared__ int s_M, s_nexc;
+    __shared__ int s_cc[kScanCells + 1];
     const int k = blockIdx.x + 2;                      // 1-based level
     const int prob = blockIdx.y, b = prob / p.nhemi, h = prob % p.nhemi;
     for (int j = p.jstart + threadIdx.x; j <= p.jend; j += blockDim.x) {
@@ -121,6 +131,26 @@ lwa_thresholds_kernel(ThrArgs p) {
     }
     for (int jj = threadIdx.x; jj <= nd + 1; jj += blockDim.x) p.nxt[pk * (nd + 2) + jj] = s_nxt[jj];
     if (threadIdx.x == 0) { p.meta[pk * 4 + 0] = M; p.meta[pk * 4 + 1] = ne; }
+    // search accelerator: cell[c] = number of thresholds in cells < c of a uniform grid over [thr_0, thr_{M-1}]
+    double lo = 0.0, inv = 0.0;
+    if (M > 0) {
+        lo = Q[s_rowof[0]];
+        const double hi = Q[s_rowof[M - 1]];
+        if (hi > lo) inv = (double)kScanCells / (hi - lo);
+        if (!(inv < 1e300)) inv = 0.0;  // overflow / NaN: every value falls in cell 0 and the search is a plain bisection
+    }
+    for (int c = threadIdx.x; c <= kScanCells; c += blockDim.x) s_cc[c] = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < M; t += blockDim.x) atomicAdd(&s_cc[scan_cell(Q[s_rowof[t]], lo, inv) + 1], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int c = 0; c <= kScanCells; ++c) { run += s_cc[c]; s_cc[c] = run; }
+        p.srch[pk * 2 + 0] = lo;
+        p.srch[pk * 2 + 1] = inv;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c <= kScanCells; c += blockDim.x) p.cell[pk * (kScanCells + 1) + c] = (short)s_cc[c];
 }
 
 __host__ __device__ inline int scan_pitch(int nd) { return ((nd - 2 + 15) / 16) * 16 + 2; }  // == 2 (mod 16)
@@ -129,7 +159,7 @@ static size_t scan_smem_bytes(int nd, bool has_nc) {
     const int ndp = scan_pitch(nd), narr = has_nc ? 4 : 3;
     size_t doubles = (size_t)2 * nd + (nd + 2) + (size_t)narr * kScanCols * ndp;
     size_t ints = (size_t)kScanCols * (nd + 2);
-    size_t shorts = (size_t)2 * kScanCols * ndp + nd + (nd + 2);
+    size_t shorts = (size_t)2 * kScanCols * ndp + nd + (nd + 2) + (kScanCells + 1);
     return doubles * 8 + ints * 4 + ((shorts * 2 + 7) / 8) * 8;
 }
 
@@ -164,6 +194,7 @@ lwa_scan_kernel(ScanArgs p) {
     short* s_perm = s_E + kScanCols * ndp;              // [C][ndp]
     short* s_rowof = s_perm + kScanCols * ndp;          // [nd]
     short* s_nxt = s_rowof + nd;                        // [nd+2]
+    short* s_cell = s_nxt + nd + 2;                     // [kScanCells+1]
 
     const int k = blockIdx.y + 2;                       // 1-based level
     const int prob = blockIdx.z, b = prob / p.nhemi, h = prob % p.nhemi;
@@ -183,6 +214,8 @@ lwa_scan_kernel(ScanArgs p) {
         s_cos[jj] = p.cosphi[jj];
         s_nxt[jj] = p.nxt[pk * (nd + 2) + jj];
     }
+    for (int c = tid; c <= kScanCells; c += blockDim.x) s_cell[c] = p.cell[pk * (kScanCells + 1) + c];
+    const double srch_lo = p.srch[pk * 2 + 0], srch_inv = p.srch[pk * 2 + 1];
     {
         const int col = tid % kScanCols, rr = tid / kScanCols;
         const bool colok = (i0 + col) < p.imax;
@@ -217,32 +250,68 @@ lwa_scan_kernel(ScanArgs p) {
     for (int r = lane; r < nd; r += 32) o_[r] = 0.0;
     __syncwarp();
 
-    // 1. E(jj) by binary search + bin counts of the displaced rows
-    int pow2 = 1;
-    while (pow2 * 2 <= M) pow2 *= 2;
+    // 1. E(jj) by binary search (four row chunks interleaved for ILP), rank of every displaced row inside its
+    //    bin (one __match_any_sync per chunk; chunks are visited in ascending row order, so a bin lists its rows
+    //    in ascending order and every sum below is reproducible bit for bit)
     unsigned long long ccyc = 0, canti = 0;
-    for (int r0 = 0; r0 < nd; r0 += 32) {
-        const int r = r0 + lane;
-        bool sc = false;
-        int e = 0;
-        if (r < nd) {
-            const double q = q_[r];
-            if (M > 0)
-                for (int step = pow2; step > 0; step >>= 1)
-                    if (e + step <= M && s_thr[e + step - 1] < q) e += step;
-            const int nx = s_nxt[r + 1];
-            E_[r] = (short)e;
-            if (e > nx) ccyc += (unsigned)(e - nx); else canti += (unsigned)(nx - e);
-            sc = (e != nx) && (e < M);
+    for (int r0 = 0; r0 < nd; r0 += 128) {
+        double q4[4];
+        int e4[4], b4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int r = r0 + 32 * c + lane;
+            q4[c] = (r < nd) ? q_[r] : 0.0;
+            const int cl = scan_cell(q4[c], srch_lo, srch_inv);
+            e4[c] = s_cell[cl];       // E lies in [cell[cl], cell[cl+1]]
+            b4[c] = s_cell[cl + 1];
         }
-        const unsigned mask = __match_any_sync(FULL, sc ? e : (0x4000 + lane));
-        if (sc && lane == (__ffs(mask) - 1)) cn[e] += __popc(mask);
-        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (e4[c] < b4[c]) {
+                    const int mid = (e4[c] + b4[c]) >> 1;
+                    if (s_thr[mid] < q4[c]) e4[c] = mid + 1; else b4[c] = mid;
+                }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            while (e4[c] < b4[c]) {
+                const int mid = (e4[c] + b4[c]) >> 1;
+                if (s_thr[mid] < q4[c]) e4[c] = mid + 1; else b4[c] = mid;
+            }
+        unsigned m4[4];
+        bool sc4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int r = r0 + 32 * c + lane;
+            sc4[c] = false;
+            if (r < nd) {
+                const int nx = s_nxt[r + 1], e = e4[c];
+                E_[r] = (short)e;
+                if (e > nx) ccyc += (unsigned)(e - nx); else canti += (unsigned)(nx - e);
+                sc4[c] = (e != nx) && (e < M);
+            }
+            m4[c] = __match_any_sync(FULL, sc4[c] ? e4[c] : (0x4000 + lane));
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (r0 + 32 * c < nd) {
+                if (sc4[c]) {
+                    const int leader = __ffs(m4[c]) - 1;
+                    int old = 0;
+                    if (lane == leader) { old = cn[e4[c]]; cn[e4[c]] = old + __popc(m4[c]); }
+                    old = __shfl_sync(m4[c], old, leader);
+                    pm[r0 + 32 * c + lane] = (short)(old + __popc(m4[c] & lt_mask));  // rank inside the bin (stash)
+                }
+                __syncwarp();
+            }
+        }
     }
-    // 2. exclusive scan of the counts -> bin starts
+    // 2. exclusive scan of the counts -> bin starts; cn[M] = number of displaced rows
     {
         int carry = 0;
-        for (int t0 = 0; t0 < M; t0 += 32) {
+        for (int t0 = 0; t0 <= M; t0 += 32) {
             const int t = t0 + lane;
             const int v = (t < M) ? cn[t] : 0;
             int incl = v;
@@ -251,30 +320,30 @@ lwa_scan_kernel(ScanArgs p) {
                 const int n = __shfl_up_sync(FULL, incl, d);
                 if (lane >= d) incl += n;
             }
-            if (t < M) cn[t] = carry + incl - v;
+            if (t <= M) cn[t] = carry + incl - v;
             carry += __shfl_sync(FULL, incl, 31);
         }
     }
     __syncwarp();
-    // 3. placement in ascending row order; afterwards cn[t] is the END of bin t
-    for (int r0 = 0; r0 < nd; r0 += 32) {
-        const int r = r0 + lane;
-        bool sc = false;
-        int e = 0;
-        if (r < nd) {
-            e = E_[r];
-            sc = (e != s_nxt[r + 1]) && (e < M);
-        }
-        const unsigned mask = __match_any_sync(FULL, sc ? e : (0x4000 + lane));
-        if (sc) {
-            const int leader = __ffs(mask) - 1;
-            int old = 0;
-            if (lane == leader) { old = cn[e]; cn[e] = old + __popc(mask); }
-            old = __shfl_sync(mask, old, leader);
-            pm[old + __popc(mask & lt_mask)] = (short)r;
+    // 3. placement: sorted position = bin start + rank.  The ranks were stashed in pm[row]; all of them are read
+    //    into registers before any sorted slot is written (a slot may alias another row's stash).
+    {
+        int dst[kScanRMax];
+#pragma unroll
+        for (int c = 0; c < kScanRMax; ++c) {
+            const int r = 32 * c + lane;
+            dst[c] = -1;
+            if (r < nd) {
+                const int e = E_[r];
+                if (e != s_nxt[r + 1] && e < M) dst[c] = cn[e] + pm[r];
+            }
         }
         __syncwarp();
+#pragma unroll
+        for (int c = 0; c < kScanRMax; ++c)
+            if (dst[c] >= 0) pm[dst[c]] = (short)(32 * c + lane);
     }
+    __syncwarp();
 
     // 4. running set sums: lane owns thresholds t = lane*R .. lane*R + R-1
     int R = (M + 31) / 32;
@@ -299,7 +368,7 @@ lwa_scan_kernel(ScanArgs p) {
                 }
             }
             // rows leaving (cyclonic) / entering (anticyclonic) at t: E(jj) == t
-            for (int x = t ? cn[t - 1] : 0, xe = cn[t]; x < xe; ++x) {
+            for (int x = cn[t], xe = cn[t + 1]; x < xe; ++x) {
                 const int r = pm[x];
                 const double q = q_[r], u = u_[r], cs = s_cos[r + 1];
                 if (t > s_nxt[r + 1]) { S1c -= q * cs; S2c -= cs; } else { S1a += q * cs; S2a += cs; }
@@ -430,22 +499,24 @@ lwa_exception_rows_kernel(ScanArgs p) {
 // Scratch of the threshold tables for nprob problems.
 struct ScanTables {
     DeviceScratch<double> dbl;   // thr, urt
-    DeviceScratch<short> sh;     // rowof, nxt, exc
+    DeviceScratch<short> sh;     // rowof, nxt, exc, cell
     DeviceScratch<int> meta;
     int alloc(int nprob, int nd, int kmax, cudaStream_t st) {
         int rc;
         const size_t pk = (size_t)nprob * kmax;
-        if ((rc = dbl.alloc(pk * nd * 2, st))) return rc;
-        if ((rc = sh.alloc(pk * ((size_t)2 * nd + nd + 2), st))) return rc;
+        if ((rc = dbl.alloc(pk * nd * 2 + pk * 2, st))) return rc;
+        if ((rc = sh.alloc(pk * ((size_t)2 * nd + nd + 2 + kScanCells + 1), st))) return rc;
         if ((rc = meta.alloc(pk * 4, st, true))) return rc;
         return 0;
     }
     void bind(ThrArgs& t, ScanArgs& s, int nprob, int nd, int kmax) {
         const size_t pk = (size_t)nprob * kmax;
-        t.thr = dbl.d; t.urt = dbl.d + pk * nd;
+        t.thr = dbl.d; t.urt = dbl.d + pk * nd; t.srch = dbl.d + pk * nd * 2;
         t.rowof = sh.d; t.exc = sh.d + pk * nd; t.nxt = sh.d + pk * nd * 2;
+        t.cell = sh.d + pk * ((size_t)2 * nd + nd + 2);
         t.meta = meta.d;
         s.thr = t.thr; s.urt = t.urt; s.rowof = t.rowof; s.exc = t.exc; s.nxt = t.nxt; s.meta = t.meta;
+        s.cell = t.cell; s.srch = t.srch;
     }
 };
 

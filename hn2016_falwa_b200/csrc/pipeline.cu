@@ -168,7 +168,7 @@ struct FusedFluxArgs {
 // blockIdx.z = snapshot * nhemi + hemisphere (0 = north, 1 = south).  When both hemispheres are computed the
 // southern one owns the equator row (the reference writes north first, south second: data_storage.py:42-62).
 template <bool BRUTE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, BRUTE ? 2 : 3)
 fused_flux_kernel(FusedFluxArgs p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;  // hemispheric row 1..nd
