@@ -107,6 +107,19 @@ __device__ __forceinline__ double ordered_to_f64(unsigned long long u) {
     return __longlong_as_double((long long)u);
 }
 
+// Area-analysis bin of a value: 1 + int((qmax - q) / dq), clamped to [1, nb]  (compute_reference_states.f90:82-86).
+// The quotient is first formed with the reciprocal (one DMUL instead of a ~40-instruction DDIV sequence); both
+// roundings are within 2 ulp of the true quotient (|t| <= nb), so they can truncate differently only when the
+// product lies within ~1e-12 of an integer — then, and only then, the exact division decides.  Bin assignment is
+// therefore identical to the reference's arithmetic for every input.
+__device__ __forceinline__ int area_bin(double qmax, double q, double dq, double rdq, int nb) {
+    const double x = qmax - q;
+    double t = x * rdq;
+    const double fr = t - floor(t);
+    if (!(fr > 1e-9 && fr < 1. - 1e-9)) t = x / dq;
+    return max(1, min(nb, 1 + (int)t));
+}
+
 // Small stream-ordered device buffer filled from a host vector (tables of a few KB).
 struct DeviceTable {
     double* d = nullptr;

@@ -64,12 +64,14 @@ area_hist3_kernel(int nlon, int nlat, int kmax, int nb, int with_avort, const do
     const double dqp = (pmax - pmin) / (double)(nb - 1);
     const double smax = -pmin;                      // southern frame: q' = -pv, max' = -min
     const double dqs = (smax - (-pmax)) / (double)(nb - 1);
+    const double rdqp = 1. / dqp, rdqs = 1. / dqs;
     double vmax = 0., dqv = 1.;
     if (with_avort) {
         vmax = ordered_to_f64(ext[(kmax + k) * 2 + 0]);
         const double vmin = ordered_to_f64(ext[(kmax + k) * 2 + 1]);
         dqv = (vmax - vmin) / (double)(nb - 1);
     }
+    const double rdqv = 1. / dqv;
     const int j0 = blockIdx.x * rows_per_block, j1 = min(nlat, j0 + rows_per_block);
     const int run = 8;
     const int runs_per_row = (nlon + run - 1) / run;
@@ -86,16 +88,16 @@ area_hist3_kernel(int nlon, int nlat, int kmax, int nb, int with_avort, const do
         double an = 0, qn = 0, as = 0, qs = 0, av = 0, qv = 0;
         for (int i = i0; i < i1; ++i) {
             const double q = pv[lev + (size_t)j * nlon + i];
-            int ind = max(1, min(nb, 1 + (int)((pmax - q) / dqp)));
+            int ind = area_bin(pmax, q, dqp, rdqp, nb);
             if (ind != cn) { hist_flush(hN, nb, cn, an, qn); cn = ind; an = 0; qn = 0; }
             an += daj; qn += daj * q;
             const double qq = -q;
-            ind = max(1, min(nb, 1 + (int)((smax - qq) / dqs)));
+            ind = area_bin(smax, qq, dqs, rdqs, nb);
             if (ind != cs) { hist_flush(hS, nb, cs, as, qs); cs = ind; as = 0; qs = 0; }
             as += daj; qs += daj * qq;
             if (with_avort) {
                 const double w = avort[lev + (size_t)j * nlon + i];
-                ind = max(1, min(nb, 1 + (int)((vmax - w) / dqv)));
+                ind = area_bin(vmax, w, dqv, rdqv, nb);
                 if (ind != cv) { hist_flush(hV, nb, cv, av, qv); cv = ind; av = 0; qv = 0; }
                 av += daj; qv += daj * w;
             }
@@ -160,6 +162,7 @@ struct FusedFluxArgs {
     const double *qref_cu, *uref_st, *tref_st;  // [b][k][nlat]
     const double *prof;                         // [b][4][kmax]
     const double *cosphi, *sinphi, *aaw, *ep11a, *vw;
+    const double *f11;                          // BRUTE = false: [b][2][kmax] = (R/H) e^{-kappa z/H} 2 dz / (tg(k+1)-tg(k-1))
     double *lwa, *out2d;
 };
 
@@ -203,10 +206,13 @@ fused_flux_kernel(FusedFluxArgs p) {
     for (int k = 2; k <= kmax; ++k) {  // 1-based level
         const size_t lev = (size_t)(k - 1) * plane;
         const double w = p.vw[k - 1];
-        s_u = s_u + uu[lev + o2] * w * p.dc;
+        const double wd = w * p.dc;
+        // numpy evaluates (x * w) * dc; the scan path folds the two weights (one rounding less per term)
+        auto acc = [&](double sum, double x) -> double { return BRUTE ? sum + x * w * p.dc : sum + x * wd; };
+        s_u = acc(s_u, uu[lev + o2]);
         {   // flux_vector_phi_baro = vertical average of -((u - uref) * v) * clat  (oopinterface.py:964-982)
             const double x = -(((uu[lev + o2] - uref[(size_t)(k - 1) * nlat + g]) * vv[lev + o2]) * cl);
-            s_fphi = s_fphi + x * w * p.dc;
+            s_fphi = acc(s_fphi, x);
         }
         if (k == kmax) break;
         double a1 = 0, a2 = 0, ncf = 0, u2 = 0, e1 = 0, e2 = 0, e3 = 0, x_ua1 = 0;
@@ -248,8 +254,12 @@ fused_flux_kernel(FusedFluxArgs p) {
             e1 = -0.5 * ((uu0 - ur) * (uu0 - ur));
             e1 = e1 + 0.5 * (vv0 * vv0);
             double ep11 = 0.5 * ((pt0 - tr) * (pt0 - tr));
-            ep11 = ep11 * p.rrh * p.ep11a[k - 1];
-            ep11 = ep11 * 2. * p.dz / (tg[k] - tg[k - 2]);
+            if (BRUTE) {
+                ep11 = ep11 * p.rrh * p.ep11a[k - 1];
+                ep11 = ep11 * 2. * p.dz / (tg[k] - tg[k - 2]);
+            } else {
+                ep11 = ep11 * p.f11[((size_t)b * 2 + (south ? 0 : 1)) * kmax + (k - 1)];
+            }
             e1 = e1 - ep11;
             const double cosp = p.cosphi[j + 1], cosm = p.cosphi[j - 1], sin0 = p.sinphi[j];
             e1 = e1 * cphi0;
@@ -276,14 +286,14 @@ fused_flux_kernel(FusedFluxArgs p) {
             e3 = (uu[r0] - uref[(size_t)(k - 1) * nlat + grow(jb + 1)]) * p.cosjbm1 * p.cosjbm1 * (sg * vv[r0]);
             if (jb == 0) wk = (k >= 3) ? p.vw[k - 2] : 0.0;  // aliased into level k-1; level 1 is not averaged
         }
-        s_a1 = s_a1 + a1 * w * p.dc;
-        s_a2 = s_a2 + a2 * w * p.dc;
-        s_ua1 = s_ua1 + x_ua1 * w * p.dc;
-        s_ua2 = s_ua2 + u2 * w * p.dc;
-        s_ep1 = s_ep1 + e1 * w * p.dc;
-        s_ep2 = s_ep2 + e2 * wk * p.dc;
-        s_ep3 = s_ep3 + e3 * wk * p.dc;
-        s_nc = s_nc + ncf * w * p.dc;
+        s_a1 = acc(s_a1, a1);
+        s_a2 = acc(s_a2, a2);
+        s_ua1 = acc(s_ua1, x_ua1);
+        s_ua2 = acc(s_ua2, u2);
+        s_ep1 = acc(s_ep1, e1);
+        s_ep2 = BRUTE ? s_ep2 + e2 * wk * p.dc : s_ep2 + e2 * (wk * p.dc);
+        s_ep3 = BRUTE ? s_ep3 + e3 * wk * p.dc : s_ep3 + e3 * (wk * p.dc);
+        s_nc = acc(s_nc, ncf);
     }
     out[(size_t)O_ASTAR1 * plane + o2] = s_a1;
     out[(size_t)O_ASTAR2 * plane + o2] = s_a2;
@@ -300,10 +310,149 @@ fused_flux_kernel(FusedFluxArgs p) {
     out[(size_t)O_FPHI * plane + o2] = s_fphi;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Column walk of the scan path (method 0): everything compute_lwa_and_barotropic_fluxes needs besides the LWA
+// pieces a1 / a2 / ua2 / ncforce3d, which lwa_scan_kernel has already written.  One thread per (lon, hemispheric
+// row) walks the levels upward (the vertical sums accumulate in numpy's order, oopinterface.py:405-420) with the
+// loads of level k+1 issued before level k is evaluated (register double buffering: the kernel is bound by DRAM
+// latency otherwise).  The eddy-momentum terms ep2(j) / ep3(j) are the same pointwise quantity
+// G = (u - uref) cos^2 (v) at rows j+1 / j-1 (compute_flux_dirinv.f90:152-157), so each thread sums G for its own
+// row only (hs) and baro_post_kernel picks the neighbours; the two rows with special rules (the first row's
+// out-of-bounds uref and the boundary row jb, :173-178) are evaluated directly.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2)
+flux_column_kernel(FusedFluxArgs p, double* __restrict__ hs /* [b][nhemi][nd][imax] */) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;  // hemispheric row 1..nd
+    const int b = blockIdx.z / p.nhemi, hidx = blockIdx.z % p.nhemi;
+    const bool south = hidx == 1;
+    if (i >= p.imax || j > p.nd) return;
+    const bool skip_out = (j == 1 && p.nhemi == 2 && !south);  // the southern launch owns the equator row
+    const int nd = p.nd, nlat = p.nlat, imax = p.imax, kmax = p.kmax, jb = p.jb;
+    const size_t plane = (size_t)nlat * imax;
+    const size_t f3 = (size_t)b * plane * kmax;
+    const double *uu = p.uu + f3, *vv = p.vv + f3, *pt = p.pt + f3;
+    const double *sa1 = p.sa1 + f3, *sa2 = p.sa2 + f3, *su2 = p.su2 + f3;
+    const double* snc = p.has_ncforce ? p.snc + f3 : nullptr;
+    const double* uref = p.uref_st + (size_t)b * kmax * nlat;
+    const double* tref = p.tref_st + (size_t)b * kmax * nlat;
+    const double* tg = p.prof + (size_t)b * 4 * kmax + (south ? 0 : kmax);  // tn0 north / ts0 south
+    const double* f11 = p.f11 + ((size_t)b * 2 + (south ? 0 : 1)) * kmax;
+    double* lwa = p.lwa + f3;
+    double* out = p.out2d + (size_t)b * O_COUNT * plane;
+    const double sg = south ? -1.0 : 1.0;
+    auto grow = [&](int jj) -> int { return south ? (nd - jj) : (nd - 2 + jj); };  // 0-based global row
+    const int g = grow(j);
+    const int jstart = jb + 1, jend = nd - 1;
+    const bool in_range = (j >= jstart && j <= jend);
+    const bool first = (j == jstart);                      // ep3 needs the reference's uref(0,k) == uref(jd,k-1)
+    const bool brow = (jb >= 1) ? (j == jb) : (j == nd);   // boundary row jb, or its alias (i,nd,k-1) when jb = 0
+    const bool own_g = (j >= jstart);                      // rows whose G sum some neighbour needs
+    const double c0 = p.cosphi[j], cm = p.cosphi[j - 1], cl = p.clat[g];
+    const size_t o2 = (size_t)g * imax + i;
+    const size_t om = (size_t)grow(j - 1) * imax + i;                       // row j-1 (first row only)
+    const size_t r1 = (size_t)grow(jb + 2) * imax + i, r0 = (size_t)grow(jb + 1) * imax + i;  // boundary row only
+    const int gr1 = grow(jb + 2), gr0 = grow(jb + 1), gnd = grow(nd);
+
+    struct Lv { double u0, v0, t0, a1, a2, u2, nc, ur, tr, um, vm, urm, bu1, bv1, bu0, bv0, bur1, bur0; };
+    auto fetch = [&](int k) -> Lv {  // 1-based level k (2..kmax)
+        Lv L;
+        const size_t lev = (size_t)(k - 1) * plane;
+        L.u0 = uu[lev + o2]; L.v0 = vv[lev + o2];
+        L.ur = uref[(size_t)(k - 1) * nlat + g];
+        L.t0 = L.a1 = L.a2 = L.u2 = L.nc = L.tr = L.um = L.vm = L.urm = 0.0;
+        L.bu1 = L.bv1 = L.bu0 = L.bv0 = L.bur1 = L.bur0 = 0.0;
+        if (k < kmax) {
+            if (in_range) {
+                L.t0 = pt[lev + o2]; L.tr = tref[(size_t)(k - 1) * nlat + g];
+                L.a1 = sa1[lev + o2]; L.a2 = sa2[lev + o2]; L.u2 = su2[lev + o2];
+                if (snc) L.nc = snc[lev + o2];
+            }
+            if (first) {
+                L.um = uu[lev + om]; L.vm = vv[lev + om];
+                L.urm = (j - jb - 1 >= 1) ? uref[(size_t)(k - 1) * nlat + grow(j - 1)] : uref[(size_t)(k - 2) * nlat + gnd];
+            }
+            if (brow) {
+                L.bu1 = uu[lev + r1]; L.bv1 = vv[lev + r1]; L.bu0 = uu[lev + r0]; L.bv0 = vv[lev + r0];
+                L.bur1 = uref[(size_t)(k - 1) * nlat + gr1]; L.bur0 = uref[(size_t)(k - 1) * nlat + gr0];
+            }
+        }
+        return L;
+    };
+
+    double s_a1 = 0, s_a2 = 0, s_ua1 = 0, s_ua2 = 0, s_ep1 = 0, s_nc = 0, s_u = 0, s_fphi = 0, s_g = 0;
+    double s_e2 = 0, s_e3 = 0, ep4 = 0;   // directly evaluated ep2 / ep3 of the two special rows
+    if (!skip_out) {
+        lwa[o2] = 0.0;
+        lwa[(size_t)(kmax - 1) * plane + o2] = 0.0;
+    }
+    if (in_range) {  // low-level meridional heat flux from levels 1 and 2 (compute_flux_dirinv.f90:160-171)
+        const double ep41 = 2. * p.om * p.sinphi[j] * c0 * p.dz / p.prefac;
+        const double ep42 = p.ep42fac * (sg * vv[plane + o2]) * (pt[plane + o2] - tref[nlat + g]) / (tg[2] - tg[0]);
+        double ep43 = (sg * vv[o2]) * (pt[o2] - tref[g]);
+        ep43 = 0.5 * ep43 / (tg[1] - tg[0]);
+        ep4 = ep41 * (ep42 + ep43);
+    }
+    Lv cur = fetch(2);
+    for (int k = 2; k <= kmax; ++k) {
+        Lv nxt = cur;
+        if (k < kmax) nxt = fetch(k + 1);
+        const double w = p.vw[k - 1];
+        const double wd = w * p.dc;
+        s_u = s_u + cur.u0 * wd;
+        s_fphi = s_fphi + (-(((cur.u0 - cur.ur) * cur.v0) * cl)) * wd;
+        if (k < kmax) {
+            const size_t lev = (size_t)(k - 1) * plane;
+            if (own_g) s_g = s_g + ((cur.u0 - cur.ur) * c0 * c0 * (sg * cur.v0)) * wd;
+            double e1 = 0, x_ua1 = 0;
+            if (in_range) {
+                const double vv0 = sg * cur.v0;
+                x_ua1 = cur.ur * (cur.a1 + cur.a2);
+                e1 = -0.5 * ((cur.u0 - cur.ur) * (cur.u0 - cur.ur));
+                e1 = e1 + 0.5 * (vv0 * vv0);
+                e1 = e1 - 0.5 * ((cur.t0 - cur.tr) * (cur.t0 - cur.tr)) * f11[k - 1];
+                e1 = e1 * c0;
+            }
+            if (!skip_out) lwa[lev + o2] = fabs(cur.a1 + cur.a2);
+            s_a1 = s_a1 + cur.a1 * wd;
+            s_a2 = s_a2 + cur.a2 * wd;
+            s_ua1 = s_ua1 + x_ua1 * wd;
+            s_ua2 = s_ua2 + cur.u2 * wd;
+            s_ep1 = s_ep1 + e1 * wd;
+            s_nc = s_nc + cur.nc * wd;
+            if (first) s_e3 = s_e3 + ((cur.um - cur.urm) * cm * cm * (sg * cur.vm)) * wd;
+            if (brow) {  // compute_flux_dirinv.f90:173-178
+                double wk = wd;
+                if (jb == 0) wk = (k >= 3) ? p.vw[k - 2] * p.dc : 0.0;  // aliased into level k-1; level 1 is not averaged
+                s_e2 = s_e2 + ((cur.bu1 - cur.bur1) * p.cosjb * p.cosjb * (sg * cur.bv1)) * wk;
+                s_e3 = s_e3 + ((cur.bu0 - cur.bur0) * p.cosjbm1 * p.cosjbm1 * (sg * cur.bv0)) * wk;
+            }
+        }
+        cur = nxt;
+    }
+    hs[(((size_t)b * p.nhemi + hidx) * nd + (j - 1)) * imax + i] = s_g;
+    if (skip_out) return;
+    out[(size_t)O_ASTAR1 * plane + o2] = s_a1;
+    out[(size_t)O_ASTAR2 * plane + o2] = s_a2;
+    out[(size_t)O_LWA * plane + o2] = s_a1 + s_a2;
+    out[(size_t)O_UA1 * plane + o2] = s_ua1;
+    out[(size_t)O_UA2 * plane + o2] = s_ua2;
+    out[(size_t)O_EP1 * plane + o2] = s_ep1;
+    // hemispheric-frame ep2 / ep3 of the special rows; baro_post_kernel fills the others from hs and applies the
+    // southern swap + sign (oopinterface.py:790-792)
+    out[(size_t)O_EP2 * plane + o2] = s_e2;
+    out[(size_t)O_EP3 * plane + o2] = s_e3;
+    out[(size_t)O_EP4 * plane + o2] = ep4;
+    out[(size_t)O_NCF * plane + o2] = south ? -s_nc : s_nc;
+    out[(size_t)O_UBARO * plane + o2] = s_u;
+    out[(size_t)O_FPHI * plane + o2] = s_fphi;
+}
+
 // barotropic post-processing (oopinterface.py:906-944, :964-982; utilities.py:189-233)
 __global__ void __launch_bounds__(256)
 baro_post_kernel(int nlon, int nlat, double a, double dphi, double dlambda, const double* __restrict__ clat,
-                 double* __restrict__ out2d) {
+                 double* __restrict__ out2d, const double* __restrict__ hs, int nhemi, int nd, int jb) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y, b = blockIdx.z;
     if (i >= nlon) return;
@@ -311,6 +460,26 @@ baro_post_kernel(int nlon, int nlat, double a, double dphi, double dlambda, cons
     double* out = out2d + (size_t)b * O_COUNT * plane;
     const size_t o = (size_t)j * nlon + i;
     const double cl = clat[j];
+    if (hs) {
+        // scan path: ep2(jh) = G(jh+1), ep3(jh) = G(jh-1) from the own-row sums of flux_column_kernel; the first row's
+        // ep3 and the boundary row are already in place.  South: swapped and negated (oopinterface.py:790-792).
+        const bool south = (nhemi == 2) && (j <= nd - 1);
+        const bool covered = south || (j >= nd - 1);
+        if (covered) {
+            const int jh = south ? (nd - j) : (j - nd + 2);   // hemispheric row 1..nd
+            const double* H = hs + (((size_t)b * nhemi + (south ? 1 : 0)) * nd) * nlon + i;
+            const int jstart = jb + 1, jend = nd - 1;
+            const bool brow = (jb >= 1) ? (jh == jb) : (jh == nd);
+            double e2 = out[(size_t)O_EP2 * plane + o], e3 = out[(size_t)O_EP3 * plane + o];
+            if (!brow) {
+                e2 = (jh >= jstart && jh <= jend) ? H[(size_t)jh * nlon] : 0.0;             // row jh+1
+                if (jh > jstart && jh <= jend) e3 = H[(size_t)(jh - 2) * nlon];               // row jh-1
+                else if (jh != jstart) e3 = 0.0;
+            }
+            out[(size_t)O_EP2 * plane + o] = south ? -e3 : e2;
+            out[(size_t)O_EP3 * plane + o] = south ? -e2 : e3;
+        }
+    }
     out[(size_t)O_DIVEMF * plane + o] = (out[(size_t)O_EP2 * plane + o] - out[(size_t)O_EP3 * plane + o]) / (2 * a * dphi * cl);
     auto zsum = [&](int ii) -> double {
         const size_t oo = (size_t)j * nlon + ii;
@@ -321,6 +490,135 @@ baro_post_kernel(int nlon, int nlat, double a, double dphi, double dlambda, cons
     if (fabs(cl) > 1.e-5) zd = zd * (-1. / (a * cl * 2. * dlambda));
     out[(size_t)O_CONV * plane + o] = zd;
     out[(size_t)O_FLAMBDA * plane + o] = zsum(i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reference-state profiles of one (level, hemisphere, snapshot): cumulative area/circulation of the PV histogram
+// and its inversion at the equivalent latitudes (qref, cref; ckref from the absolute-vorticity histogram for
+// NHN22), the zonal-mean circulation cbar, the normalisation of qref, and the hemispheric ubar / tbar rows
+// (compute_reference_states.f90:60-130, compute_qref_and_fawa_first.f90:44-160).  Same arithmetic and summation
+// order as qref_invert_kernel + cbar_normalise_kernel + extract_rows_kernel + tb_mean_kernel, one launch.
+// work layout per (b, hs): qref, cref, cbar, ubar, tbar, fjk [nd*kmax each]; uref, tref [jd*kmax]; tb[kmax]; uz[nd]
+// ---------------------------------------------------------------------------------------------
+struct LevelArgs {
+    int kind, kmax, nlat, nd, nb;
+    double a, dphi, pi;
+    const double *zm, *hist, *alat, *cosmid, *norm, *cosw;
+    const unsigned long long* ext;
+    double *work, *ckref;
+    size_t per, njk, njd;
+};
+
+__global__ void __launch_bounds__(256)
+refstate_level_kernel(LevelArgs p) {
+    extern __shared__ double sh[];
+    const int nb = p.nb, nd = p.nd, nlat = p.nlat, kmax = p.kmax;
+    double* aan = sh;            // [nb]
+    double* ccn = aan + nb;      // [nb]
+    double* aav = ccn + nb;      // [nb]  (vorticity)
+    double* ccv = aav + nb;      // [nb]
+    double* qrow = ccv + nb;     // [nd]
+    double* crow = qrow + nd;    // [nd]
+    double* term = crow + nd;    // [nd]
+    const int k = blockIdx.x, hs = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
+    const double sgn = hs == 0 ? 1.0 : -1.0;
+    const bool interior = (k >= 1 && k <= kmax - 2);
+    const bool do_vort = (p.kind != 0) && hs == 0 && interior;
+    const double* zmb = p.zm + (size_t)b * 3 * kmax * nlat;
+    double* W = p.work + ((size_t)b * 2 + hs) * p.per;
+    double *qref = W, *cref = W + p.njk, *cbar = W + 2 * p.njk, *ubar = W + 3 * p.njk, *tbar = W + 4 * p.njk;
+    auto grow = [&](int j) -> int { return hs == 0 ? (nd - 1 + j) : (nlat - 1 - (nd - 1 + j)); };  // 0-based hemispheric -> global
+    // hemispheric zonal-mean rows (all levels)
+    for (int j = tid; j < nd; j += blockDim.x) {
+        ubar[(size_t)k * nd + j] = zmb[((size_t)1 * kmax + k) * nlat + grow(j)];
+        tbar[(size_t)k * nd + j] = zmb[((size_t)2 * kmax + k) * nlat + grow(j)];
+    }
+    if (p.kind == 0) {  // hemispheric-mean theta of the SOR routine (compute_reference_states.f90:60-65)
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0., w = 0.;
+            for (int j = 0; j < nd; ++j) { s = s + p.cosw[j] * tbar[(size_t)k * nd + j]; w = w + p.cosw[j]; }
+            W[6 * p.njk + 2 * p.njd + k] = s / w;
+        }
+    }
+    if (!interior) return;
+    const unsigned long long* extb = p.ext + (size_t)b * 2 * kmax * 2;
+    const double* histb = p.hist + (size_t)b * 3 * kmax * 2 * nb;
+    double qmax = ordered_to_f64(extb[k * 2 + 0]), qmin = ordered_to_f64(extb[k * 2 + 1]);
+    if (sgn < 0) { const double t = qmax; qmax = -qmin; qmin = -t; }
+    const double dq = (qmax - qmin) / (double)(nb - 1);
+    double vmax = 0., dqv = 1.;
+    if (do_vort) {
+        vmax = ordered_to_f64(extb[(kmax + k) * 2 + 0]);
+        const double vmin = ordered_to_f64(extb[(kmax + k) * 2 + 1]);
+        dqv = (vmax - vmin) / (double)(nb - 1);
+    }
+    {   // cumulative sums in the reference's order (bin 1 is never added)
+        const double* an = histb + ((size_t)hs * kmax + k) * 2 * nb;
+        const double* av = histb + ((size_t)2 * kmax + k) * 2 * nb;
+        for (int t = tid; t < nb; t += blockDim.x) {
+            aan[t] = an[t]; ccn[t] = an[nb + t];
+            if (do_vort) { aav[t] = av[t]; ccv[t] = av[nb + t]; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double a = 0., c = 0.;
+            aan[0] = 0.; ccn[0] = 0.;
+            for (int nn = 1; nn < nb; ++nn) { a = a + aan[nn]; c = c + ccn[nn]; aan[nn] = a; ccn[nn] = c; }
+        }
+        if (tid == 32 && do_vort) {
+            double a = 0., c = 0.;
+            aav[0] = 0.; ccv[0] = 0.;
+            for (int nn = 1; nn < nb; ++nn) { a = a + aav[nn]; c = c + ccv[nn]; aav[nn] = a; ccv[nn] = c; }
+        }
+        __syncthreads();
+    }
+    for (int j = tid; j < nd; j += blockDim.x) {
+        double qv = 0., cv = 0., kv = 0.;
+        if (j < nd - 1) {
+            const double x = p.alat[j];
+            int lo = 0, hi = nb;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (aan[mid] <= x) lo = mid + 1; else hi = mid; }
+            if (lo >= 1 && lo <= nb - 1) {
+                const double a0 = aan[lo - 1], a1 = aan[lo];
+                const double dd = (x - a0) / (a1 - a0);
+                const double qn0 = qmax - dq * (double)(lo - 1), qn1 = qmax - dq * (double)lo;
+                qv = qn0 * (1. - dd) + qn1 * dd;
+                cv = ccn[lo - 1] * (1. - dd) + ccn[lo] * dd;
+            }
+            if (do_vort) {
+                lo = 0; hi = nb;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (aav[mid] <= x) lo = mid + 1; else hi = mid; }
+                if (lo >= 1 && lo <= nb - 1) {
+                    const double a0 = aav[lo - 1], a1 = aav[lo];
+                    const double dd = (x - a0) / (a1 - a0);
+                    kv = ccv[lo - 1] * (1. - dd) + ccv[lo] * dd;
+                }
+            }
+        } else {
+            qv = qmax;
+        }
+        qrow[j] = qv;
+        crow[j] = cv;
+        if (do_vort) p.ckref[(size_t)b * p.njk + (size_t)k * nd + j] = kv;
+        // cbar increment of row j (added when marching from j+1 down to j)
+        if (j < nd - 1) {
+            const double qb1 = sgn * zmb[(size_t)k * nlat + grow(j + 1)], qb0 = sgn * zmb[(size_t)k * nlat + grow(j)];
+            term[j] = 0.5 * (qb1 + qb0) * p.a * p.dphi * 2. * p.pi * p.a * p.cosmid[j];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double c = 0.0;
+        cbar[(size_t)k * nd + nd - 1] = 0.0;
+        for (int j = nd - 2; j >= 0; --j) { c = c + term[j]; cbar[(size_t)k * nd + j] = c; }
+    }
+    for (int j = tid; j < nd; j += blockDim.x) {
+        cref[(size_t)k * nd + j] = crow[j];
+        if (j >= 1) qrow[j] = qrow[j] / p.norm[j];
+    }
+    __syncthreads();
+    for (int j = tid; j < nd; j += blockDim.x) qref[(size_t)k * nd + j] = (j == 0) ? 2. * qrow[1] - qrow[2] : qrow[j];
 }
 
 // small helpers -------------------------------------------------------------------------------
@@ -506,27 +804,40 @@ extern "C" int falwa_b200_theta_hemispheric_means(const falwa_plan* P, int batch
 }
 
 // vertical interpolation + QGPV.  profiles_host [batch][4][kmax] = t0_s, t0_n, stat_s, stat_n at `height`.
+// zm [batch][3][kmax][nlat] / ext (uint64 [batch][2][kmax][2]), both optional: zonal means of qgpv, u, theta and the
+// per-level extrema of qgpv and avort, produced on the fly for falwa_b200_reference_states.
 extern "C" int falwa_b200_interpolate_fields(const falwa_plan* P, int batch, const double* u_in, const double* v_in,
                                              const double* t_in, int already_on_height_grid,
                                              const double* profiles_host, double* u, double* v, double* theta,
-                                             double* avort, double* qgpv, void* stream) {
+                                             double* avort, double* qgpv, double* zm, void* ext, void* stream) {
     if (!P || !u_in || !v_in || !t_in || !profiles_host || !u || !v || !theta || !avort || !qgpv) return FALWA_ERR_NULL;
     if (batch < 1) return FALWA_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const double* d = P->d_tab;
+    const int kmax = P->kmax;
     int rc;
     if (!already_on_height_grid) {
-        if ((rc = interp_launch(P->nlon, P->nlat, P->nlev, P->kmax, batch, u_in, v_in, t_in, P->d_lo, d + P->o_whi,
+        if ((rc = interp_launch(P->nlon, P->nlat, P->nlev, kmax, batch, u_in, v_in, t_in, P->d_lo, d + P->o_whi,
                                 d + P->o_wlo, d + P->o_fac, u, v, theta, st)))
             return rc;
     }
-    DeviceScratch<double> prof;
-    if ((rc = prof.alloc((size_t)batch * 4 * P->kmax, st))) return rc;
-    FALWA_CUDA_TRY(cudaMemcpyAsync(prof.d, profiles_host, sizeof(double) * (size_t)batch * 4 * P->kmax,
-                                   cudaMemcpyHostToDevice, st));
+    // profiles + reciprocal static stability: [batch][6][kmax]
+    std::vector<double> hp((size_t)batch * 6 * kmax);
+    for (int b = 0; b < batch; ++b) {
+        const double* src = profiles_host + (size_t)b * 4 * kmax;
+        double* dst = hp.data() + (size_t)b * 6 * kmax;
+        for (int t = 0; t < 4 * kmax; ++t) dst[t] = src[t];
+        for (int t = 0; t < 2 * kmax; ++t) dst[4 * kmax + t] = 1. / src[2 * kmax + t];
+    }
+    DeviceTable prof;
+    if ((rc = prof.upload(hp, st))) return rc;
+    DeviceScratch<double> part;
+    if (zm && ext) {
+        if ((rc = part.alloc((size_t)batch * 3 * kmax * P->nlat * ceil_div(P->nlon, 32), st))) return rc;
+    }
     const int jdsplit = (P->kind == 0) ? P->nlat : P->nd;  // NHN22: rows j <= equator use the southern profile
-    return qgpv_launch(P->kind == 0 ? 0 : 1, P->nlon, P->nlat, P->kmax, jdsplit, batch, u, v, theta, d + P->o_qg, prof.d,
-                       qgpv, avort, st);
+    return qgpv_launch(P->kind == 0 ? 0 : 1, P->nlon, P->nlat, kmax, jdsplit, batch, u, v, theta, d + P->o_qg, prof.d,
+                       qgpv, avort, st, 1, zm, (unsigned long long*)ext, part.d);
 }
 
 // reference states of both hemispheres -> global-latitude storage [batch][kmax][nlat]
@@ -535,7 +846,8 @@ extern "C" int falwa_b200_interpolate_fields(const falwa_plan* P, int batch, con
 extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const double* qgpv, const double* u,
                                            const double* theta, const double* avort, const double* profiles_host,
                                            int north_only, double* qref_st, double* qref_cu, double* uref_st,
-                                           double* ptref_st, int* num_of_iter_host, void* stream) {
+                                           double* ptref_st, int* num_of_iter_host, const double* zm_in,
+                                           const void* ext_in, void* stream) {
     if (!P || !qgpv || !u || !theta || !avort || !profiles_host || !qref_st || !qref_cu || !uref_st || !ptref_st ||
         !num_of_iter_host)
         return FALWA_ERR_NULL;
@@ -550,17 +862,24 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
     DeviceScratch<double> zm, hist, prof, work;
     DeviceScratch<unsigned long long> ext;
     DeviceScratch<int> nit;
-    if ((rc = zm.alloc((size_t)batch * 3 * kmax * nlat, st))) return rc;
+    const bool have_stats = zm_in && ext_in;
+    if (!have_stats) {
+        if ((rc = zm.alloc((size_t)batch * 3 * kmax * nlat, st))) return rc;
+        if ((rc = ext.alloc((size_t)batch * 2 * kmax * 2, st))) return rc;
+    }
     if ((rc = hist.alloc((size_t)batch * 3 * kmax * 2 * nb, st, true))) return rc;
-    if ((rc = ext.alloc((size_t)batch * 2 * kmax * 2, st))) return rc;
     if ((rc = nit.alloc((size_t)batch * 2, st, true))) return rc;
     // per (b, hemisphere): qref, cref, cbar, ubar, tbar [njk each]; uref, tref [njd]; fjk [njk]; tb[kmax]; uz[nd]
     const size_t per = 6 * njk + 2 * njd + kmax + nd;
     const size_t ckoff = (size_t)batch * 2 * per;  // ckref per snapshot
     if ((rc = work.alloc(ckoff + (size_t)batch * njk, st, true))) return rc;
-    { FALWA_KERNEL("init_ext_kernel", st); init_ext_kernel<<<ceil_div((long long)batch * 2 * kmax * 2, 128), 128, 0, st>>>(ext.d, batch * 2 * kmax * 2); }
-    { FALWA_KERNEL("zonal_stats_kernel", st); zonal_stats_kernel<<<dim3(nlat, kmax, batch), 256, 0, st>>>(nlon, nlat, kmax, qgpv, u, theta, avort, zm.d, ext.d,
-                                                                P->kind == 0 ? 1 : 3); }
+    const double* zmd = have_stats ? zm_in : zm.d;
+    const unsigned long long* extd = have_stats ? (const unsigned long long*)ext_in : ext.d;
+    if (!have_stats) {
+        { FALWA_KERNEL("init_ext_kernel", st); init_ext_kernel<<<ceil_div((long long)batch * 2 * kmax * 2, 128), 128, 0, st>>>(ext.d, batch * 2 * kmax * 2); }
+        { FALWA_KERNEL("zonal_stats_kernel", st); zonal_stats_kernel<<<dim3(nlat, kmax, batch), 256, 0, st>>>(nlon, nlat, kmax, qgpv, u, theta, avort, zm.d, ext.d,
+                                                                    P->kind == 0 ? 1 : 3); }
+    }
     FALWA_LAUNCH_CHECK();
     {
         int slabs = std::max(1, std::min(nlat, (148 * 4 + (kmax - 3)) / (kmax - 2) / std::max(1, std::min(batch, 4))));
@@ -571,7 +890,7 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
         if (smem > 48 * 1024)
             FALWA_CUDA_TRY(cudaFuncSetAttribute(area_hist3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         { FALWA_KERNEL("area_hist3_kernel", st); area_hist3_kernel<<<dim3(slabs, kmax - 2, batch), 256, smem, st>>>(nlon, nlat, kmax, nb, P->kind != 0, qgpv, avort,
-                                                                          ext.d, d + P->o_da, rows, hist.d); }
+                                                                          extd, d + P->o_da, rows, hist.d); }
         FALWA_LAUNCH_CHECK();
     }
     // host-built per-problem tables
@@ -611,37 +930,24 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
     auto WT = [&](int b, int hs) { return work.d + ((size_t)b * 2 + hs) * per + 6 * njk + njd; };
     auto WTB = [&](int b, int hs) { return work.d + ((size_t)b * 2 + hs) * per + 6 * njk + 2 * njd; };
     auto WUZ = [&](int b, int hs) { return work.d + ((size_t)b * 2 + hs) * per + 6 * njk + 2 * njd + kmax; };
-    for (int b = 0; b < batch; ++b) {
-        const double* zmb = zm.d + (size_t)b * 3 * kmax * nlat;
-        const unsigned long long* extb = ext.d + (size_t)b * 2 * kmax * 2;
-        const double* histb = hist.d + (size_t)b * 3 * kmax * 2 * nb;
-        double* ckref = work.d + ckoff + (size_t)b * njk;
-        if (P->kind != 0) {
-            { FALWA_KERNEL("qref_invert_kernel", st); qref_invert_kernel<<<kmax - 2, 256, sizeof(double) * 2 * nb, st>>>(
-                kmax, nb, nd, nd, histb + (size_t)2 * kmax * 2 * nb, extb + (size_t)kmax * 2, 1.0, d + P->o_alat, nullptr,
-                ckref, 0); }
-            FALWA_LAUNCH_CHECK();
-        }
-        for (int hs = 0; hs < 2; ++hs) {
-            const double sgn = hs == 0 ? 1.0 : -1.0;
-            const int flip = hs == 0 ? 0 : nlat;
-            { FALWA_KERNEL("qref_invert_kernel", st); qref_invert_kernel<<<kmax - 2, 256, sizeof(double) * 2 * nb, st>>>(
-                kmax, nb, nd, nd, histb + (size_t)hs * kmax * 2 * nb, extb, sgn, d + P->o_alat, W(b, hs, 0), W(b, hs, 1), 1); }
-            FALWA_LAUNCH_CHECK();
-            { FALWA_KERNEL("cbar_normalise_kernel", st); cbar_normalise_kernel<<<ceil_div(kmax, 64), 64, 0, st>>>(kmax, nd, zmb, nlat, sgn, flip, nd - 1, d + P->o_cosmid,
-                                                                     d + P->o_norm, P->a, P->dphi, pi, W(b, hs, 0),
-                                                                     W(b, hs, 1), W(b, hs, 2), nullptr); }
-            { FALWA_KERNEL("extract_rows_kernel", st); extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, nd, nlat, nd - 1, flip, 1.0,
-                                                                   zmb + (size_t)1 * kmax * nlat, W(b, hs, 3)); }
-            { FALWA_KERNEL("extract_rows_kernel", st); extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, nd, nlat, nd - 1, flip, 1.0,
-                                                                   zmb + (size_t)2 * kmax * nlat, W(b, hs, 4)); }
-            FALWA_LAUNCH_CHECK();
-            if (P->kind == 0) {
-                { FALWA_KERNEL("tb_mean_kernel", st); tb_mean_kernel<<<ceil_div(kmax, 64), 64, 0, st>>>(kmax, nd, W(b, hs, 4), d + P->o_cosw, WTB(b, hs)); }
-                { FALWA_KERNEL("sor_uz_kernel", st); sor_uz_kernel<<<ceil_div(nd, 128), 128, 0, st>>>(nd, kmax, d + P->o_uzc1, d + P->o_uzc2, W(b, hs, 4),
-                                                                 WUZ(b, hs)); }
-                FALWA_LAUNCH_CHECK();
-            }
+    {
+        LevelArgs la;
+        la.kind = P->kind; la.kmax = kmax; la.nlat = nlat; la.nd = nd; la.nb = nb;
+        la.a = P->a; la.dphi = P->dphi; la.pi = pi;
+        la.zm = zmd; la.hist = hist.d; la.alat = d + P->o_alat; la.cosmid = d + P->o_cosmid; la.norm = d + P->o_norm;
+        la.cosw = (P->kind == 0) ? d + P->o_cosw : nullptr;
+        la.ext = extd; la.work = work.d; la.ckref = work.d + ckoff; la.per = per; la.njk = njk; la.njd = njd;
+        const size_t smem = sizeof(double) * ((size_t)4 * nb + 3 * nd);
+        if (smem > 48 * 1024)
+            FALWA_CUDA_TRY(cudaFuncSetAttribute(refstate_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { FALWA_KERNEL("refstate_level_kernel", st); refstate_level_kernel<<<dim3(kmax, 2, batch), 256, smem, st>>>(la); }
+        FALWA_LAUNCH_CHECK();
+        if (P->kind == 0) {
+            for (int b = 0; b < batch; ++b)
+                for (int hs = 0; hs < 2; ++hs) {
+                    { FALWA_KERNEL("sor_uz_kernel", st); sor_uz_kernel<<<ceil_div(nd, 128), 128, 0, st>>>(nd, kmax, d + P->o_uzc1, d + P->o_uzc2, W(b, hs, 4), WUZ(b, hs)); }
+                    FALWA_LAUNCH_CHECK();
+                }
         }
     }
     // ---- batched solves --------------------------------------------------------------------------
@@ -753,10 +1059,21 @@ extern "C" int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* P, int bat
     const int nhemi = north_only ? 1 : 2;
     const size_t f3 = (size_t)kmax * nlat * nlon;
     int rc;
-    DeviceScratch<double> prof, tmp;
-    if ((rc = prof.alloc((size_t)batch * 4 * kmax, st))) return rc;
-    FALWA_CUDA_TRY(cudaMemcpyAsync(prof.d, profiles_host, sizeof(double) * (size_t)batch * 4 * kmax,
-                                   cudaMemcpyHostToDevice, st));
+    DeviceScratch<double> tmp, hsum;
+    DeviceTable prof;
+    {   // profiles [batch][4][kmax] followed by the per-level factor of the ep1 heat term, [batch][2][kmax]
+        std::vector<double> hp(profiles_host, profiles_host + (size_t)batch * 4 * kmax);
+        const double rkappa = P->rr / P->cp;
+        hp.resize((size_t)batch * 6 * kmax, 0.0);
+        for (int b = 0; b < batch; ++b)
+            for (int hs = 0; hs < 2; ++hs) {  // slot 0: south (ts0), slot 1: north (tn0)
+                const double* tg = profiles_host + ((size_t)b * 4 + hs) * kmax;
+                double* f = hp.data() + (size_t)batch * 4 * kmax + ((size_t)b * 2 + hs) * kmax;
+                for (int k = 2; k <= kmax - 1; ++k)
+                    f[k - 1] = (P->rr / P->h) * std::exp(-rkappa * (P->dz * (double)(k - 1)) / P->h) * 2. * P->dz / (tg[k] - tg[k - 2]);
+            }
+        if ((rc = prof.upload(hp, st))) return rc;
+    }
     FusedFluxArgs p;
     p.imax = nlon; p.nlat = nlat; p.kmax = kmax; p.nd = nd; p.jb = jb; p.jd = P->jd; p.nhemi = nhemi;
     p.has_ncforce = ncforce != nullptr;
@@ -768,6 +1085,7 @@ extern "C" int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* P, int bat
     p.cosphi = d + P->o_cosphi; p.sinphi = d + P->o_sinphi; p.aaw = d + P->o_aaw; p.ep11a = d + P->o_ep11a; p.vw = d + P->o_vw;
     p.clat = d + P->o_clat;
     p.sa1 = p.sa2 = p.su2 = p.snc = nullptr;
+    p.f11 = prof.d + (size_t)batch * 4 * kmax;
     p.lwa = lwa; p.out2d = out2d;
     if (north_only) {  // rows the northern launch does not cover stay zero
         FALWA_CUDA_TRY(cudaMemsetAsync(lwa, 0, sizeof(double) * (size_t)batch * f3, st));
@@ -808,8 +1126,9 @@ extern "C" int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* P, int bat
         dim3 block(32, 8);
         dim3 grid(ceil_div(nlon, 32), ceil_div(nd, 8), batch * nhemi);
         if (use_scan) {
+            if ((rc = hsum.alloc((size_t)batch * nhemi * nd * nlon, st))) return rc;
             FALWA_KERNEL("flux_column_kernel", st);
-            fused_flux_kernel<false><<<grid, block, 0, st>>>(p);
+            flux_column_kernel<<<grid, block, 0, st>>>(p, hsum.d);
         } else {
             FALWA_KERNEL("fused_flux_bruteforce_kernel", st);
             fused_flux_kernel<true><<<grid, block, 0, st>>>(p);
@@ -817,7 +1136,7 @@ extern "C" int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* P, int bat
         FALWA_LAUNCH_CHECK();
     }
     { FALWA_KERNEL("baro_post_kernel", st); baro_post_kernel<<<dim3(ceil_div(P->nlon, 256), P->nlat, batch), 256, 0, st>>>(
-        P->nlon, P->nlat, P->a, P->dphi, P->dlambda, d + P->o_clat, out2d); }
+        P->nlon, P->nlat, P->a, P->dphi, P->dlambda, d + P->o_clat, out2d, use_scan ? hsum.d : nullptr, nhemi, nd, jb); }
     FALWA_LAUNCH_CHECK();
     return 0;
 }

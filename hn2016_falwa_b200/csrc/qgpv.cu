@@ -14,102 +14,190 @@
 
 namespace falwa {
 
+__global__ void init_ext_kernel(unsigned long long* ext, int n);  // refstate.cu
+
 struct QgpvTables {
-    // per latitude row (nlat each): av1 = 2*omega*sin(phi0), den = 2*aa*cos(phi0)*dphi, cosp, cosm
+    // per latitude row (nlat each): av1 = 2*omega*sin(phi0), den = 2*aa*cos(phi0)*dphi, cosp, cosm, rden = 1/den
     const double* av1;
     const double* den;
     const double* cosp;
     const double* cosm;
-    // per level (kmax each): ep[k] = exp(-height[k]/hh), e0[k] = exp(height[k]/hh), height[k]
+    const double* rden;
+    // per level (kmax each): ep[k] = exp(-height[k]/hh), e0[k] = exp(height[k]/hh), height[k],
+    // rdh[k] = 1/(height[k+1]-height[k-1])
     const double* ep;
     const double* e0;
     const double* height;
+    const double* rdh;
 };
-// Per-snapshot profiles live in a separate device array prof[batch][4][kmax]:
-//   row 0 = t0 south (rows j <= jd), 1 = t0 north, 2 = static stability south, 3 = north.
+// Per-snapshot profiles live in a separate device array prof[batch][prof_rows][kmax]:
+//   row 0 = t0 south (rows j <= jd), 1 = t0 north, 2 = static stability south, 3 = north
+//   (FAST only) 4, 5 = reciprocal static stability south, north.
+
+// Fused zonal statistics (FAST pipeline): per (row, level) sums of pv, u, theta and per-level extrema of pv and
+// avort, so that the reference-state stage does not have to read the four 3-D fields again.
+struct QgpvStats {
+    double* part;              // [batch][3][kmax][nlat][nwx] warp partial sums (f = 0 pv, 1 u, 2 theta); null = off
+    unsigned long long* ext;   // [batch][2][kmax][2] ordered {max, min} of pv, avort (initialised by the caller)
+    int nwx;
+};
 
 // mode 0: NH18  — pv receives (altp - altm), finished by nh18_finish_kernel (needs the zonal-mean avort)
 // mode 1: NHN22 — pv = avort + e0 * ((altp - altm) * f / dh)
-template <int MODE>
+// FAST = false: the reference's divisions (bit-comparable with the CPU oracle; F2PY-compatible entry points).
+// FAST = true : host-rounded reciprocals instead of the five ~40-instruction DDIV sequences per point
+//               (<= 2 ulp per term; the kernel becomes HBM-bound instead of issue-bound).
+// The static-stability term alt(l) = ep[l]*(theta(l)-t0[l])/stat[l] is evaluated once per level and rolled.
+template <int MODE, bool FAST>
 __global__ void __launch_bounds__(256)
 avort_pv_kernel(int nlon, int nlat, int kmax, int jd, int kchunk, const double* __restrict__ u,
                 const double* __restrict__ v, const double* __restrict__ th, QgpvTables tb,
                 const double* __restrict__ prof, double* __restrict__ avort, double* __restrict__ pv,
-                size_t batch_stride) {
+                size_t batch_stride, QgpvStats stats) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;  // 0-based row
     const int nchunks = (kmax + kchunk - 1) / kchunk;
     const int chunk = blockIdx.z % nchunks;
     const int b = blockIdx.z / nchunks;
-    if (i >= nlon || j >= nlat) return;
+    const bool valid = (i < nlon && j < nlat);
+    if (!FAST && !valid) return;            // FAST keeps whole warps alive for the shuffles below
+    if (FAST && j >= nlat) return;          // warp-uniform (a warp is one row)
+    constexpr int PR = FAST ? 6 : 4;
     const size_t plane = (size_t)nlon * nlat;
     const size_t base = (size_t)b * batch_stride;
     u += base; v += base; th += base; avort += base; pv += base;
     const int k0 = chunk * kchunk;
     const int k1 = min(kmax, k0 + kchunk);
     const bool interior_row = (j >= 1 && j <= nlat - 2);
-    const int ip = (i == nlon - 1) ? 0 : i + 1;
-    const int im = (i == 0) ? nlon - 1 : i - 1;
-    const double av1 = tb.av1[j], den = tb.den[j], cp = tb.cosp[j], cm = tb.cosm[j];
+    const int ic = valid ? i : nlon - 1;
+    const int ip = (ic == nlon - 1) ? 0 : ic + 1;
+    const int im = (ic == 0) ? nlon - 1 : ic - 1;
+    const double av1 = tb.av1[j], den = tb.den[j], cp = tb.cosp[j], cm = tb.cosm[j], rden = tb.rden[j];
     const int hemi = (j + 1 <= jd) ? 0 : 1;
-    const double* t0 = prof + (size_t)b * 4 * kmax + hemi * kmax;
+    const double* t0 = prof + (size_t)b * PR * kmax + hemi * kmax;
     const double* stat = t0 + 2 * kmax;
-    const size_t col = (size_t)j * nlon + i;
-    // rolling theta registers: tm = theta(k-1), tp = theta(k+1)
-    double tm = (k0 >= 1) ? th[(size_t)(k0 - 1) * plane + col] : 0.0;
+    const double* rstat = t0 + 4 * kmax;
+    const size_t col = (size_t)j * nlon + ic;
+    auto alt = [&](int l, double theta) -> double {
+        return FAST ? tb.ep[l] * (theta - t0[l]) * rstat[l] : tb.ep[l] * (theta - t0[l]) / stat[l];
+    };
+    // rolling static-stability terms: am = alt(k-1), ac = alt(k)
+    double am = (k0 >= 1) ? alt(k0 - 1, th[(size_t)(k0 - 1) * plane + col]) : 0.0;
     double tc = th[(size_t)k0 * plane + col];
+    double ac = alt(k0, tc);
+    const int lane = threadIdx.x;
     for (int k = k0; k < k1; ++k) {
         const size_t off = (size_t)k * plane;
-        double tp = (k + 1 < kmax) ? th[off + plane + col] : 0.0;
+        const double tp = (k + 1 < kmax) ? th[off + plane + col] : 0.0;
+        const double ap = (k + 1 < kmax) ? alt(k + 1, tp) : 0.0;
         double av = 0.0;
         if (interior_row) {
-            const double av2 = (v[off + (size_t)j * nlon + ip] - v[off + (size_t)j * nlon + im]) / den;
-            const double av3 = -(u[off + col + nlon] * cp - u[off + col - nlon] * cm) / den;
-            av = av1 + av2 + av3;
+            const double dv = v[off + (size_t)j * nlon + ip] - v[off + (size_t)j * nlon + im];
+            const double du = -(u[off + col + nlon] * cp - u[off + col - nlon] * cm);
+            av = FAST ? av1 + dv * rden + du * rden : av1 + dv / den + du / den;
         }
         double q = 0.0;
         if (k >= 1 && k <= kmax - 2) {
-            const double altp = tb.ep[k + 1] * (tp - t0[k + 1]) / stat[k + 1];
-            const double altm = tb.ep[k - 1] * (tm - t0[k - 1]) / stat[k - 1];
             if (MODE == 0) {
-                q = altp - altm;
+                q = ap - am;
             } else {
-                const double strc = (altp - altm) * av1 / (tb.height[k + 1] - tb.height[k - 1]);
+                const double strc = FAST ? (ap - am) * av1 * tb.rdh[k]
+                                         : (ap - am) * av1 / (tb.height[k + 1] - tb.height[k - 1]);
                 q = av + tb.e0[k] * strc;
             }
         }
-        st_stream(&avort[off + col], av);
-        st_stream(&pv[off + col], q);
-        tm = tc;
-        tc = tp;
+        if (valid) {
+            st_stream(&avort[off + col], av);
+            st_stream(&pv[off + col], q);
+        }
+        if (FAST && stats.part) {
+            // warp = 32 consecutive longitudes of row j: partial zonal sums and extrema (deterministic two-stage sum)
+            const double uc = valid ? u[off + col] : 0.0;
+            double s0 = (valid && interior_row && MODE == 1) ? q : 0.0, s1 = uc, s2 = valid ? tc : 0.0;
+            s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+            if (lane == 0) {
+                double* pp = stats.part + (size_t)b * 3 * kmax * nlat * stats.nwx;
+                const size_t o = ((size_t)k * nlat + j) * stats.nwx + blockIdx.x;
+                const size_t fs = (size_t)kmax * nlat * stats.nwx;
+                pp[o] = s0; pp[fs + o] = s1; pp[2 * fs + o] = s2;
+            }
+            if (interior_row && k >= 1 && k <= kmax - 2) {
+                const double qx = warp_max(valid ? q : -INFINITY), qn = warp_min(valid ? q : INFINITY);
+                const double ax = warp_max(valid ? av : -INFINITY), an = warp_min(valid ? av : INFINITY);
+                if (lane == 0) {
+                    unsigned long long* e = stats.ext + (size_t)b * 2 * kmax * 2;
+                    if (MODE == 1) {
+                        atomicMax(&e[k * 2 + 0], f64_to_ordered(qx));
+                        atomicMin(&e[k * 2 + 1], f64_to_ordered(qn));
+                    }
+                    atomicMax(&e[(kmax + k) * 2 + 0], f64_to_ordered(ax));
+                    atomicMin(&e[(kmax + k) * 2 + 1], f64_to_ordered(an));
+                }
+            }
+        }
+        am = ac; ac = ap; tc = tp;
     }
 }
 
 // Polar rows: avort(:,1,k) / avort(:,nlat,k) = zonal mean of the adjacent row (compute_qgpv.f90:86-93).
 // For NHN22 the pole rows of pv (which hold only the stretching term so far) receive that mean too.
+// With stats: the polar rows' contribution to the pv row sums and to the pv / avort extrema.
 __global__ void __launch_bounds__(256)
 polar_rows_kernel(int nlon, int nlat, int kmax, int add_to_pv, double* __restrict__ avort,
-                  double* __restrict__ pv, size_t batch_stride) {
+                  double* __restrict__ pv, size_t batch_stride, QgpvStats stats) {
     __shared__ double red[33];
     const int k = blockIdx.x;
     const int pole = blockIdx.y;  // 0 south, 1 north
-    const size_t base = (size_t)blockIdx.z * batch_stride + (size_t)k * nlon * nlat;
+    const int b = blockIdx.z;
+    const size_t base = (size_t)b * batch_stride + (size_t)k * nlon * nlat;
     const int jsrc = pole ? nlat - 2 : 1;
     const int jdst = pole ? nlat - 1 : 0;
     double s = 0.0;
     for (int i = threadIdx.x; i < nlon; i += blockDim.x) s += avort[base + (size_t)jsrc * nlon + i] / (double)nlon;
     s = block_sum(s, red);
     const bool interior = (k >= 1 && k <= kmax - 2);
+    double psum = 0.0, pmx = -INFINITY, pmn = INFINITY;
     for (int i = threadIdx.x; i < nlon; i += blockDim.x) {
         avort[base + (size_t)jdst * nlon + i] = s;
-        if (add_to_pv && interior) pv[base + (size_t)jdst * nlon + i] = s + pv[base + (size_t)jdst * nlon + i];
+        if (add_to_pv && interior) {
+            const double q = s + pv[base + (size_t)jdst * nlon + i];
+            pv[base + (size_t)jdst * nlon + i] = q;
+            psum += q; pmx = fmax(pmx, q); pmn = fmin(pmn, q);
+        }
     }
+    if (stats.part && add_to_pv && interior) {
+        psum = block_sum(psum, red);
+        pmx = warp_max(pmx); pmn = warp_min(pmn);
+        unsigned long long* e = stats.ext + (size_t)b * 2 * kmax * 2;
+        if ((threadIdx.x & 31) == 0) {
+            atomicMax(&e[k * 2 + 0], f64_to_ordered(pmx));
+            atomicMin(&e[k * 2 + 1], f64_to_ordered(pmn));
+            atomicMax(&e[(kmax + k) * 2 + 0], f64_to_ordered(s));
+            atomicMin(&e[(kmax + k) * 2 + 1], f64_to_ordered(s));
+        }
+        if (threadIdx.x == 0) {  // slot 0 of the polar row carries the whole row sum; the other slots are zero
+            double* pp = stats.part + (size_t)b * 3 * kmax * nlat * stats.nwx;
+            pp[((size_t)k * nlat + jdst) * stats.nwx] = psum;
+        }
+    }
+}
+
+// zm[f][k][j] = (sum of the warp partials, fixed order) / nlon
+__global__ void zonal_finalize_kernel(int nlon, int nlat, int kmax, int nwx, const double* __restrict__ part,
+                                      double* __restrict__ zm) {
+    const size_t n = (size_t)3 * kmax * nlat;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const double* p = part + ((size_t)blockIdx.y * n + t) * nwx;
+    double s = 0.0;
+    for (int w = 0; w < nwx; ++w) s += p[w];
+    zm[(size_t)blockIdx.y * n + t] = s / (double)nlon;
 }
 
 // NH18: pv = avort + e0 * ((altp-altm) * zonal_mean(avort) / dh)   (compute_qgpv.f90:98-124)
 __global__ void __launch_bounds__(256)
 nh18_finish_kernel(int nlon, int nlat, int kmax, const double* __restrict__ avort, double* __restrict__ pv,
-                   QgpvTables tb, size_t batch_stride) {
+                   QgpvTables tb, size_t batch_stride, QgpvStats stats) {
     __shared__ double red[33];
     const int j = blockIdx.x, k = blockIdx.y + 1;  // interior levels only
     const size_t row = (size_t)blockIdx.z * batch_stride + ((size_t)k * nlat + j) * nlon;
@@ -118,9 +206,25 @@ nh18_finish_kernel(int nlon, int nlat, int kmax, const double* __restrict__ avor
     const double zm = block_sum(s, red);
     const double dh = tb.height[k + 1] - tb.height[k - 1];
     const double e0 = tb.e0[k];
+    double psum = 0.0, pmx = -INFINITY, pmn = INFINITY;
     for (int i = threadIdx.x; i < nlon; i += blockDim.x) {
         const double strc = pv[row + i] * zm / dh;
-        pv[row + i] = avort[row + i] + e0 * strc;
+        const double q = avort[row + i] + e0 * strc;
+        pv[row + i] = q;
+        psum += q; pmx = fmax(pmx, q); pmn = fmin(pmn, q);
+    }
+    if (stats.part) {
+        psum = block_sum(psum, red);
+        pmx = warp_max(pmx); pmn = warp_min(pmn);
+        unsigned long long* e = stats.ext + (size_t)blockIdx.z * 2 * kmax * 2;
+        if ((threadIdx.x & 31) == 0) {
+            atomicMax(&e[k * 2 + 0], f64_to_ordered(pmx));
+            atomicMin(&e[k * 2 + 1], f64_to_ordered(pmn));
+        }
+        if (threadIdx.x == 0) {
+            double* pp = stats.part + (size_t)blockIdx.z * 3 * kmax * nlat * stats.nwx;
+            pp[((size_t)k * nlat + j) * stats.nwx] = psum;   // MODE 0 leaves the pv slots of avort_pv_kernel at zero
+        }
     }
 }
 
@@ -135,28 +239,30 @@ static int build_qgpv_tables(int nlat, int kmax, bool deg_lat, const double* hei
         }
         return -0.5 * pi + pi * (double)jm1 / (double)(nlat - 1);  // compute_qgpv_direct_inv.f90:30-32
     };
-    h.assign((size_t)4 * nlat + 3 * kmax, 0.0);
-    double *av1 = h.data(), *den = av1 + nlat, *cosp = den + nlat, *cosm = cosp + nlat;
-    double *ep = cosm + nlat, *e0 = ep + kmax, *hg = e0 + kmax;
+    h.assign((size_t)5 * nlat + 4 * kmax, 0.0);
+    double *av1 = h.data(), *den = av1 + nlat, *cosp = den + nlat, *cosm = cosp + nlat, *rden = cosm + nlat;
+    double *ep = rden + nlat, *e0 = ep + kmax, *hg = e0 + kmax, *rdh = hg + kmax;
     for (int j = 1; j <= nlat; ++j) {
         const double phi0 = lat(j - 1), phim = lat(j - 2), phip = lat(j);
         av1[j - 1] = 2. * omega * std::sin(phi0);
         den[j - 1] = 2. * aa * std::cos(phi0) * dphi;
         cosp[j - 1] = std::cos(phip);
         cosm[j - 1] = std::cos(phim);
+        rden[j - 1] = 1. / den[j - 1];
     }
     for (int k = 0; k < kmax; ++k) {
         ep[k] = std::exp(-height[k] / hh);
         e0[k] = std::exp(height[k] / hh);
         hg[k] = height[k];
     }
+    for (int k = 1; k + 1 < kmax; ++k) rdh[k] = 1. / (height[k + 1] - height[k - 1]);
     return 0;
 }
 
 static QgpvTables view_tables(const double* d, int nlat, int kmax) {
     QgpvTables t;
-    t.av1 = d; t.den = d + nlat; t.cosp = d + 2 * nlat; t.cosm = d + 3 * nlat;
-    t.ep = d + 4 * nlat; t.e0 = t.ep + kmax; t.height = t.e0 + kmax;
+    t.av1 = d; t.den = d + nlat; t.cosp = d + 2 * nlat; t.cosm = d + 3 * nlat; t.rden = d + 4 * nlat;
+    t.ep = d + 5 * nlat; t.e0 = t.ep + kmax; t.height = t.e0 + kmax; t.rdh = t.height + kmax;
     return t;
 }
 
@@ -169,26 +275,46 @@ static int pick_kchunk(int nlon, int nlat, int kmax, int batch) {
 }
 
 // Shared driver: mode 0 = NH18 (global t0/stat), mode 1 = NHN22 (hemispheric, split at row jd).
+// fast = 0: exact divisions, prof has 4 rows per snapshot.  fast = 1: reciprocals, prof has 6 rows; when zm / ext are
+// given the zonal statistics of the reference-state stage are produced on the fly (part = scratch
+// [batch][3][kmax][nlat][ceil(nlon/32)], zero-filled here).
 int qgpv_launch(int mode, int nlon, int nlat, int kmax, int jd, int batch, const double* u, const double* v,
                 const double* th, const double* d_tables, const double* d_prof, double* pv, double* avort,
-                cudaStream_t st) {
+                cudaStream_t st, int fast = 0, double* zm = nullptr, unsigned long long* ext = nullptr,
+                double* part = nullptr) {
     const QgpvTables tb = view_tables(d_tables, nlat, kmax);
     const size_t bstride = (size_t)nlon * nlat * kmax;
     const int kchunk = pick_kchunk(nlon, nlat, kmax, batch);
     dim3 block(32, 8);
     dim3 grid(ceil_div(nlon, 32), ceil_div(nlat, 8), ceil_div(kmax, kchunk) * batch);
+    QgpvStats stt;
+    stt.part = (fast && zm && ext) ? part : nullptr;
+    stt.ext = ext;
+    stt.nwx = grid.x;
+    if (stt.part) {  // every partial-sum slot is written by the kernels below
+        { FALWA_KERNEL("init_ext_kernel", st); init_ext_kernel<<<ceil_div((long long)batch * 2 * kmax * 2, 128), 128, 0, st>>>(ext, batch * 2 * kmax * 2); }
+    }
     {
         FALWA_KERNEL("avort_pv_kernel", st);
-        if (mode == 0)
-            avort_pv_kernel<0><<<grid, block, 0, st>>>(nlon, nlat, kmax, jd, kchunk, u, v, th, tb, d_prof, avort, pv, bstride);
+        if (mode == 0 && !fast)
+            avort_pv_kernel<0, false><<<grid, block, 0, st>>>(nlon, nlat, kmax, jd, kchunk, u, v, th, tb, d_prof, avort, pv, bstride, stt);
+        else if (mode == 0)
+            avort_pv_kernel<0, true><<<grid, block, 0, st>>>(nlon, nlat, kmax, jd, kchunk, u, v, th, tb, d_prof, avort, pv, bstride, stt);
+        else if (!fast)
+            avort_pv_kernel<1, false><<<grid, block, 0, st>>>(nlon, nlat, kmax, jd, kchunk, u, v, th, tb, d_prof, avort, pv, bstride, stt);
         else
-            avort_pv_kernel<1><<<grid, block, 0, st>>>(nlon, nlat, kmax, jd, kchunk, u, v, th, tb, d_prof, avort, pv, bstride);
+            avort_pv_kernel<1, true><<<grid, block, 0, st>>>(nlon, nlat, kmax, jd, kchunk, u, v, th, tb, d_prof, avort, pv, bstride, stt);
     }
     FALWA_LAUNCH_CHECK();
-    { FALWA_KERNEL("polar_rows_kernel", st); polar_rows_kernel<<<dim3(kmax, 2, batch), 256, 0, st>>>(nlon, nlat, kmax, mode == 1, avort, pv, bstride); }
+    { FALWA_KERNEL("polar_rows_kernel", st); polar_rows_kernel<<<dim3(kmax, 2, batch), 256, 0, st>>>(nlon, nlat, kmax, mode == 1, avort, pv, bstride, stt); }
     FALWA_LAUNCH_CHECK();
     if (mode == 0) {
-        { FALWA_KERNEL("nh18_finish_kernel", st); nh18_finish_kernel<<<dim3(nlat, kmax - 2, batch), 256, 0, st>>>(nlon, nlat, kmax, avort, pv, tb, bstride); }
+        { FALWA_KERNEL("nh18_finish_kernel", st); nh18_finish_kernel<<<dim3(nlat, kmax - 2, batch), 256, 0, st>>>(nlon, nlat, kmax, avort, pv, tb, bstride, stt); }
+        FALWA_LAUNCH_CHECK();
+    }
+    if (stt.part) {
+        FALWA_KERNEL("zonal_finalize_kernel", st);
+        zonal_finalize_kernel<<<dim3(ceil_div((long long)3 * kmax * nlat, 256), batch), 256, 0, st>>>(nlon, nlat, kmax, stt.nwx, part, zm);
         FALWA_LAUNCH_CHECK();
     }
     return 0;
@@ -199,7 +325,7 @@ int qgpv_tables_host(int mode, int nlat, int kmax, const double* height, double 
     return build_qgpv_tables(nlat, kmax, mode == 0, height, aa, omega, hh, h);
 }
 
-size_t qgpv_tables_size(int nlat, int kmax) { return (size_t)4 * nlat + 3 * kmax; }
+size_t qgpv_tables_size(int nlat, int kmax) { return (size_t)5 * nlat + 4 * kmax; }
 
 // ---------------------------------------------------------------------------------------------
 // Vertical interpolation plev -> uniform pseudo-height, scipy.interpolate.interp1d(kind="linear",

@@ -51,7 +51,7 @@ zonal_stats_kernel(int nlon, int nlat, int kmax, const double* __restrict__ f0, 
         for (int f = 0; f < 3; ++f)
             if (fs[f]) {
                 const double x = fs[f][row + i];
-                s[f] += x / (double)nlon;
+                s[f] += x;
                 if (f == 0) { mx0 = fmax(mx0, x); mn0 = fmin(mn0, x); }
             }
         if (f3 && (ext_mask & 2)) {
@@ -63,7 +63,7 @@ zonal_stats_kernel(int nlon, int nlat, int kmax, const double* __restrict__ f0, 
     for (int f = 0; f < 3; ++f)
         if (fs[f]) {
             const double t = block_sum(s[f], red);
-            if (threadIdx.x == 0) zm[((size_t)f * kmax + k) * nlat + j] = t;
+            if (threadIdx.x == 0) zm[((size_t)f * kmax + k) * nlat + j] = t / (double)nlon;
         }
     if (ext) {
         mx0 = warp_max(mx0); mn0 = warp_min(mn0); mx3 = warp_max(mx3); mn3 = warp_min(mn3);

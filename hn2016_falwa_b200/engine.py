@@ -29,6 +29,7 @@ OUT2D = {  # slot order of falwa_b200.h (enum FALWA_OUT2D_*)
     "convergence_zonal_advective_flux": 11, "divergence_eddy_momentum_flux": 12, "flux_vector_lambda_baro": 13,
     "flux_vector_phi_baro": 14}
 N_OUT2D = 15
+FUSE_ZONAL_STATS = False
 
 _registered = False
 
@@ -40,8 +41,8 @@ def _register():
     _lib.register("falwa_b200_plan_create", [c_dp] + [c_i] * 8 + [c_dp] * 4 + [c_d] * 9)
     _lib.register("falwa_b200_plan_destroy", [c_dp])
     _lib.register("falwa_b200_theta_hemispheric_means", [c_dp, c_i, c_dp, c_dp, c_dp])
-    _lib.register("falwa_b200_interpolate_fields", [c_dp, c_i, c_dp, c_dp, c_dp, c_i, c_dp] + [c_dp] * 5 + [c_dp])
-    _lib.register("falwa_b200_reference_states", [c_dp, c_i] + [c_dp] * 5 + [c_i] + [c_dp] * 4 + [c_dp, c_dp])
+    _lib.register("falwa_b200_interpolate_fields", [c_dp, c_i, c_dp, c_dp, c_dp, c_i, c_dp] + [c_dp] * 7 + [c_dp])
+    _lib.register("falwa_b200_reference_states", [c_dp, c_i] + [c_dp] * 5 + [c_i] + [c_dp] * 4 + [c_dp] * 4)
     _lib.register("falwa_b200_lwa_and_barotropic_fluxes",
                   [c_dp, c_i] + [c_dp] * 9 + [c_i, c_dp, c_dp, c_i, c_dp])
     _registered = True
@@ -107,7 +108,7 @@ class QGBatch:
             if tuple(x.shape) != exp:
                 raise TypeError(f"Incorrect dimension of {name}_field. Expected dimension: {exp}")
         self.profiles = None          # host [B][4][kmax]: t0_s, t0_n, stat_s, stat_n
-        self.u = self.v = self.theta = self.avort = self.qgpv = None
+        self.u = self.v = self.theta = self.avort = self.qgpv = self.zm = self.ext = None
         self.qref_st = self.qref_cu = self.uref = self.ptref = None
         self.num_of_iter = None
         self.lwa = self.out2d = None
@@ -162,10 +163,15 @@ class QGBatch:
         else:
             self.u, self.v, self.theta = self._new(*shape), self._new(*shape), self._new(*shape)
         self.avort, self.qgpv = self._new(*shape), self._new(*shape)
+        # zonal means of (qgpv, u, theta) and per-level extrema of (qgpv, avort) can be fused into the QGPV kernel
+        # (FUSE_ZONAL_STATS); measured slower than the separate row-reduction kernel on B200, so off by default
+        if FUSE_ZONAL_STATS:
+            self.zm = self._new(self.B, 3, p.kmax, p.nlat)
+            self.ext = torch.empty((self.B, 2, p.kmax, 2), dtype=torch.int64, device=self.u_in.device)
         check(self.lib.falwa_b200_interpolate_fields(
             p.handle, self.B, dptr(self.u_in), dptr(self.v_in), dptr(self.t_in), int(self.on_height_grid),
             hptr(self.profiles), dptr(self.u), dptr(self.v), dptr(self.theta), dptr(self.avort), dptr(self.qgpv),
-            stream_ptr()), "interpolate_fields")
+            dptr(self.zm), dptr(self.ext), stream_ptr()), "interpolate_fields")
 
     # ---- stage 2 -------------------------------------------------------------------------------
     def compute_reference_states(self):
@@ -178,7 +184,7 @@ class QGBatch:
         check(self.lib.falwa_b200_reference_states(
             p.handle, self.B, dptr(self.qgpv), dptr(self.u), dptr(self.theta), dptr(self.avort), hptr(self.profiles),
             self.north_only, dptr(self.qref_st), dptr(self.qref_cu), dptr(self.uref), dptr(self.ptref),
-            nit.ctypes.data_as(ctypes.c_void_p), stream_ptr()), "reference_states")
+            nit.ctypes.data_as(ctypes.c_void_p), dptr(self.zm), dptr(self.ext), stream_ptr()), "reference_states")
         self.num_of_iter = nit
 
     # ---- stage 3 -------------------------------------------------------------------------------

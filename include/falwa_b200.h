@@ -158,21 +158,26 @@ int falwa_b200_theta_hemispheric_means(const falwa_plan* plan, int batch, const 
  * onto the uniform pseudo-height grid, absolute vorticity and QGPV.
  * profiles_host [batch][4][kmax] = t0_s, t0_n, stat_s, stat_n evaluated at the height grid (for NH18 pass
  * the hemispheric averages in both slots).  If already_on_height_grid != 0 the interpolation is skipped
- * and u, v, theta must already hold the fields on the height grid. */
+ * and u, v, theta must already hold the fields on the height grid.
+ * zm [batch][3][kmax][nlat] and ext (uint64 [batch][2][kmax][2]) are optional outputs (both or neither): the zonal
+ * means of qgpv, u, theta and the per-level extrema of qgpv and avort, accumulated while the fields are produced so
+ * that falwa_b200_reference_states need not read the 3-D fields again. */
 int falwa_b200_interpolate_fields(const falwa_plan* plan, int batch, const double* u_in, const double* v_in,
                                   const double* t_in, int already_on_height_grid, const double* profiles_host,
                                   double* u, double* v, double* theta, double* avort, double* qgpv,
-                                  void* stream);
+                                  double* zm, void* ext, void* stream);
 
 /* compute_reference_states (oopinterface.py:550-615, :1604-1674, :1774-1888), both hemispheres, merged
  * into global-latitude storage like data_storage.py:32-62 (north first, south second).
  *   qref_st: qref as the reference stores it (qref/f); qref_cu: qref in s^-1 (data_storage.py:170-179).
  *   num_of_iter_host [batch][2]: NH18 SOR iteration counts (north, south); 0 for NHN22.
- * north_only != 0 computes the northern hemisphere only.  Synchronises the stream before returning. */
+ * north_only != 0 computes the northern hemisphere only.  zm / ext: the statistics written by
+ * falwa_b200_interpolate_fields, or NULL (recomputed from the fields).  Synchronises the stream before returning. */
 int falwa_b200_reference_states(const falwa_plan* plan, int batch, const double* qgpv, const double* u,
                                 const double* theta, const double* avort, const double* profiles_host,
                                 int north_only, double* qref_st, double* qref_cu, double* uref_st,
-                                double* ptref_st, int* num_of_iter_host, void* stream);
+                                double* ptref_st, int* num_of_iter_host, const double* zm, const void* ext,
+                                void* stream);
 
 /* compute_lwa_and_barotropic_fluxes (oopinterface.py:716-982), both hemispheres.
  *   lwa   [batch][kmax][nlat][nlon]
