@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 #include "../../include/falwa_b200.h"
 
@@ -153,6 +154,12 @@ struct DeviceScratch {
 };
 
 inline double host_pi() { return std::acos(-1.0); }
+
+// Integer tuning knob from the environment (benchmark experiments only; defaults are the shipped values).
+inline int tune_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

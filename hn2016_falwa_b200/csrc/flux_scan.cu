@@ -236,13 +236,13 @@ lwa_scan_kernel(ScanArgs p) {
     __syncthreads();
 
     // ---- per-warp column work ----------------------------------------------------------------
-    double* q_ = s_q + w * ndp;
-    double* u_ = s_u + w * ndp;
-    double* o_ = s_o + w * ndp;
-    double* n_ = s_n + w * ndp;
-    int* cn = s_cnt + w * cp;
-    short* E_ = s_E + w * ndp;
-    short* pm = s_perm + w * ndp;
+    double* __restrict__ q_ = s_q + w * ndp;
+    double* __restrict__ u_ = s_u + w * ndp;
+    double* __restrict__ o_ = s_o + w * ndp;
+    double* __restrict__ n_ = s_n + w * ndp;
+    int* __restrict__ cn = s_cnt + w * cp;
+    short* __restrict__ E_ = s_E + w * ndp;
+    short* __restrict__ pm = s_perm + w * ndp;
     const unsigned FULL = 0xffffffffu;
     const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -357,7 +357,7 @@ lwa_scan_kernel(ScanArgs p) {
         const int t = lane * R + s;
         if (s < R && t < M) {
             const int j = s_rowof[t];
-            // rows entering at t: nxt(jj) == t  <=>  m_{t-1} <= jj < m_t
+            // rows entering at t: nxt(jj) == t  <=>  m_{t-1} <= jj < m_t  (a single row when Qref is monotone)
             for (int jj = t ? (int)s_rowof[t - 1] : 1; jj < j; ++jj) {
                 const int e = E_[jj - 1];
                 if (e != t) {
@@ -375,10 +375,12 @@ lwa_scan_kernel(ScanArgs p) {
                 T3 -= q * u; T4 -= u;
                 if (HAS_NC) T5 -= n_[r] * cs;
             }
+            // a1 = ab (S1c - Q S2c),  a2 = ab (Q S2a - S1a),  ua2 = ab cos_j (T3 - Q T4) - uref_j (a1 - a2)
             const double Q = s_thr[t], ur = s_urt[t], cj = s_cos[j];
-            o_[j - 1] = (S1c - Q * S2c) * ab;
-            a2l[s] = (Q * S2a - S1a) * ab;
-            u2l[s] = ab * (cj * T3 - ur * (S1c - S1a) - Q * cj * T4 + Q * ur * (S2c - S2a));
+            const double a1 = __fma_rn(-Q, S2c, S1c) * ab, a2 = __fma_rn(Q, S2a, -S1a) * ab;
+            o_[j - 1] = a1;
+            a2l[s] = a2;
+            u2l[s] = __fma_rn(ab * cj, __fma_rn(-Q, T4, T3), -ur * (a1 - a2));
             if (HAS_NC) ncl[s] = ab * T5;
         }
     }
@@ -399,9 +401,10 @@ lwa_scan_kernel(ScanArgs p) {
         if (s < R && t < M) {
             const int j = s_rowof[t];
             const double Q = s_thr[t], ur = s_urt[t], cj = s_cos[j];
-            o_[j - 1] += (O1c - Q * O2c) * ab;
-            q_[j - 1] = a2l[s] + (Q * O2a - O1a) * ab;
-            u_[j - 1] = u2l[s] + ab * (cj * O3 - ur * (O1c - O1a) - Q * cj * O4 + Q * ur * (O2c - O2a));
+            const double d1 = __fma_rn(-Q, O2c, O1c) * ab, d2 = __fma_rn(Q, O2a, -O1a) * ab;
+            o_[j - 1] += d1;
+            q_[j - 1] = a2l[s] + d2;
+            u_[j - 1] = u2l[s] + __fma_rn(ab * cj, __fma_rn(-Q, O4, O3), -ur * (d1 - d2));
             if (HAS_NC) n_[j - 1] = ncl[s] + ab * O5;
         }
     }

@@ -50,7 +50,7 @@ __device__ __forceinline__ void hist_flush(double* sh, int nb, int cur, double s
 __global__ void __launch_bounds__(256)
 area_hist3_kernel(int nlon, int nlat, int kmax, int nb, int with_avort, const double* __restrict__ pv,
                   const double* __restrict__ avort, const unsigned long long* __restrict__ ext,
-                  const double* __restrict__ da, int rows_per_block, double* __restrict__ hist) {
+                  const double* __restrict__ da, int rows_per_block, double* __restrict__ hist, int run) {
     extern __shared__ double sh[];  // [3][2][nb]
     const int k = blockIdx.y + 1, b = blockIdx.z;
     const int nh = with_avort ? 3 : 2;
@@ -73,16 +73,18 @@ area_hist3_kernel(int nlon, int nlat, int kmax, int nb, int with_avort, const do
     }
     const double rdqv = 1. / dqv;
     const int j0 = blockIdx.x * rows_per_block, j1 = min(nlat, j0 + rows_per_block);
-    const int run = 8;
     const int runs_per_row = (nlon + run - 1) / run;
     const int total = (j1 - j0) * runs_per_row;
     const size_t lev = (size_t)k * nlat * nlon;
     double* hN = sh;
     double* hS = sh + 2 * nb;
     double* hV = sh + 4 * nb;
+    const int nrows = j1 - j0;
     for (int t = threadIdx.x; t < total; t += blockDim.x) {
-        const int j = j0 + t / runs_per_row;
-        const int i0 = (t % runs_per_row) * run, i1 = min(nlon, i0 + run);
+        // consecutive lanes take the same longitude run of consecutive ROWS: PV differs from row to row, so the
+        // lanes of a warp hit different bins and the shared-memory CAS loops rarely collide
+        const int j = j0 + t % nrows;
+        const int i0 = (t / nrows) * run, i1 = min(nlon, i0 + run);
         const double daj = da[j];
         int cn = -1, cs = -1, cv = -1;
         double an = 0, qn = 0, as = 0, qs = 0, av = 0, qv = 0;
@@ -877,12 +879,12 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
     const unsigned long long* extd = have_stats ? (const unsigned long long*)ext_in : ext.d;
     if (!have_stats) {
         { FALWA_KERNEL("init_ext_kernel", st); init_ext_kernel<<<ceil_div((long long)batch * 2 * kmax * 2, 128), 128, 0, st>>>(ext.d, batch * 2 * kmax * 2); }
-        { FALWA_KERNEL("zonal_stats_kernel", st); zonal_stats_kernel<<<dim3(nlat, kmax, batch), 256, 0, st>>>(nlon, nlat, kmax, qgpv, u, theta, avort, zm.d, ext.d,
+        { FALWA_KERNEL("zonal_stats_kernel", st); zonal_stats_kernel<<<dim3(ceil_div((long long)nlat * kmax, 8), 1, batch), 256, 0, st>>>(nlon, nlat, kmax, qgpv, u, theta, avort, zm.d, ext.d,
                                                                     P->kind == 0 ? 1 : 3); }
     }
     FALWA_LAUNCH_CHECK();
     {
-        int slabs = std::max(1, std::min(nlat, (148 * 4 + (kmax - 3)) / (kmax - 2) / std::max(1, std::min(batch, 4))));
+        int slabs = std::max(1, std::min(nlat, (148 * tune_int("FALWA_HIST_CTAS", 8) + (kmax - 3)) / (kmax - 2) / std::max(1, std::min(batch, 4))));
         const int rows = ceil_div(nlat, slabs);
         slabs = ceil_div(nlat, rows);
         const int nh = (P->kind == 0) ? 2 : 3;
@@ -890,7 +892,7 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
         if (smem > 48 * 1024)
             FALWA_CUDA_TRY(cudaFuncSetAttribute(area_hist3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         { FALWA_KERNEL("area_hist3_kernel", st); area_hist3_kernel<<<dim3(slabs, kmax - 2, batch), 256, smem, st>>>(nlon, nlat, kmax, nb, P->kind != 0, qgpv, avort,
-                                                                          extd, d + P->o_da, rows, hist.d); }
+                                                                          extd, d + P->o_da, rows, hist.d, tune_int("FALWA_HIST_RUN", 16)); }
         FALWA_LAUNCH_CHECK();
     }
     // host-built per-problem tables

@@ -86,14 +86,30 @@ avort_pv_kernel(int nlon, int nlat, int kmax, int jd, int kchunk, const double* 
     double tc = th[(size_t)k0 * plane + col];
     double ac = alt(k0, tc);
     const int lane = threadIdx.x;
+    // loads of level k+1 are issued before level k is evaluated (register double buffering)
+    struct In { double tp, vp, vm, up, um; };
+    auto fetch = [&](int k) -> In {
+        In r;
+        const size_t off = (size_t)k * plane;
+        r.tp = (k + 1 < kmax) ? th[off + plane + col] : 0.0;
+        r.vp = r.vm = r.up = r.um = 0.0;
+        if (interior_row) {
+            r.vp = v[off + (size_t)j * nlon + ip]; r.vm = v[off + (size_t)j * nlon + im];
+            r.up = u[off + col + nlon]; r.um = u[off + col - nlon];
+        }
+        return r;
+    };
+    In cur = fetch(k0);
     for (int k = k0; k < k1; ++k) {
         const size_t off = (size_t)k * plane;
-        const double tp = (k + 1 < kmax) ? th[off + plane + col] : 0.0;
+        In nxt = cur;
+        if (k + 1 < k1) nxt = fetch(k + 1);
+        const double tp = cur.tp;
         const double ap = (k + 1 < kmax) ? alt(k + 1, tp) : 0.0;
         double av = 0.0;
         if (interior_row) {
-            const double dv = v[off + (size_t)j * nlon + ip] - v[off + (size_t)j * nlon + im];
-            const double du = -(u[off + col + nlon] * cp - u[off + col - nlon] * cm);
+            const double dv = cur.vp - cur.vm;
+            const double du = -(cur.up * cp - cur.um * cm);
             av = FAST ? av1 + dv * rden + du * rden : av1 + dv / den + du / den;
         }
         double q = 0.0;
@@ -136,6 +152,7 @@ avort_pv_kernel(int nlon, int nlat, int kmax, int jd, int kchunk, const double* 
             }
         }
         am = ac; ac = ap; tc = tp;
+        cur = nxt;
     }
 }
 

@@ -29,6 +29,9 @@ __global__ void __launch_bounds__(256)
 zonal_stats_kernel(int nlon, int nlat, int kmax, const double* __restrict__ f0, const double* __restrict__ f1,
                    const double* __restrict__ f2, const double* __restrict__ f3, double* __restrict__ zm,
                    unsigned long long* __restrict__ ext, int ext_mask) {
+    // One warp per (row, level): 8 independent row reductions per CTA, no block-level synchronisation; every lane
+    // streams nlon/32 elements of each field with all loads of an unrolled group in flight.
+    // f0..f2: fields whose zonal mean is wanted (may be null); extrema are taken of f0 (ext_mask&1) and f3 (ext_mask&2).
     {   // batch: blockIdx.z selects the snapshot (contiguous fields / zm / ext per snapshot)
         const size_t fs = (size_t)blockIdx.z * nlon * nlat * kmax;
         if (f0) f0 += fs;
@@ -38,41 +41,43 @@ zonal_stats_kernel(int nlon, int nlat, int kmax, const double* __restrict__ f0, 
         zm += (size_t)blockIdx.z * 3 * kmax * nlat;
         if (ext) ext += (size_t)blockIdx.z * 2 * kmax * 2;
     }
-    // f0..f2: fields whose zonal mean is wanted (may be null); extrema are taken of f0 (ext_mask&1)
-    // and f3 (ext_mask&2).
-    __shared__ double red[33];
-    const int j = blockIdx.x, k = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const long long rowid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (rowid >= (long long)nlat * kmax) return;
+    const int k = (int)(rowid / nlat), j = (int)(rowid % nlat);
     const size_t row = ((size_t)k * nlat + j) * nlon;
     const double* fs[3] = {f0, f1, f2};
     double s[3] = {0, 0, 0};
     double mx0 = -INFINITY, mn0 = INFINITY, mx3 = -INFINITY, mn3 = INFINITY;
-    for (int i = threadIdx.x; i < nlon; i += blockDim.x) {
+    const bool want3 = f3 && (ext_mask & 2);
+#pragma unroll 4
+    for (int i = lane; i < nlon; i += 32) {
 #pragma unroll
         for (int f = 0; f < 3; ++f)
             if (fs[f]) {
-                const double x = fs[f][row + i];
+                const double x = ld_stream(&fs[f][row + i]);
                 s[f] += x;
                 if (f == 0) { mx0 = fmax(mx0, x); mn0 = fmin(mn0, x); }
             }
-        if (f3 && (ext_mask & 2)) {
-            const double x = f3[row + i];
+        if (want3) {
+            const double x = ld_stream(&f3[row + i]);
             mx3 = fmax(mx3, x); mn3 = fmin(mn3, x);
         }
     }
 #pragma unroll
     for (int f = 0; f < 3; ++f)
         if (fs[f]) {
-            const double t = block_sum(s[f], red);
-            if (threadIdx.x == 0) zm[((size_t)f * kmax + k) * nlat + j] = t / (double)nlon;
+            const double t = warp_sum(s[f]);
+            if (lane == 0) zm[((size_t)f * kmax + k) * nlat + j] = t / (double)nlon;
         }
     if (ext) {
         mx0 = warp_max(mx0); mn0 = warp_min(mn0); mx3 = warp_max(mx3); mn3 = warp_min(mn3);
-        if ((threadIdx.x & 31) == 0) {
+        if (lane == 0) {
             if (f0 && (ext_mask & 1)) {
                 atomicMax(&ext[(0 * kmax + k) * 2 + 0], f64_to_ordered(mx0));
                 atomicMin(&ext[(0 * kmax + k) * 2 + 1], f64_to_ordered(mn0));
             }
-            if (f3 && (ext_mask & 2)) {
+            if (want3) {
                 atomicMax(&ext[(1 * kmax + k) * 2 + 0], f64_to_ordered(mx3));
                 atomicMin(&ext[(1 * kmax + k) * 2 + 1], f64_to_ordered(mn3));
             }
@@ -661,7 +666,7 @@ extern "C" int falwa_b200_compute_reference_states(const double* pv, const doubl
     FALWA_CUDA_TRY(cudaMemsetAsync(qref, 0, sizeof(double) * njk, st));
     FALWA_CUDA_TRY(cudaMemsetAsync(tref, 0, sizeof(double) * njk, st));
     { FALWA_KERNEL("init_ext_kernel", st); init_ext_kernel<<<ceil_div(2 * kmax * 2, 128), 128, 0, st>>>(ext.d, 2 * kmax * 2); }
-    { FALWA_KERNEL("zonal_stats_kernel", st); zonal_stats_kernel<<<dim3(nlat, kmax), 256, 0, st>>>(nlon, nlat, kmax, pv, uu, pt, nullptr, zm.d, ext.d, 1); }
+    { FALWA_KERNEL("zonal_stats_kernel", st); zonal_stats_kernel<<<dim3(ceil_div((long long)nlat * kmax, 8)), 256, 0, st>>>(nlon, nlat, kmax, pv, uu, pt, nullptr, zm.d, ext.d, 1); }
     FALWA_LAUNCH_CHECK();
     { FALWA_KERNEL("extract_rows_kernel", st); extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, jd, nlat, jd - 1, 0, 1.0, zm.d + (size_t)1 * kmax * nlat, ubar); }
     { FALWA_KERNEL("extract_rows_kernel", st); extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, jd, nlat, jd - 1, 0, 1.0, zm.d + (size_t)2 * kmax * nlat, tbar); }
@@ -756,7 +761,7 @@ extern "C" int falwa_b200_compute_qref_and_fawa_first(const double* pv, const do
     FALWA_CUDA_TRY(cudaMemsetAsync(tjk, 0, sizeof(double) * (size_t)n * (kmax - 1), st));
     FALWA_CUDA_TRY(cudaMemsetAsync(sjk, 0, sizeof(double) * (size_t)n * n * (kmax - 1), st));
     { FALWA_KERNEL("init_ext_kernel", st); init_ext_kernel<<<ceil_div(2 * kmax * 2, 128), 128, 0, st>>>(ext.d, 2 * kmax * 2); }
-    { FALWA_KERNEL("zonal_stats_kernel", st); zonal_stats_kernel<<<dim3(jmax, kmax), 256, 0, st>>>(imax, jmax, kmax, pv, uu, pt, vort, zm.d, ext.d, 3); }
+    { FALWA_KERNEL("zonal_stats_kernel", st); zonal_stats_kernel<<<dim3(ceil_div((long long)jmax * kmax, 8)), 256, 0, st>>>(imax, jmax, kmax, pv, uu, pt, vort, zm.d, ext.d, 3); }
     FALWA_LAUNCH_CHECK();
     { FALWA_KERNEL("extract_rows_kernel", st); extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, nd, jmax, nd - 1, 0, 1.0, zm.d + (size_t)1 * kmax * jmax, ubar); }
     { FALWA_KERNEL("extract_rows_kernel", st); extract_rows_kernel<<<ceil_div(njk, 256), 256, 0, st>>>(kmax, nd, jmax, nd - 1, 0, 1.0, zm.d + (size_t)2 * kmax * jmax, tbar); }
