@@ -6,3 +6,4 @@
 #include "flux.cu"
 #include "nhn22_solve.cu"
 #include "pipeline.cu"
+#include "baro2d.cu"

@@ -375,12 +375,12 @@ lwa_scan_kernel(ScanArgs p) {
                 T3 -= q * u; T4 -= u;
                 if (HAS_NC) T5 -= n_[r] * cs;
             }
-            // a1 = ab (S1c - Q S2c),  a2 = ab (Q S2a - S1a),  ua2 = ab cos_j (T3 - Q T4) - uref_j (a1 - a2)
+            // a1 = ab (S1c - Q S2c),  a2 = ab (Q S2a - S1a),  ua2 = ab cos_j (T3 - Q T4) - uref_j (a1 + a2)
             const double Q = s_thr[t], ur = s_urt[t], cj = s_cos[j];
             const double a1 = __fma_rn(-Q, S2c, S1c) * ab, a2 = __fma_rn(Q, S2a, -S1a) * ab;
             o_[j - 1] = a1;
             a2l[s] = a2;
-            u2l[s] = __fma_rn(ab * cj, __fma_rn(-Q, T4, T3), -ur * (a1 - a2));
+            u2l[s] = __fma_rn(ab * cj, __fma_rn(-Q, T4, T3), -ur * (a1 + a2));
             if (HAS_NC) ncl[s] = ab * T5;
         }
     }
@@ -404,7 +404,7 @@ lwa_scan_kernel(ScanArgs p) {
             const double d1 = __fma_rn(-Q, O2c, O1c) * ab, d2 = __fma_rn(Q, O2a, -O1a) * ab;
             o_[j - 1] += d1;
             q_[j - 1] = a2l[s] + d2;
-            u_[j - 1] = u2l[s] + __fma_rn(ab * cj, __fma_rn(-Q, O4, O3), -ur * (d1 - d2));
+            u_[j - 1] = u2l[s] + __fma_rn(ab * cj, __fma_rn(-Q, O4, O3), -ur * (d1 + d2));
             if (HAS_NC) n_[j - 1] = ncl[s] + ab * O5;
         }
     }

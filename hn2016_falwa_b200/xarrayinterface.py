@@ -1,0 +1,473 @@
+"""``QGDataset`` — the batch wrapper of falwa.xarrayinterface (/root/reference/src/falwa/xarrayinterface.py:258-661) on
+top of the batched device engine.
+
+The reference builds one ``QGField`` object per (time, member, ...) combination and loops over them in Python
+(:376-410, :454-455, :512-513, :546-548).  Here the flattened leading index is the batch axis of ``engine.QGBatch``:
+snapshots are processed in chunks on one GPU and — when the job runs one process per GPU — the flattened index is
+split into contiguous shards, one per rank, with no communication on the data path and a single gather of the
+outputs at the end.
+
+xarray is optional (it is absent from the build image).  With xarray installed the constructor takes and the methods
+return ``xarray`` objects exactly like the reference; without it the same classes accept / return ``SimpleDataArray``
+/ ``SimpleDataset`` (dims + coords + NumPy data), which is also what the tests use.
+"""
+import itertools
+from collections import OrderedDict
+
+import numpy as np
+
+try:  # pragma: no cover - not available in the build image
+    import xarray as xr
+except Exception:  # noqa: BLE001
+    xr = None
+
+from . import __version__
+
+_NAMES_PLEV = ["plev", "lev", "level", "isobaricInhPa", "pressure_level"]
+_NAMES_YLAT = ["ylat", "lat", "latitude"]
+_NAMES_XLON = ["xlon", "lon", "longitude"]
+_NAMES_U, _NAMES_V, _NAMES_T = ["u", "U"], ["v", "V"], ["t", "T"]
+
+# variable registry (xarrayinterface.py:207-238): core dims and the template attribute holding each coordinate
+_VARS = {}
+for _v in ("qgpv", "interpolated_u", "interpolated_v", "interpolated_theta"):
+    _VARS[_v] = (("height", "ylat", "xlon"), ("height", "ylat", "xlon"))
+for _v in ("static_stability", "static_stability_n", "static_stability_s"):
+    _VARS[_v] = (("height",), ("height",))
+for _v in ("qref", "uref", "ptref"):
+    _VARS[_v] = (("height", "ylat"), ("height", "ylat_ref_states"))
+for _v in ("u_baro", "lwa_baro", "ncforce_baro", "adv_flux_f1", "adv_flux_f2", "adv_flux_f3",
+           "convergence_zonal_advective_flux", "divergence_eddy_momentum_flux", "meridional_heat_flux",
+           "flux_vector_lambda_baro", "flux_vector_phi_baro"):
+    _VARS[_v] = (("ylat", "xlon"), ("ylat_ref_states", "xlon"))
+for _v in ("lwa",):
+    _VARS[_v] = (("height", "ylat", "xlon"), ("height", "ylat_ref_states", "xlon"))
+
+STAGE_VARS = {
+    "interp": ("qgpv", "interpolated_u", "interpolated_v", "interpolated_theta"),
+    "ref": ("qref", "uref", "ptref"),
+    "flux": ("adv_flux_f1", "adv_flux_f2", "adv_flux_f3", "convergence_zonal_advective_flux",
+             "divergence_eddy_momentum_flux", "meridional_heat_flux", "lwa_baro", "u_baro", "ncforce_baro",
+             "flux_vector_lambda_baro", "flux_vector_phi_baro", "lwa"),
+}
+
+
+class SimpleDataArray:
+    """Minimal stand-in for xarray.DataArray: ``data`` (NumPy), ``dims`` (names), ``coords`` (name -> 1-D array)."""
+
+    def __init__(self, data, dims, coords=None, name=None, attrs=None):
+        self.data = np.asarray(data)
+        self.dims = tuple(dims)
+        assert self.data.ndim == len(self.dims)
+        self.coords = OrderedDict((k, np.asarray(v)) for k, v in (coords or {}).items())
+        self.name, self.attrs = name, dict(attrs or {})
+
+    values = property(lambda self: self.data)
+    shape = property(lambda self: self.data.shape)
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self.data, dtype=dtype)
+
+
+class SimpleDataset(OrderedDict):
+    """name -> SimpleDataArray, with ``attrs`` (stand-in for xarray.Dataset)."""
+
+    def __init__(self, data_vars=None, attrs=None):
+        super().__init__(data_vars or {})
+        self.attrs = dict(attrs or {})
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous block [lo, hi) of the flattened snapshot index owned by ``rank`` (blocks differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _find(names, available, user_names, what):
+    if user_names and names[0] in user_names:
+        if user_names[names[0]] not in available:
+            raise KeyError(f"specified variable '{user_names[names[0]]}' not found")
+        return user_names[names[0]]
+    for n in names:
+        if n in available:
+            return n
+    raise KeyError(f"no matching variable for '{what}' found")
+
+
+class _FieldView:
+    """Per-snapshot read-only view (``QGDataset.fields[i].lwa_baro`` ...), for code that iterates over fields."""
+
+    def __init__(self, qgds, idx):
+        self._q, self._i = qgds, idx
+
+    def __getattr__(self, name):
+        store = self._q._store
+        if name in store:
+            return store[name][self._i]
+        return getattr(self._q._template, name)
+
+
+class QGDataset:
+    """Batch of snapshots with the interface of falwa.xarrayinterface.QGDataset.
+
+    Extra keyword arguments (all optional): ``chunk`` — snapshots per device batch; ``shard=(rank, world)`` — process
+    only this rank's contiguous block of the flattened leading index (defaults to torch.distributed's rank / world size
+    when a process group is initialised); ``keep_3d`` — copy the 3-D outputs (qgpv, interpolated fields, lwa) to the
+    host (default True, like the reference); ``runner`` — the object that runs a chunk (tests inject a CPU runner).
+    """
+
+    def __init__(self, da_u, da_v=None, da_t=None, *, var_names=None, qgfield=None, qgfield_args=None,
+                 qgfield_kwargs=None, chunk=None, shard=None, keep_3d=True, runner=None):
+        from .oopinterface import QGFieldNH18
+        var_names = var_names or {}
+        self._qgfield = qgfield or QGFieldNH18
+        self._qgfield_args = list(qgfield_args or [])
+        self._qgfield_kwargs = dict(qgfield_kwargs or {})
+        u, v, t, dims, coords = self._extract(da_u, da_v, da_t, var_names)
+        name_p = _find(_NAMES_PLEV, coords, var_names, "plev")
+        name_y = _find(_NAMES_YLAT, coords, var_names, "ylat")
+        name_x = _find(_NAMES_XLON, coords, var_names, "xlon")
+        assert dims[-3] == name_p, f"dimension -3 of input fields must be '{name_p}' (plev)"
+        assert dims[-2] == name_y, f"dimension -2 of input fields must be '{name_y}' (ylat)"
+        assert dims[-1] == name_x, f"dimension -1 of input fields must be '{name_x}' (xlon)"
+        assert u.shape == v.shape == t.shape, "dimensions of the u, v, t fields don't match"
+        self._other_dims = tuple(dims[:-3])
+        self._other_coords = OrderedDict((d, np.asarray(coords[d]) if d in coords else np.arange(u.shape[i]))
+                                         for i, d in enumerate(self._other_dims))
+        self._other_shape = tuple(u.shape[:-3])
+        n = int(np.prod(self._other_shape, dtype=np.int64))
+        assert n > 0, "empty input"
+        shape = (n,) + tuple(u.shape[-3:])
+        u, v, t = u.reshape(shape), v.reshape(shape), t.reshape(shape)
+        ylat, plev, xlon = np.asarray(coords[name_y]), np.asarray(coords[name_p]), np.asarray(coords[name_x])
+        flip = []
+        if not np.all(np.diff(ylat) > 0):   # xarrayinterface.py:386-395: latitude ascending, pressure descending
+            ylat = np.flip(ylat)
+            flip.append(-2)
+        if not np.all(np.diff(plev) < 0):
+            plev = np.flip(plev)
+            flip.append(-3)
+        if flip:
+            u, v, t = (np.flip(x, axis=flip) for x in (u, v, t))
+        self._n = n
+        if shard is None:
+            shard = (0, 1)
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    shard = (dist.get_rank(), dist.get_world_size())
+            except Exception:  # noqa: BLE001
+                pass
+        self._rank, self._world = shard
+        self._lo, self._hi = shard_bounds(n, *shard)
+        self._u, self._v, self._t = u[self._lo:self._hi], v[self._lo:self._hi], t[self._lo:self._hi]
+        self._xlon, self._ylat, self._plev = xlon, ylat, plev
+        self._keep_3d = keep_3d
+        self._chunk = chunk
+        self._runner = runner
+        self._template = None
+        self._store = {}      # name -> host array [n_local, ...]
+        self._done = set()
+        self._gathered = False
+        if self._hi > self._lo or runner is None:
+            self._make_template()
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _extract(da_u, da_v, da_t, var_names):
+        """-> u, v, t (NumPy, same shape), dims, coords from xarray objects or the Simple* stand-ins."""
+        def is_ds(x):
+            return (xr is not None and isinstance(x, xr.Dataset)) or isinstance(x, SimpleDataset)
+
+        def pick(ds, names, what):
+            return ds[_find(names, list(ds.keys()) if not (xr is not None and isinstance(ds, xr.Dataset)) else ds,
+                            var_names, what)]
+        if is_ds(da_u):
+            src = da_u
+            if da_v is None:
+                da_v = pick(src, _NAMES_V, "v")
+            elif is_ds(da_v):
+                da_v = pick(da_v, _NAMES_V, "v")
+            if da_t is None:
+                da_t = pick(src, _NAMES_T, "t")
+            elif is_ds(da_t):
+                da_t = pick(da_t, _NAMES_T, "t")
+            da_u = pick(src, _NAMES_U, "u")
+        assert da_u is not None, "missing u field"
+        assert da_v is not None, "missing v field"
+        assert da_t is not None, "missing t field"
+        assert tuple(da_u.dims) == tuple(da_v.dims), "dimensions of fields u and v don't match"
+        assert tuple(da_u.dims) == tuple(da_t.dims), "dimensions of fields u and t don't match"
+        coords = {k: np.asarray(getattr(c, "values", c)) for k, c in da_u.coords.items()}
+        return (np.asarray(da_u.data), np.asarray(da_v.data), np.asarray(da_t.data), tuple(da_u.dims), coords)
+
+    def _make_template(self):
+        if self._template is None:
+            i = 0 if self._hi > self._lo else None
+            assert i is not None or self._runner is not None
+            self._template = self._qgfield(self._xlon, self._ylat, self._plev, self._u[0], self._v[0], self._t[0],
+                                           *self._qgfield_args, **self._qgfield_kwargs)
+        return self._template
+
+    @property
+    def fields(self):
+        """Per-snapshot views of this rank's shard (the reference returns its list of QGField objects)."""
+        return [_FieldView(self, i) for i in range(self._hi - self._lo)]
+
+    @property
+    def shard(self):
+        return self._lo, self._hi
+
+    @property
+    def attrs(self):
+        f = self._template
+        return {"kmax": f.kmax, "dz": f.dz, "maxit": f.maxit, "tol": f.tol, "npart": f.npart, "rjac": f.rjac,
+                "scale_height": f.scale_height, "cp": f.cp, "dry_gas_constant": f.dry_gas_constant, "omega": f.omega,
+                "planet_radius": f.planet_radius, "prefactor": f.prefactor, "protocol": type(f).__name__,
+                "package": f"hn2016_falwa_b200 {__version__}"}
+
+    # ---- execution ---------------------------------------------------------------------------------
+    def _run(self, upto, ncforce=None):
+        """Run the pipeline up to stage ``upto`` over this rank's shard, chunk by chunk, keeping the outputs of the
+        stages that have not been stored yet.  Earlier stages are recomputed on the device rather than re-uploaded:
+        they cost ~1 ms per 0.25-degree snapshot, a PCIe round trip of their five 3-D fields costs ~40 ms."""
+        order = ("interp", "ref", "flux")
+        stages = order[:order.index(upto) + 1]
+        todo = [s for s in stages if s not in self._done]
+        if not todo:
+            return
+        nloc = self._hi - self._lo
+        if nloc == 0:
+            self._done.update(todo)
+            return
+        runner = self._runner
+        if runner is None:
+            tpl = self._make_template()
+            # inputs on an even latitude grid are regridded per field by the QGField constructor
+            # (oopinterface.py:147-154): rare path, one object per snapshot like the reference
+            runner = _FieldLoopRunner(self) if tpl.need_latitude_interpolation else _DeviceRunner(tpl, self._chunk)
+        want = [v for s in todo for v in STAGE_VARS[s]]
+        if "interp" in todo:
+            want += ["static_stability"]
+        if not self._keep_3d:
+            want = [v for v in want if len(_VARS.get(v, ((), ()))[0]) < 3]
+        for lo, hi, out in runner.run(self._u, self._v, self._t, stages, want,
+                                      None if ncforce is None else ncforce[self._lo:self._hi]):
+            for name, arr in out.items():
+                if name not in self._store:
+                    self._store[name] = np.empty((nloc,) + arr.shape[1:], dtype=arr.dtype)
+                self._store[name][lo:hi] = arr
+        self._done.update(todo)
+
+    def gather(self):
+        """Concatenate every rank's shard of the stored outputs on all ranks (one all_gather per variable; the only
+        communication of the whole job).  No-op for a single process."""
+        if self._world == 1 or self._gathered:
+            return
+        import torch.distributed as dist
+        # agree on the variable list first (a rank with an empty shard has stored nothing)
+        meta = {k: (str(a.dtype), tuple(a.shape[1:])) for k, a in self._store.items()}
+        metas = [None] * self._world
+        dist.all_gather_object(metas, meta)
+        union = {}
+        for m in metas:
+            union.update(m)
+        for name in sorted(union):
+            dtype, tail = union[name]
+            loc = self._store.get(name)
+            if loc is None:
+                loc = np.empty((0,) + tuple(tail), dtype=dtype)
+            parts = [None] * self._world
+            if int(np.prod(tail, dtype=np.int64)) * max(1, loc.shape[0]) < (1 << 14):
+                dist.all_gather_object(parts, (self._lo, loc))
+            else:
+                self._gather_big(parts, loc)
+            parts = sorted((p for p in parts if p[1].shape[0] > 0), key=lambda p: p[0])
+            self._store[name] = np.concatenate([p[1] for p in parts], axis=0)
+        self._lo, self._hi = 0, self._n
+        self._gathered = True
+
+    def _gather_big(self, parts, loc):
+        """Tensor all_gather (NCCL on GPUs, gloo on CPU) of equally padded shards."""
+        import torch
+        import torch.distributed as dist
+        backend = dist.get_backend()
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        nmax = max(shard_bounds(self._n, r, self._world)[1] - shard_bounds(self._n, r, self._world)[0]
+                   for r in range(self._world))
+        pad = np.zeros((nmax,) + loc.shape[1:], dtype=loc.dtype)
+        pad[:loc.shape[0]] = loc
+        mine = torch.from_numpy(pad).to(dev)
+        bufs = [torch.empty_like(mine) for _ in range(self._world)]
+        dist.all_gather(bufs, mine)
+        for r, b in enumerate(bufs):
+            lo, hi = shard_bounds(self._n, r, self._world)
+            parts[r] = (lo, b[:hi - lo].cpu().numpy())
+
+    # ---- output helpers -------------------------------------------------------------------------------
+    def _coords_for(self, var):
+        core, names = _VARS[var]
+        coords = OrderedDict(self._other_coords)
+        for dim, attr in zip(core, names):
+            coords[dim] = np.asarray(getattr(self._template, attr))
+        return self._other_dims + core, coords
+
+    def _as_dataarray(self, var):
+        if var not in self._store:
+            raise ValueError(f"{var} is not computed yet.")
+        arr = self._store[var]
+        dims, coords = self._coords_for(var)
+        if arr.shape[0] == self._n:          # full (single process or gathered): restore the leading dims
+            arr = arr.reshape(self._other_shape + arr.shape[1:])
+        else:                                # a shard: one flattened leading dim
+            dims = ("snapshot",) + dims[len(self._other_dims):]
+            coords = OrderedDict((k, v) for k, v in coords.items() if k not in self._other_dims)
+            coords["snapshot"] = np.arange(self._lo, self._hi)
+        if xr is not None:  # pragma: no cover
+            return xr.DataArray(arr, dims=dims, coords=coords, name=var)
+        return SimpleDataArray(arr, dims, coords, name=var)
+
+    def _dataset(self, names):
+        data_vars = OrderedDict((n, self._as_dataarray(n)) for n in names if n in self._store or self._keep_3d)
+        if xr is not None:  # pragma: no cover
+            return xr.Dataset(data_vars, attrs=self.attrs)
+        return SimpleDataset(data_vars, attrs=self.attrs)
+
+    def __getattr__(self, name):
+        if name in _VARS and not name.startswith("static_stability"):
+            return self._as_dataarray(name)
+        raise AttributeError(name)
+
+    @property
+    def static_stability(self):
+        """Global definition (NH18): one DataArray; hemispheric (NHN22): the (north, south) pair like the reference
+        (xarrayinterface.py:476-497, whose suffixes follow the order of QGFieldNHN22.static_stability)."""
+        st = self._store.get("static_stability")
+        if st is None:
+            raise ValueError("static_stability is not computed yet.")
+        if st.ndim == 2:
+            self._store["static_stability"] = st
+            return self._as_dataarray("static_stability")
+        self._store["static_stability_n"], self._store["static_stability_s"] = st[:, 0, :], st[:, 1, :]
+        return self._as_dataarray("static_stability_n"), self._as_dataarray("static_stability_s")
+
+    # ---- the reference's methods ---------------------------------------------------------------------
+    def interpolate_fields(self, return_dataset=True):
+        self._run("interp")
+        if return_dataset:
+            ds = self._dataset(STAGE_VARS["interp"])
+            stab = self.static_stability
+            for s in (stab if isinstance(stab, tuple) else (stab,)):
+                ds[s.name] = s
+            return ds
+
+    def compute_reference_states(self, return_dataset=True):
+        self._run("ref")
+        if return_dataset:
+            return self._dataset(STAGE_VARS["ref"])
+
+    def compute_lwa_and_barotropic_fluxes(self, ncforce=None, return_dataset=True):
+        nc = None
+        if ncforce is not None:
+            nc = np.asarray(getattr(ncforce, "data", ncforce))
+            nc = nc.reshape((self._n,) + nc.shape[-3:])
+        self._run("flux", ncforce=nc)
+        if return_dataset:
+            return self._dataset(STAGE_VARS["flux"])
+
+
+class _DeviceRunner:
+    """Runs chunks of snapshots through ``engine.QGBatch`` on the current CUDA device and yields host copies of the
+    requested variables.  The next chunk's inputs are uploaded on a side stream while the current chunk computes."""
+
+    _NAMES2D = None
+
+    def __init__(self, template, chunk=None):
+        import torch
+        from . import engine
+        self.torch, self.engine = torch, engine
+        self.f = template
+        self.plan = template._plan
+        if chunk is None:
+            per = 8 * self.plan.nlon * self.plan.nlat * (3 * self.plan.nlev + 10 * self.plan.kmax + 20)
+            free = torch.cuda.mem_get_info()[0]
+            chunk = int(max(1, min(256, 0.4 * free // per)))
+        self.chunk = chunk
+
+    def run(self, u, v, t, stages, want, ncforce=None):
+        torch, engine = self.torch, self.engine
+        f = self.f
+        n = u.shape[0]
+        nh_only = f.northern_hemisphere_results_only
+        on_h = f._data_on_evenly_spaced_pseudoheight_grid
+        side = torch.cuda.Stream()
+
+        def upload(lo, hi):
+            with torch.cuda.stream(side):
+                arrs = [torch.from_numpy(np.ascontiguousarray(x[lo:hi], dtype=np.float64)).pin_memory().cuda(
+                    non_blocking=True) for x in (u, v, t)]
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return arrs, ev
+        bounds = [(lo, min(n, lo + self.chunk)) for lo in range(0, n, self.chunk)]
+        nxt = upload(*bounds[0])
+        for c, (lo, hi) in enumerate(bounds):
+            (du, dv, dt_), ev = nxt
+            if c + 1 < len(bounds):
+                nxt = upload(*bounds[c + 1])
+            torch.cuda.current_stream().wait_event(ev)
+            b = engine.QGBatch(self.plan, du, dv, dt_, on_height_grid=on_h, northern_hemisphere_results_only=nh_only)
+            b.interpolate_fields()
+            if "ref" in stages:
+                b.compute_reference_states()
+                if self.plan.kind == 0 and (b.num_of_iter >= f.maxit).any():
+                    msg = "The reference state does not converge for at least one snapshot of the batch."
+                    if f._raise_error_for_nonconvergence:
+                        raise ValueError(msg)
+                    import warnings
+                    warnings.warn(msg)
+            if "flux" in stages:
+                b.compute_lwa_and_barotropic_fluxes(ncforce=None if ncforce is None else ncforce[lo:hi])
+            out = {}
+            eq = f.equator_idx
+            for name in want:
+                if name == "static_stability":
+                    p = b.profiles
+                    out[name] = p[:, 2].copy() if self.plan.kind == 0 else np.stack([p[:, 2], p[:, 3]], axis=1)
+                    if self.plan.kind == 1 and nh_only:
+                        out[name] = p[:, 3].copy()
+                    continue
+                src = {"qgpv": b.qgpv, "interpolated_u": b.u, "interpolated_v": b.v, "interpolated_theta": b.theta,
+                       "qref": b.qref_cu, "uref": b.uref, "ptref": b.ptref, "lwa": b.lwa}.get(name)
+                if src is None:
+                    src = b.out(name)
+                a = src.cpu().numpy()
+                if nh_only and name not in ("qgpv", "interpolated_u", "interpolated_v", "interpolated_theta"):
+                    a = a[..., -eq:, :] if name in engine.OUT2D or name == "lwa" else a[..., -eq:]
+                out[name] = a
+            yield lo, hi, out
+
+
+class _FieldLoopRunner:
+    """One QGField object per snapshot (the reference's own structure); used when the inputs need the constructor's
+    latitude regridding."""
+
+    def __init__(self, qgds):
+        self.q = qgds
+
+    def run(self, u, v, t, stages, want, ncforce=None):
+        q = self.q
+        for i in range(u.shape[0]):
+            f = q._qgfield(q._xlon, q._ylat, q._plev, u[i], v[i], t[i], *q._qgfield_args, **q._qgfield_kwargs)
+            f.interpolate_fields(return_named_tuple=False)
+            if "ref" in stages:
+                f.compute_reference_states(return_named_tuple=False)
+            if "flux" in stages:
+                f.compute_lwa_and_barotropic_fluxes(return_named_tuple=False,
+                                                    ncforce=None if ncforce is None else ncforce[i])
+            out = {}
+            for name in want:
+                val = getattr(f, name)
+                out[name] = np.asarray(val)[None] if not isinstance(val, tuple) else np.stack(val)[None]
+            yield i, i + 1, out

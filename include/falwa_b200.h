@@ -197,6 +197,17 @@ int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* plan, int batch, cons
                                          const double* uref_st, const double* ptref_st, int north_only,
                                          double* lwa, double* out2d, int method, void* stream);
 
+/* ======================================================================================
+ * Section C — 2-D (barotropic) path: BarotropicField.equivalent_latitudes / .lwa for a batch of fields
+ * (replaces src/falwa/barotropic_field.py:104-125 -> basis.eqvlat_fawa(output_fawa=False), basis.lwa;
+ * basis.py:11-64, :137-205).  vort [batch][nlat][nlon]; area [nlat][nlon]; ylat_host (degrees, ascending) and
+ * dmu_host = a*cos(lat)*dphi, [nlat] each.  qref [batch][nlat]; lwa [batch][nlat][nlon], or [batch][2][nlat][nlon]
+ * (anticyclonic, cyclonic) when partitioned != 0; lwa may be NULL (equivalent latitude only).
+ * ====================================================================================== */
+int falwa_b200_barotropic_eqvlat_lwa(int batch, int nlon, int nlat, int n_points, const double* vort,
+                                     const double* area, const double* ylat_host, const double* dmu_host,
+                                     double planet_radius, double* qref, double* lwa, int partitioned, void* stream);
+
 /* Diagnostics used by bench.py (not on the data path): number of kernels launched by this library so far;
  * optional per-kernel timing with CUDA events on the launching stream.  profile_read synchronises the device
  * and writes one line "kernel_name launches total_ms" per kernel into buf, then clears the records. */

@@ -1,0 +1,52 @@
+"""GPU test of QGDataset's device runner (BASELINE.json config 4 in miniature): a (time, member) batch through
+hn2016_falwa_b200.xarrayinterface.QGDataset equals each snapshot through QGFieldNHN22 / QGFieldNH18 on its own and the
+CPU oracle; leading dimensions are restored like the reference (tests/test_xarrayinterface.py:75-106)."""
+import numpy as np
+import pytest
+
+from hn2016_falwa_b200.synthetic import synthetic_snapshot
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(nt, nm):
+    from hn2016_falwa_b200 import xarrayinterface as xi
+    snaps = [synthetic_snapshot(nlon=96, nlat=49, seed=21, t_index=k) for k in range(nt * nm)]
+    xlon, ylat, plev = snaps[0][:3]
+    u, v, t = (np.stack([s[i] for s in snaps]).reshape((nt, nm) + snaps[0][3].shape) for i in (3, 4, 5))
+    # files usually come north->south and top->bottom
+    u, v, t = (x[:, :, ::-1, ::-1, :] for x in (u, v, t))
+    coords = dict(time=np.arange(nt), number=np.arange(nm), level=plev[::-1], latitude=ylat[::-1], longitude=xlon)
+    dims = ("time", "number", "level", "latitude", "longitude")
+    mk = lambda a, n: xi.SimpleDataArray(a, dims, coords, name=n)
+    return xi.SimpleDataset(dict(u=mk(u, "u"), v=mk(v, "v"), t=mk(t, "t"))), snaps
+
+
+@pytest.mark.parametrize("kind", ["nh18", "nhn22"])
+def test_dataset_equals_single_fields_and_oracle(kind):
+    from hn2016_falwa_b200 import xarrayinterface as xi
+    from hn2016_falwa_b200.oopinterface import QGFieldNH18, QGFieldNHN22
+    from oracle import pipeline
+    cls = QGFieldNH18 if kind == "nh18" else QGFieldNHN22
+    ds, snaps = _make(2, 2)
+    q = xi.QGDataset(ds, qgfield=cls, chunk=3)          # 4 snapshots in chunks of 3 + 1
+    interp = q.interpolate_fields()
+    assert interp["qgpv"].dims == ("time", "number", "height", "ylat", "xlon")
+    assert interp["qgpv"].shape == (2, 2, 49, 49, 96)
+    ref = q.compute_reference_states()
+    flux = q.compute_lwa_and_barotropic_fluxes()
+    assert set(flux) >= {"lwa_baro", "u_baro", "adv_flux_f1", "convergence_zonal_advective_flux", "lwa"}
+    assert len(q.fields) == 4 and q.attrs["protocol"] == cls.__name__
+    idx = 3
+    f = cls(*snaps[idx])
+    f.interpolate_fields(False); f.compute_reference_states(False); f.compute_lwa_and_barotropic_fluxes(False)
+    want = pipeline.run_qgfield(kind, *snaps[idx])
+    for name in ("qgpv", "uref", "lwa_baro", "adv_flux_f2", "lwa", "divergence_eddy_momentum_flux"):
+        got = np.asarray(getattr(q, name).data).reshape((4,) + np.asarray(getattr(f, name)).shape)[idx]
+        np.testing.assert_allclose(got, getattr(f, name), rtol=1e-11, atol=1e-12 * np.abs(want[name]).max())
+        np.testing.assert_allclose(got, want[name], rtol=1e-8, atol=1e-9 * np.abs(want[name]).max())
+    stab = q.static_stability
+    if kind == "nh18":
+        assert stab.shape == (2, 2, 49)
+    else:
+        assert stab[0].name == "static_stability_n" and stab[0].shape == (2, 2, 49)
