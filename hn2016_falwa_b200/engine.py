@@ -226,20 +226,21 @@ class HostStream:
       (optional, ``want_lwa3d``).
     """
 
-    def __init__(self, plan, chunk=1, want_lwa3d=True, method=0, on_height_grid=False):
+    def __init__(self, plan, chunk=1, want_lwa3d=True, method=0, on_height_grid=False, input_dtype=torch.float64):
         self.plan, self.chunk, self.want_lwa3d, self.method = plan, int(chunk), want_lwa3d, method
         self.on_height_grid = on_height_grid
+        self.input_dtype = input_dtype   # float32 host inputs (ERA5's native precision) are widened on the device
         self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
         nl = plan.kmax if on_height_grid else plan.nlev
         shape = (self.chunk, nl, plan.nlat, plan.nlon)
-        self.slots = [tuple(torch.empty(shape, dtype=torch.float64, device="cuda") for _ in range(3)) for _ in range(2)]
+        self.slots = [tuple(torch.empty(shape, dtype=input_dtype, device="cuda") for _ in range(3)) for _ in range(2)]
         self.ev_in = [torch.cuda.Event() for _ in range(2)]
         self.ev_free = [torch.cuda.Event() for _ in range(2)]
         self.h2d_bytes = self.d2h_bytes = 0
 
     @staticmethod
-    def pinned(shape):
-        return torch.empty(shape, dtype=torch.float64).pin_memory()
+    def pinned(shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype).pin_memory()
 
     def alloc_outputs(self, n):
         p = self.plan
@@ -255,16 +256,19 @@ class HostStream:
             self.s_in.wait_event(self.ev_free[slot])
             for dst, src in zip(self.slots[slot], host):
                 dst[:hi - lo].copy_(src[lo:hi], non_blocking=True)
-                self.h2d_bytes += (hi - lo) * dst[0].numel() * 8
+                self.h2d_bytes += (hi - lo) * dst[0].numel() * dst.element_size()
             self.ev_in[slot].record(self.s_in)
 
-    def run(self, u, v, t, out=None):
-        """u, v, t: pinned float64 host tensors [N][nlev][nlat][nlon] (NumPy arrays are staged through pinned
-        memory first).  Returns the dict of pinned host result tensors (``out`` is reused when given)."""
+    def run(self, u, v, t, out=None, cycles=1):
+        """u, v, t: pinned host tensors [N][nlev][nlat][nlon] of ``input_dtype`` (NumPy arrays are staged through
+        pinned memory first).  Returns the dict of pinned host result tensors (``out`` is reused when given).
+        ``cycles`` > 1 streams the same N host snapshots that many times through one uninterrupted pipeline (the
+        results of the last cycle remain in ``out``): a long time series without holding it all in host memory."""
         host = []
         for x in (u, v, t):
             if not isinstance(x, torch.Tensor):
-                x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+                x = torch.from_numpy(np.ascontiguousarray(x))
+            x = x.to(self.input_dtype)
             if not x.is_pinned():
                 x = x.pin_memory()
             host.append(x)
@@ -275,14 +279,15 @@ class HostStream:
         main = torch.cuda.current_stream()
         for e in self.ev_free:
             e.record(main)
-        bounds = [(lo, min(n, lo + self.chunk)) for lo in range(0, n, self.chunk)]
+        bounds = [(lo, min(n, lo + self.chunk)) for lo in range(0, n, self.chunk)] * int(cycles)
         self._h2d(0, host, *bounds[0])
         for c, (lo, hi) in enumerate(bounds):
             slot = c & 1
             if c + 1 < len(bounds):
                 self._h2d(slot ^ 1, host, *bounds[c + 1])
             main.wait_event(self.ev_in[slot])
-            b = QGBatch(self.plan, *(x[:hi - lo] for x in self.slots[slot]), on_height_grid=self.on_height_grid)
+            b = QGBatch(self.plan, *(x[:hi - lo].to(torch.float64) for x in self.slots[slot]),
+                        on_height_grid=self.on_height_grid)
             b.run(method=self.method)
             self.ev_free[slot].record(main)
             done = torch.cuda.Event()
