@@ -6,6 +6,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <vector>
+#include <thread>
+#include <atomic>
+#include <algorithm>
 #include "../../include/falwa_b200.h"
 
 #define FALWA_CUDA_TRY(expr)                         \

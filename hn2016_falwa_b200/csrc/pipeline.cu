@@ -124,14 +124,19 @@ area_hist3_kernel(int nlon, int nlat, int kmax, int nb, int with_avort, const do
 //   qref_st[k][nlat] <- stored (normalised) qref ; qref_cu = ((qref_st*2)*omega)*sin(lat)
 // ---------------------------------------------------------------------------------------------
 __global__ void merge_refstates_kernel(int kmax, int nlat, int nd, int jd, int north_only, double qscale, double omega,
-                                       const double* __restrict__ sinlat, const double* __restrict__ qN,
-                                       const double* __restrict__ qS, const double* __restrict__ uN,
-                                       const double* __restrict__ uS, const double* __restrict__ tN,
-                                       const double* __restrict__ tS, double* __restrict__ qref_st,
+                                       const double* __restrict__ sinlat, const double* __restrict__ work, size_t per,
+                                       size_t njk, size_t njd, double* __restrict__ qref_st,
                                        double* __restrict__ qref_cu, double* __restrict__ uref_st,
                                        double* __restrict__ ptref_st) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= kmax * nlat) return;
+    {   // blockIdx.y = snapshot; hemispheric work areas: qref at 0, uref at 6*njk, tref at 6*njk + njd
+        const size_t b = blockIdx.y, o = b * (size_t)kmax * nlat;
+        qref_st += o; qref_cu += o; uref_st += o; ptref_st += o;
+    }
+    const double* wN = work + ((size_t)blockIdx.y * 2 + 0) * per;
+    const double* wS = work + ((size_t)blockIdx.y * 2 + 1) * per;
+    const double *qN = wN, *qS = wS, *uN = wN + 6 * njk, *uS = wS + 6 * njk, *tN = uN + njd, *tS = uS + njd;
     const int k = t / nlat, j = t % nlat;  // global row
     double q, u = 0.0, th = 0.0;
     // south covers rows [0, nd), north rows [nlat-nd, nlat); the equator row takes the southern value
@@ -895,31 +900,48 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
                                                                           extd, d + P->o_da, rows, hist.d, tune_int("FALWA_HIST_RUN", 16)); }
         FALWA_LAUNCH_CHECK();
     }
-    // host-built per-problem tables
+    // host-built per-problem tables (the 2*batch eigen-decompositions run on a few host threads)
     std::vector<double> htab;
     std::vector<size_t> o_spec((size_t)batch * 2), o_amp((size_t)batch * 2);
-    for (int b = 0; b < batch; ++b)
-        for (int hs = 0; hs < 2; ++hs) {
-            // hs 0 = north uses stat_n (row 3), hs 1 = south uses stat_s (row 2)
-            const double* stat = profiles_host + ((size_t)b * 4 + (hs == 0 ? 3 : 2)) * kmax;
-            if (P->kind == 0) {
-                std::vector<double> amp(kmax, 0.), amm(kmax, 0.);
-                for (int k = 2; k <= kmax - 1; ++k) {
-                    const double zk = P->dz * (double)(k - 1), zkp = P->dz * (double)k, zkm = P->dz * (double)(k - 2);
-                    const double zp = 0.5 * (zkp + zk), zmm = 0.5 * (zkm + zk);
-                    const double statp = 0.5 * (stat[k] + stat[k - 1]), statm = 0.5 * (stat[k - 2] + stat[k - 1]);
-                    amp[k - 1] = std::exp(-zp / P->h) * std::exp(rkappa * zp / P->h) / statp;
-                    amm[k - 1] = std::exp(-zmm / P->h) * std::exp(rkappa * zmm / P->h) / statm;
+    {
+        const int m = kmax - 2;
+        const size_t each = (P->kind == 0) ? (size_t)2 * kmax : (size_t)m + 2 * (size_t)m * m + 1;
+        htab.assign(each * batch * 2, 0.0);
+        std::atomic<int> err{0};
+        auto work_fn = [&](int q0, int q1) {
+            for (int q = q0; q < q1; ++q) {
+                const int b = q / 2, hs = q % 2;
+                // hs 0 = north uses stat_n (row 3), hs 1 = south uses stat_s (row 2)
+                const double* stat = profiles_host + ((size_t)b * 4 + (hs == 0 ? 3 : 2)) * kmax;
+                double* dst = htab.data() + each * q;
+                if (P->kind == 0) {
+                    double *amp = dst, *amm = dst + kmax;
+                    for (int k = 2; k <= kmax - 1; ++k) {
+                        const double zk = P->dz * (double)(k - 1), zkp = P->dz * (double)k, zkm = P->dz * (double)(k - 2);
+                        const double zp = 0.5 * (zkp + zk), zmm = 0.5 * (zkm + zk);
+                        const double statp = 0.5 * (stat[k] + stat[k - 1]), statm = 0.5 * (stat[k - 2] + stat[k - 1]);
+                        amp[k - 1] = std::exp(-zp / P->h) * std::exp(rkappa * zp / P->h) / statp;
+                        amm[k - 1] = std::exp(-zmm / P->h) * std::exp(rkappa * zmm / P->h) / statm;
+                    }
+                    o_amp[q] = each * q;
+                } else {
+                    std::vector<double> spec;
+                    if (vertical_operator_spectrum(kmax, stat, P->dz, P->h, rkappa, spec)) { err = 1; continue; }
+                    std::copy(spec.begin(), spec.end(), dst);
+                    o_spec[q] = each * q;
                 }
-                o_amp[(size_t)b * 2 + hs] = push_tab(htab, amp);
-                push_tab(htab, amm);
-            } else {
-                std::vector<double> spec;
-                const int er = vertical_operator_spectrum(kmax, stat, P->dz, P->h, rkappa, spec);
-                if (er) return FALWA_ERR_UNSUPPORTED;
-                o_spec[(size_t)b * 2 + hs] = push_tab(htab, spec);
             }
+        };
+        const int nq = batch * 2;
+        const int nthr = (P->kind == 0) ? 1 : std::max(1, std::min({nq / 4, (int)std::thread::hardware_concurrency(), 16}));
+        if (nthr <= 1) work_fn(0, nq);
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nthr; ++t) pool.emplace_back(work_fn, (int)((long long)nq * t / nthr), (int)((long long)nq * (t + 1) / nthr));
+            for (auto& th : pool) th.join();
         }
+        if (err) return FALWA_ERR_UNSUPPORTED;
+    }
     const size_t o_prof = push_tab(htab, std::vector<double>(profiles_host, profiles_host + (size_t)batch * 4 * kmax));
     DeviceTable HT;
     if ((rc = HT.upload(htab, st))) return rc;
@@ -1020,22 +1042,16 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
         { FALWA_KERNEL("sweep_post_kernel", st); sweep_post_kernel<<<nprob, 512, 0, st>>>(dwp.d); }
         FALWA_LAUNCH_CHECK();
         // dsp/dwp/sw are stream-ordered: freed after the kernels that use them
-        for (int b = 0; b < batch; ++b) {
-            { FALWA_KERNEL("merge_refstates_kernel", st); merge_refstates_kernel<<<ceil_div((long long)kmax * nlat, 256), 256, 0, st>>>(
-                kmax, nlat, nd, jd, north_only, 2. * P->omega, P->omega, d + P->o_sinlat, W(b, 0, 0), W(b, 1, 0), WU(b, 0), WU(b, 1),
-                WT(b, 0), WT(b, 1), qref_st + (size_t)b * kmax * nlat, qref_cu + (size_t)b * kmax * nlat,
-                uref_st + (size_t)b * kmax * nlat, ptref_st + (size_t)b * kmax * nlat); }
-            FALWA_LAUNCH_CHECK();
-        }
+        { FALWA_KERNEL("merge_refstates_kernel", st); merge_refstates_kernel<<<dim3(ceil_div((long long)kmax * nlat, 256), batch), 256, 0, st>>>(
+            kmax, nlat, nd, jd, north_only, 2. * P->omega, P->omega, d + P->o_sinlat, work.d, per, njk, njd, qref_st, qref_cu,
+            uref_st, ptref_st); }
+        FALWA_LAUNCH_CHECK();
     }
     if (P->kind == 0) {
-        for (int b = 0; b < batch; ++b) {
-            { FALWA_KERNEL("merge_refstates_kernel", st); merge_refstates_kernel<<<ceil_div((long long)kmax * nlat, 256), 256, 0, st>>>(
-                kmax, nlat, nd, nd, north_only, 1.0, P->omega, d + P->o_sinlat, W(b, 0, 0), W(b, 1, 0), WU(b, 0), WU(b, 1), WT(b, 0),
-                WT(b, 1), qref_st + (size_t)b * kmax * nlat, qref_cu + (size_t)b * kmax * nlat,
-                uref_st + (size_t)b * kmax * nlat, ptref_st + (size_t)b * kmax * nlat); }
-            FALWA_LAUNCH_CHECK();
-        }
+        { FALWA_KERNEL("merge_refstates_kernel", st); merge_refstates_kernel<<<dim3(ceil_div((long long)kmax * nlat, 256), batch), 256, 0, st>>>(
+            kmax, nlat, nd, nd, north_only, 1.0, P->omega, d + P->o_sinlat, work.d, per, njk, njd, qref_st, qref_cu, uref_st,
+            ptref_st); }
+        FALWA_LAUNCH_CHECK();
     }
     FALWA_CUDA_TRY(cudaMemcpyAsync(num_of_iter_host, nit.d, sizeof(int) * nprob, cudaMemcpyDeviceToHost, st));
     FALWA_CUDA_TRY(cudaStreamSynchronize(st));
