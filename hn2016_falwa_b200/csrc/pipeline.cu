@@ -37,36 +37,44 @@ struct falwa_plan {
 namespace falwa {
 
 // ---------------------------------------------------------------------------------------------
-// three area-analysis histograms in one pass over pv and avort (north: +pv, south: -pv, avort)
-// hist layout: [b][3][k][2][nb]
+// Area-analysis histograms in one pass over pv and avort.
+// hist layout: [b][4][k][2][nb]   slot 0: +pv (northern frame), slot 2: avort,
+//                                  slot 1 / 3: the southern / northern contributions of "edge" points only.
+// The southern analysis histograms -pv from its own maximum: ind_S = 1 + int((q - pmin)/dq).  Because
+// (pmax - q) + (q - pmin) = (nb-1) dq, ind_S = nb - ind_N unless the quotient lies within rounding distance of an
+// integer (area_bin's edge test, |frac| < 1e-9), so the southern histogram is the MIRROR of the northern one and is
+// not accumulated at all: refstate_level_kernel forms  S[m] = (N - N_edge)[nb - m] (sign-flipped circulation)
+// + S_edge[m],  where the edge points (exactly classified with the reference's divisions) go to slots 1 and 3.
+// NEED_QN: the circulation sums of the pv histogram are only needed by the NH18 boundary condition.
 // ---------------------------------------------------------------------------------------------
+template <bool NEED_QN>
 __device__ __forceinline__ void hist_flush(double* sh, int nb, int cur, double sa, double sc) {
     if (cur > 0) {
         atomicAdd(&sh[cur - 1], sa);
-        atomicAdd(&sh[nb + cur - 1], sc);
+        if (NEED_QN) atomicAdd(&sh[nb + cur - 1], sc);
     }
 }
 
+template <bool NEED_QN, bool WITH_V>
 __global__ void __launch_bounds__(256)
-area_hist3_kernel(int nlon, int nlat, int kmax, int nb, int with_avort, const double* __restrict__ pv,
+area_hist3_kernel(int nlon, int nlat, int kmax, int nb, const double* __restrict__ pv,
                   const double* __restrict__ avort, const unsigned long long* __restrict__ ext,
                   const double* __restrict__ da, int rows_per_block, double* __restrict__ hist, int run) {
-    extern __shared__ double sh[];  // [3][2][nb]
+    extern __shared__ double sh[];  // [4][2][nb]
     const int k = blockIdx.y + 1, b = blockIdx.z;
-    const int nh = with_avort ? 3 : 2;
     pv += (size_t)b * nlon * nlat * kmax;
-    if (avort) avort += (size_t)b * nlon * nlat * kmax;
+    if (WITH_V) avort += (size_t)b * nlon * nlat * kmax;
     ext += (size_t)b * 2 * kmax * 2;
-    hist += (size_t)b * 3 * kmax * 2 * nb;
-    for (int t = threadIdx.x; t < nh * 2 * nb; t += blockDim.x) sh[t] = 0.0;
+    hist += (size_t)b * 4 * kmax * 2 * nb;
+    for (int t = threadIdx.x; t < 4 * 2 * nb; t += blockDim.x) sh[t] = 0.0;
     __syncthreads();
     const double pmax = ordered_to_f64(ext[k * 2 + 0]), pmin = ordered_to_f64(ext[k * 2 + 1]);
     const double dqp = (pmax - pmin) / (double)(nb - 1);
     const double smax = -pmin;                      // southern frame: q' = -pv, max' = -min
     const double dqs = (smax - (-pmax)) / (double)(nb - 1);
-    const double rdqp = 1. / dqp, rdqs = 1. / dqs;
+    const double rdqp = 1. / dqp;
     double vmax = 0., dqv = 1.;
-    if (with_avort) {
+    if (WITH_V) {
         vmax = ordered_to_f64(ext[(kmax + k) * 2 + 0]);
         const double vmin = ordered_to_f64(ext[(kmax + k) * 2 + 1]);
         dqv = (vmax - vmin) / (double)(nb - 1);
@@ -77,8 +85,9 @@ area_hist3_kernel(int nlon, int nlat, int kmax, int nb, int with_avort, const do
     const int total = (j1 - j0) * runs_per_row;
     const size_t lev = (size_t)k * nlat * nlon;
     double* hN = sh;
-    double* hS = sh + 2 * nb;
+    double* hSx = sh + 2 * nb;
     double* hV = sh + 4 * nb;
+    double* hNx = sh + 6 * nb;
     const int nrows = j1 - j0;
     for (int t = threadIdx.x; t < total; t += blockDim.x) {
         // consecutive lanes take the same longitude run of consecutive ROWS: PV differs from row to row, so the
@@ -86,30 +95,32 @@ area_hist3_kernel(int nlon, int nlat, int kmax, int nb, int with_avort, const do
         const int j = j0 + t % nrows;
         const int i0 = (t / nrows) * run, i1 = min(nlon, i0 + run);
         const double daj = da[j];
-        int cn = -1, cs = -1, cv = -1;
-        double an = 0, qn = 0, as = 0, qs = 0, av = 0, qv = 0;
+        int cn = -1, cv = -1;
+        double an = 0, qn = 0, av = 0, qv = 0;
         for (int i = i0; i < i1; ++i) {
             const double q = pv[lev + (size_t)j * nlon + i];
-            int ind = area_bin(pmax, q, dqp, rdqp, nb);
-            if (ind != cn) { hist_flush(hN, nb, cn, an, qn); cn = ind; an = 0; qn = 0; }
+            bool edge;
+            int ind = area_bin(pmax, q, dqp, rdqp, nb, &edge);
+            if (ind != cn) { hist_flush<NEED_QN>(hN, nb, cn, an, qn); cn = ind; an = 0; qn = 0; }
             an += daj; qn += daj * q;
-            const double qq = -q;
-            ind = area_bin(smax, qq, dqs, rdqs, nb);
-            if (ind != cs) { hist_flush(hS, nb, cs, as, qs); cs = ind; as = 0; qs = 0; }
-            as += daj; qs += daj * qq;
-            if (with_avort) {
+            if (edge) {  // rare: classify the southern bin with the reference's own division
+                const double qq = -q;
+                const int is = max(1, min(nb, 1 + (int)((smax - qq) / dqs)));
+                atomicAdd(&hSx[is - 1], daj); atomicAdd(&hSx[nb + is - 1], daj * qq);
+                atomicAdd(&hNx[ind - 1], daj); atomicAdd(&hNx[nb + ind - 1], daj * q);
+            }
+            if (WITH_V) {
                 const double w = avort[lev + (size_t)j * nlon + i];
                 ind = area_bin(vmax, w, dqv, rdqv, nb);
-                if (ind != cv) { hist_flush(hV, nb, cv, av, qv); cv = ind; av = 0; qv = 0; }
+                if (ind != cv) { hist_flush<true>(hV, nb, cv, av, qv); cv = ind; av = 0; qv = 0; }
                 av += daj; qv += daj * w;
             }
         }
-        hist_flush(hN, nb, cn, an, qn);
-        hist_flush(hS, nb, cs, as, qs);
-        if (with_avort) hist_flush(hV, nb, cv, av, qv);
+        hist_flush<NEED_QN>(hN, nb, cn, an, qn);
+        if (WITH_V) hist_flush<true>(hV, nb, cv, av, qv);
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < nh * 2 * nb; t += blockDim.x) {
+    for (int t = threadIdx.x; t < 4 * 2 * nb; t += blockDim.x) {
         const double x = sh[t];
         if (x != 0.0) {
             const int hsel = t / (2 * nb), r = t % (2 * nb);
@@ -550,7 +561,7 @@ refstate_level_kernel(LevelArgs p) {
     }
     if (!interior) return;
     const unsigned long long* extb = p.ext + (size_t)b * 2 * kmax * 2;
-    const double* histb = p.hist + (size_t)b * 3 * kmax * 2 * nb;
+    const double* histb = p.hist + (size_t)b * 4 * kmax * 2 * nb;
     double qmax = ordered_to_f64(extb[k * 2 + 0]), qmin = ordered_to_f64(extb[k * 2 + 1]);
     if (sgn < 0) { const double t = qmax; qmax = -qmin; qmin = -t; }
     const double dq = (qmax - qmin) / (double)(nb - 1);
@@ -561,10 +572,19 @@ refstate_level_kernel(LevelArgs p) {
         dqv = (vmax - vmin) / (double)(nb - 1);
     }
     {   // cumulative sums in the reference's order (bin 1 is never added)
-        const double* an = histb + ((size_t)hs * kmax + k) * 2 * nb;
-        const double* av = histb + ((size_t)2 * kmax + k) * 2 * nb;
+        const double* an = histb + ((size_t)0 * kmax + k) * 2 * nb;     // +pv, all points
+        const double* sx = histb + ((size_t)1 * kmax + k) * 2 * nb;     // southern bins of the edge points
+        const double* av = histb + ((size_t)2 * kmax + k) * 2 * nb;     // avort
+        const double* nx = histb + ((size_t)3 * kmax + k) * 2 * nb;     // northern bins of the edge points
         for (int t = tid; t < nb; t += blockDim.x) {
-            aan[t] = an[t]; ccn[t] = an[nb + t];
+            if (hs == 0) {
+                aan[t] = an[t]; ccn[t] = an[nb + t];
+            } else {   // mirror: southern bin t <- northern bin nb-2-t (circulation changes sign), plus the edge points
+                const int tn = nb - 2 - t;
+                double a = sx[t], c = sx[nb + t];
+                if (tn >= 0) { a += an[tn] - nx[tn]; c += -(an[nb + tn] - nx[nb + tn]); }
+                aan[t] = a; ccn[t] = c;
+            }
             if (do_vort) { aav[t] = av[t]; ccv[t] = av[nb + t]; }
         }
         __syncthreads();
@@ -874,7 +894,7 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
         if ((rc = zm.alloc((size_t)batch * 3 * kmax * nlat, st))) return rc;
         if ((rc = ext.alloc((size_t)batch * 2 * kmax * 2, st))) return rc;
     }
-    if ((rc = hist.alloc((size_t)batch * 3 * kmax * 2 * nb, st, true))) return rc;
+    if ((rc = hist.alloc((size_t)batch * 4 * kmax * 2 * nb, st, true))) return rc;
     if ((rc = nit.alloc((size_t)batch * 2, st, true))) return rc;
     // per (b, hemisphere): qref, cref, cbar, ubar, tbar [njk each]; uref, tref [njd]; fjk [njk]; tb[kmax]; uz[nd]
     const size_t per = 6 * njk + 2 * njd + kmax + nd;
@@ -892,12 +912,17 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
         int slabs = std::max(1, std::min(nlat, (148 * tune_int("FALWA_HIST_CTAS", 8) + (kmax - 3)) / (kmax - 2) / std::max(1, std::min(batch, 4))));
         const int rows = ceil_div(nlat, slabs);
         slabs = ceil_div(nlat, rows);
-        const int nh = (P->kind == 0) ? 2 : 3;
-        const size_t smem = sizeof(double) * nh * 2 * nb;
-        if (smem > 48 * 1024)
-            FALWA_CUDA_TRY(cudaFuncSetAttribute(area_hist3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        { FALWA_KERNEL("area_hist3_kernel", st); area_hist3_kernel<<<dim3(slabs, kmax - 2, batch), 256, smem, st>>>(nlon, nlat, kmax, nb, P->kind != 0, qgpv, avort,
-                                                                          extd, d + P->o_da, rows, hist.d, tune_int("FALWA_HIST_RUN", 16)); }
+        const size_t smem = sizeof(double) * 4 * 2 * nb;
+        const int hrun = tune_int("FALWA_HIST_RUN", 16);
+        dim3 hgrid(slabs, kmax - 2, batch);
+        FALWA_KERNEL("area_hist3_kernel", st);
+        if (P->kind == 0) {  // NH18: pv histogram with circulation sums (SOR boundary condition), no vorticity histogram
+            FALWA_CUDA_TRY(cudaFuncSetAttribute(area_hist3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            area_hist3_kernel<true, false><<<hgrid, 256, smem, st>>>(nlon, nlat, kmax, nb, qgpv, avort, extd, d + P->o_da, rows, hist.d, hrun);
+        } else {             // NHN22: areas of the pv histogram, areas + circulation of the vorticity histogram
+            FALWA_CUDA_TRY(cudaFuncSetAttribute(area_hist3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            area_hist3_kernel<false, true><<<hgrid, 256, smem, st>>>(nlon, nlat, kmax, nb, qgpv, avort, extd, d + P->o_da, rows, hist.d, hrun);
+        }
         FALWA_LAUNCH_CHECK();
     }
     // host-built per-problem tables (the 2*batch eigen-decompositions run on a few host threads)

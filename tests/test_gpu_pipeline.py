@@ -131,3 +131,51 @@ def test_northern_hemisphere_results_only_and_errors():
         g.compute_lwa_and_barotropic_fluxes()
     g.compute_lwa_only()
     assert g.lwa.shape == (49, 49, 96) and np.isfinite(g.lwa_baro).all()
+
+
+@pytest.mark.parametrize("kind", ["nh18", "nhn22"])
+def test_area_bins_on_exact_bin_edges(kind):
+    """Every QGPV value sits exactly on a histogram bin edge (integers, qmax - qmin = nb - 1): the fast reciprocal
+    binning must fall back to the reference's division, and the mirrored southern histogram must take its bins from
+    the exactly classified edge points.  Qref of both hemispheres has to match the oracle's routine."""
+    from hn2016_falwa_b200 import engine
+    from oracle import f2py_shim as ora
+    import torch
+    inputs = testdata.synthetic_snapshot(nlon=96, nlat=49, seed=5)
+    f = _cls(kind)(*inputs)
+    b = f._batch
+    b.interpolate_fields()
+    q = b.qgpv[0].cpu().numpy()
+    nb = 49
+    lo, hi = q.min(axis=(1, 2), keepdims=True), q.max(axis=(1, 2), keepdims=True)
+    span = np.where(hi > lo, hi - lo, 1.0)
+    qi = np.rint((q - lo) / span * (nb - 1))            # integers 0..nb-1 on every interior level
+    qi[0] = 0.0; qi[-1] = 0.0
+    b.qgpv = torch.from_numpy(qi[None].copy()).cuda()
+    b.zm = b.ext = None
+    b.compute_reference_states()
+    got = b.qref_st[0].cpu().numpy()                     # (kmax, nlat), stored normalisation
+    c = pipeline.run_qgfield(kind, *inputs, stages=("interp",))["config"]
+    pv, uu, pt, av = (np.swapaxes(x, 0, 2) for x in (qi, b.u[0].cpu().numpy(), b.theta[0].cpu().numpy(),
+                                                     b.avort[0].cpu().numpy()))
+    prof = b.profiles[0]
+    eq = c["equator_idx"]
+    for hemi in ("north", "south"):
+        if hemi == "north":
+            args = (pv, uu, av, pt)
+        else:
+            args = (-pv[:, ::-1, :], uu[:, ::-1, :], av[:, ::-1, :], pt[:, ::-1, :])
+        if kind == "nhn22":
+            want = ora.compute_qref_and_fawa_first(pv=args[0], uu=args[1], vort=args[2], pt=args[3], tn0=prof[1],
+                                                   nd=eq, nnd=49, jb=c["jb"], jd=c["jd"], a=c["a"], omega=c["omega"],
+                                                   dz=c["dz"], h=c["h"], dphi=c["dphi"], dlambda=c["dlambda"],
+                                                   rr=c["rr"], cp=c["cp"])[0] / (2. * c["omega"])
+        else:
+            want = ora.compute_reference_states(pv=args[0], uu=args[1], pt=args[3], stat=prof[2], jd=eq, npart=49,
+                                                maxits=5, a=c["a"], om=c["omega"], dz=c["dz"], eps=1e-5, h=c["h"],
+                                                dphi=c["dphi"], dlambda=c["dlambda"], r=c["rr"], cp=c["cp"],
+                                                rjac=0.95)[0]
+        mine = got[:, -eq:].T if hemi == "north" else got[:, :eq][:, ::-1].T
+        rows = slice(1, None) if hemi == "north" else slice(1, None)   # the equator row belongs to the south
+        compare(f"edges/{kind}/{hemi}/qref", mine[rows, 1:-1], want[rows, 1:-1], rtol=1e-9,
+                atol=1e-12 * np.abs(want).max())
