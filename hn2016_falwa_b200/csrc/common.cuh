@@ -116,12 +116,14 @@ __device__ __forceinline__ double ordered_to_f64(unsigned long long u) {
 // roundings are within 2 ulp of the true quotient (|t| <= nb), so they can truncate differently only when the
 // product lies within ~1e-12 of an integer — then, and only then, the exact division decides.  Bin assignment is
 // therefore identical to the reference's arithmetic for every input.
+__device__ __noinline__ double area_bin_exact(double x, double dq) { return x / dq; }  // kept out of line: rare
+
 __device__ __forceinline__ int area_bin(double qmax, double q, double dq, double rdq, int nb, bool* near_edge = nullptr) {
     const double x = qmax - q;
     double t = x * rdq;
     const double fr = t - floor(t);
     const bool edge = !(fr > 1e-9 && fr < 1. - 1e-9);
-    if (edge) t = x / dq;
+    if (__builtin_expect(edge, 0)) t = area_bin_exact(x, dq);
     if (near_edge) *near_edge = edge;
     return max(1, min(nb, 1 + (int)t));
 }

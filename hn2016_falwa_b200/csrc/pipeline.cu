@@ -97,25 +97,42 @@ area_hist3_kernel(int nlon, int nlat, int kmax, int nb, const double* __restrict
         const double daj = da[j];
         int cn = -1, cv = -1;
         double an = 0, qn = 0, av = 0, qv = 0;
-        for (int i = i0; i < i1; ++i) {
-            const double q = pv[lev + (size_t)j * nlon + i];
+        auto point = [&](double q, double w) {
             bool edge;
             int ind = area_bin(pmax, q, dqp, rdqp, nb, &edge);
             if (ind != cn) { hist_flush<NEED_QN>(hN, nb, cn, an, qn); cn = ind; an = 0; qn = 0; }
             an += daj; qn += daj * q;
-            if (edge) {  // rare: classify the southern bin with the reference's own division
+            if (__builtin_expect(edge, 0)) {  // rare: classify the southern bin with the reference's own division
                 const double qq = -q;
-                const int is = max(1, min(nb, 1 + (int)((smax - qq) / dqs)));
+                const int is = max(1, min(nb, 1 + (int)area_bin_exact(smax - qq, dqs)));
                 atomicAdd(&hSx[is - 1], daj); atomicAdd(&hSx[nb + is - 1], daj * qq);
                 atomicAdd(&hNx[ind - 1], daj); atomicAdd(&hNx[nb + ind - 1], daj * q);
             }
             if (WITH_V) {
-                const double w = avort[lev + (size_t)j * nlon + i];
                 ind = area_bin(vmax, w, dqv, rdqv, nb);
                 if (ind != cv) { hist_flush<true>(hV, nb, cv, av, qv); cv = ind; av = 0; qv = 0; }
                 av += daj; qv += daj * w;
             }
+        };
+        const size_t row = lev + (size_t)j * nlon;
+        int i = i0;
+        if (((row + i0) & 1) == 0) {
+            // 16-byte vector loads, eight points (four double2 per field) in flight per lane: the lanes of a warp
+            // read different rows, so every access is its own sector and memory-level parallelism has to come
+            // from the thread itself
+            for (; i + 8 <= i1; i += 8) {
+                double2 a[4], c[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    a[v] = __ldg(reinterpret_cast<const double2*>(pv + row + i) + v);
+                    if (WITH_V) c[v] = __ldg(reinterpret_cast<const double2*>(avort + row + i) + v);
+                    else c[v] = make_double2(0., 0.);
+                }
+#pragma unroll
+                for (int v = 0; v < 4; ++v) { point(a[v].x, c[v].x); point(a[v].y, c[v].y); }
+            }
         }
+        for (; i < i1; ++i) point(pv[row + i], WITH_V ? avort[row + i] : 0.0);
         hist_flush<NEED_QN>(hN, nb, cn, an, qn);
         if (WITH_V) hist_flush<true>(hV, nb, cv, av, qv);
     }
@@ -843,11 +860,6 @@ extern "C" int falwa_b200_interpolate_fields(const falwa_plan* P, int batch, con
     const double* d = P->d_tab;
     const int kmax = P->kmax;
     int rc;
-    if (!already_on_height_grid) {
-        if ((rc = interp_launch(P->nlon, P->nlat, P->nlev, kmax, batch, u_in, v_in, t_in, P->d_lo, d + P->o_whi,
-                                d + P->o_wlo, d + P->o_fac, u, v, theta, st)))
-            return rc;
-    }
     // profiles + reciprocal static stability: [batch][6][kmax]
     std::vector<double> hp((size_t)batch * 6 * kmax);
     for (int b = 0; b < batch; ++b) {
@@ -858,11 +870,22 @@ extern "C" int falwa_b200_interpolate_fields(const falwa_plan* P, int batch, con
     }
     DeviceTable prof;
     if ((rc = prof.upload(hp, st))) return rc;
+    const int jdsplit = (P->kind == 0) ? P->nlat : P->nd;  // NHN22: rows j <= equator use the southern profile
+    if (!already_on_height_grid && !(zm && ext) && tune_int("FALWA_FUSED_STAGE1", 1)) {
+        // one pass: interpolation + absolute vorticity + QGPV
+        return interp_qgpv_launch(P->kind == 0 ? 0 : 1, P->nlon, P->nlat, P->nlev, kmax, jdsplit, batch, u_in, v_in, t_in,
+                                  P->d_lo, d + P->o_whi, d + P->o_wlo, d + P->o_fac, d + P->o_qg, prof.d, u, v, theta, qgpv,
+                                  avort, st);
+    }
+    if (!already_on_height_grid) {
+        if ((rc = interp_launch(P->nlon, P->nlat, P->nlev, kmax, batch, u_in, v_in, t_in, P->d_lo, d + P->o_whi,
+                                d + P->o_wlo, d + P->o_fac, u, v, theta, st)))
+            return rc;
+    }
     DeviceScratch<double> part;
     if (zm && ext) {
         if ((rc = part.alloc((size_t)batch * 3 * kmax * P->nlat * ceil_div(P->nlon, 32), st))) return rc;
     }
-    const int jdsplit = (P->kind == 0) ? P->nlat : P->nd;  // NHN22: rows j <= equator use the southern profile
     return qgpv_launch(P->kind == 0 ? 0 : 1, P->nlon, P->nlat, kmax, jdsplit, batch, u, v, theta, d + P->o_qg, prof.d,
                        qgpv, avort, st, 1, zm, (unsigned long long*)ext, part.d);
 }
@@ -913,7 +936,7 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
         const int rows = ceil_div(nlat, slabs);
         slabs = ceil_div(nlat, rows);
         const size_t smem = sizeof(double) * 4 * 2 * nb;
-        const int hrun = tune_int("FALWA_HIST_RUN", 16);
+        const int hrun = tune_int("FALWA_HIST_RUN", 32);
         dim3 hgrid(slabs, kmax - 2, batch);
         FALWA_KERNEL("area_hist3_kernel", st);
         if (P->kind == 0) {  // NH18: pv histogram with circulation sums (SOR boundary condition), no vorticity histogram

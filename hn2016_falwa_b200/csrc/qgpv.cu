@@ -422,6 +422,121 @@ theta_hemi_kernel(int nlat, int nlev, int jd, const double* __restrict__ rowmean
     if (threadIdx.x == 0) out[((size_t)b * 2 + hemi) * nlev + l] = s / c;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused stage 1 (pipeline path): vertical interpolation of u, v, theta AND the absolute-vorticity / QGPV stencils in
+// one pass, so the interpolated fields are written once and never read back (2957 MB instead of 4178 MB of traffic
+// per 0.25-degree snapshot).  Each thread owns one (lon, lat) column and keeps seven rolling interpolation series in
+// registers — its own u, v, theta plus u at (j+1), (j-1) and v at (i+1), (i-1), whose input levels the neighbouring
+// threads load as their own (L1/L2 hits) — evaluated with exactly the arithmetic of interp_kernel, so the stencil
+// sees bit-identical values to the unfused path.  QGPV of level k-1 is emitted at iteration k (it needs theta(k)).
+// The input levels of the next bracket are loaded one iteration ahead (register prefetch).
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256, 2)
+interp_qgpv_kernel(int nlon, int nlat, int nlev, int kmax, int jd, const double* __restrict__ uin,
+                   const double* __restrict__ vin, const double* __restrict__ tin, const int* __restrict__ lo,
+                   const double* __restrict__ whi, const double* __restrict__ wlo, const double* __restrict__ fac,
+                   QgpvTables tb, const double* __restrict__ prof, double* __restrict__ uo, double* __restrict__ vo,
+                   double* __restrict__ to, double* __restrict__ avort, double* __restrict__ pv, size_t in_stride,
+                   size_t out_stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int b = blockIdx.z;
+    if (i >= nlon || j >= nlat) return;
+    const size_t plane = (size_t)nlon * nlat;
+    uin += (size_t)b * in_stride; vin += (size_t)b * in_stride; tin += (size_t)b * in_stride;
+    uo += (size_t)b * out_stride; vo += (size_t)b * out_stride; to += (size_t)b * out_stride;
+    avort += (size_t)b * out_stride; pv += (size_t)b * out_stride;
+    const bool interior_row = (j >= 1 && j <= nlat - 2);
+    const int ip = (i == nlon - 1) ? 0 : i + 1, im = (i == 0) ? nlon - 1 : i - 1;
+    const size_t col = (size_t)j * nlon + i;
+    const size_t cvp = (size_t)j * nlon + ip, cvm = (size_t)j * nlon + im;
+    const size_t cup = interior_row ? col + nlon : col, cum = interior_row ? col - nlon : col;
+    const double av1 = tb.av1[j], cp = tb.cosp[j], cm = tb.cosm[j], rden = tb.rden[j];
+    const int hemi = (j + 1 <= jd) ? 0 : 1;
+    const double* t0 = prof + (size_t)b * 6 * kmax + hemi * kmax;
+    const double* rstat = t0 + 4 * kmax;
+    struct Lev { double u, v, t, up, um, vp, vm; };
+    auto load = [&](int l) -> Lev {
+        Lev r;
+        const size_t off = (size_t)l * plane;
+        r.u = ld_stream(&uin[off + col]); r.v = ld_stream(&vin[off + col]); r.t = ld_stream(&tin[off + col]) * fac[l];
+        r.up = uin[off + cup]; r.um = uin[off + cum]; r.vp = vin[off + cvp]; r.vm = vin[off + cvm];
+        return r;
+    };
+    int cur = lo[0];
+    Lev L0 = load(cur), L1 = load(cur + 1);
+    Lev P = L1;              // prefetched level `pre`
+    int pre = -1;
+    double am = 0.0, ac = 0.0, av_prev = 0.0;   // alt(k-2), alt(k-1), avort(k-1)
+    for (int k = 0; k < kmax; ++k) {
+        const int l = lo[k];
+        if (l != cur) {      // advance the bracket (the tables only ever move upward)
+            if (l == cur + 1) { L0 = L1; L1 = (pre == l + 1) ? P : load(l + 1); }
+            else { L0 = (pre == l) ? P : load(l); L1 = load(l + 1); }
+            cur = l;
+        }
+        if (k + 1 < kmax) {  // issue the loads of the next bracket now; they land while this level is evaluated
+            const int ln = lo[k + 1];
+            if (ln != cur) { pre = (ln == cur + 1) ? ln + 1 : ln; P = load(pre); }
+        }
+        const double a1 = whi[k], a0 = wlo[k];
+        const double u = a1 * L1.u + a0 * L0.u, v = a1 * L1.v + a0 * L0.v, th = a1 * L1.t + a0 * L0.t;
+        const size_t off = (size_t)k * plane;
+        st_stream(&uo[off + col], u);
+        st_stream(&vo[off + col], v);
+        st_stream(&to[off + col], th);
+        double av = 0.0;
+        if (interior_row) {
+            const double upv = a1 * L1.up + a0 * L0.up, umv = a1 * L1.um + a0 * L0.um;
+            const double vpv = a1 * L1.vp + a0 * L0.vp, vmv = a1 * L1.vm + a0 * L0.vm;
+            const double dv = vpv - vmv;
+            const double du = -(upv * cp - umv * cm);
+            av = av1 + dv * rden + du * rden;
+        }
+        st_stream(&avort[off + col], av);
+        const double ap = tb.ep[k] * (th - t0[k]) * rstat[k];      // alt(k)
+        if (k == 0) st_stream(&pv[col], 0.0);
+        if (k >= 2) {                                               // QGPV of level k-1
+            double q;
+            if (MODE == 0) q = ap - am;
+            else q = av_prev + tb.e0[k - 1] * ((ap - am) * av1 * tb.rdh[k - 1]);
+            st_stream(&pv[off - plane + col], q);
+        }
+        if (k == kmax - 1) st_stream(&pv[off + col], 0.0);
+        am = ac; ac = ap; av_prev = av;
+    }
+}
+
+// fused stage 1: interpolation + avort + QGPV (mode 0 NH18 / 1 NHN22), then the polar rows (and the NH18 finish)
+int interp_qgpv_launch(int mode, int nlon, int nlat, int nlev, int kmax, int jd, int batch, const double* uin,
+                       const double* vin, const double* tin, const int* lo, const double* whi, const double* wlo,
+                       const double* fac, const double* d_tables, const double* d_prof6, double* uo, double* vo,
+                       double* to, double* pv, double* avort, cudaStream_t st) {
+    const QgpvTables tb = view_tables(d_tables, nlat, kmax);
+    const size_t plane = (size_t)nlon * nlat;
+    dim3 block(32, 8), grid(ceil_div(nlon, 32), ceil_div(nlat, 8), batch);
+    QgpvStats stt;
+    stt.part = nullptr; stt.ext = nullptr; stt.nwx = 0;
+    {
+        FALWA_KERNEL("interp_qgpv_kernel", st);
+        if (mode == 0)
+            interp_qgpv_kernel<0><<<grid, block, 0, st>>>(nlon, nlat, nlev, kmax, jd, uin, vin, tin, lo, whi, wlo, fac, tb,
+                                                         d_prof6, uo, vo, to, avort, pv, plane * nlev, plane * kmax);
+        else
+            interp_qgpv_kernel<1><<<grid, block, 0, st>>>(nlon, nlat, nlev, kmax, jd, uin, vin, tin, lo, whi, wlo, fac, tb,
+                                                         d_prof6, uo, vo, to, avort, pv, plane * nlev, plane * kmax);
+    }
+    FALWA_LAUNCH_CHECK();
+    { FALWA_KERNEL("polar_rows_kernel", st); polar_rows_kernel<<<dim3(kmax, 2, batch), 256, 0, st>>>(nlon, nlat, kmax, mode == 1, avort, pv, plane * kmax, stt); }
+    FALWA_LAUNCH_CHECK();
+    if (mode == 0) {
+        { FALWA_KERNEL("nh18_finish_kernel", st); nh18_finish_kernel<<<dim3(nlat, kmax - 2, batch), 256, 0, st>>>(nlon, nlat, kmax, avort, pv, tb, plane * kmax, stt); }
+        FALWA_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 int interp_launch(int nlon, int nlat, int nlev, int kmax, int batch, const double* uin, const double* vin,
                   const double* tin, const int* lo, const double* whi, const double* wlo, const double* fac, double* uo,
                   double* vo, double* to, cudaStream_t st) {
