@@ -250,9 +250,8 @@ lwa_scan_kernel(ScanArgs p) {
     for (int r = lane; r < nd; r += 32) o_[r] = 0.0;
     __syncwarp();
 
-    // 1. E(jj) by binary search (four row chunks interleaved for ILP), rank of every displaced row inside its
-    //    bin (one __match_any_sync per chunk; chunks are visited in ascending row order, so a bin lists its rows
-    //    in ascending order and every sum below is reproducible bit for bit)
+    // 1. E(jj) by cell table + bisection (four row chunks interleaved for ILP) and the slot of every displaced row
+    //    inside its bin
     unsigned long long ccyc = 0, canti = 0;
     for (int r0 = 0; r0 < nd; r0 += 128) {
         double q4[4];
@@ -280,34 +279,20 @@ lwa_scan_kernel(ScanArgs p) {
                 const int mid = (e4[c] + b4[c]) >> 1;
                 if (s_thr[mid] < q4[c]) e4[c] = mid + 1; else b4[c] = mid;
             }
-        unsigned m4[4];
-        bool sc4[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int r = r0 + 32 * c + lane;
-            sc4[c] = false;
             if (r < nd) {
                 const int nx = s_nxt[r + 1], e = e4[c];
                 E_[r] = (short)e;
                 if (e > nx) ccyc += (unsigned)(e - nx); else canti += (unsigned)(nx - e);
-                sc4[c] = (e != nx) && (e < M);
-            }
-            m4[c] = __match_any_sync(FULL, sc4[c] ? e4[c] : (0x4000 + lane));
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if (r0 + 32 * c < nd) {
-                if (sc4[c]) {
-                    const int leader = __ffs(m4[c]) - 1;
-                    int old = 0;
-                    if (lane == leader) { old = cn[e4[c]]; cn[e4[c]] = old + __popc(m4[c]); }
-                    old = __shfl_sync(m4[c], old, leader);
-                    pm[r0 + 32 * c + lane] = (short)(old + __popc(m4[c] & lt_mask));  // rank inside the bin (stash)
-                }
-                __syncwarp();
+                // slot inside the bin: native 32-bit shared-memory atomic (arrival order is arbitrary; step 4 sorts
+                // the few bins that hold more than one row, so every sum is still reproducible bit for bit)
+                if ((e != nx) && (e < M)) pm[r] = (short)atomicAdd(&cn[e], 1);
             }
         }
     }
+    __syncwarp();
     // 2. exclusive scan of the counts -> bin starts; cn[M] = number of displaced rows
     {
         int carry = 0;
@@ -368,7 +353,14 @@ lwa_scan_kernel(ScanArgs p) {
                 }
             }
             // rows leaving (cyclonic) / entering (anticyclonic) at t: E(jj) == t
-            for (int x = cn[t], xe = cn[t + 1]; x < xe; ++x) {
+            const int x0 = cn[t], xe = cn[t + 1];
+            for (int a = x0 + 1; a < xe; ++a) {   // ascending row order inside the bin (insertion sort, bins are tiny)
+                const short v = pm[a];
+                int c = a - 1;
+                for (; c >= x0 && pm[c] > v; --c) pm[c + 1] = pm[c];
+                pm[c + 1] = v;
+            }
+            for (int x = x0; x < xe; ++x) {
                 const int r = pm[x];
                 const double q = q_[r], u = u_[r], cs = s_cos[r + 1];
                 if (t > s_nxt[r + 1]) { S1c -= q * cs; S2c -= cs; } else { S1a += q * cs; S2a += cs; }
