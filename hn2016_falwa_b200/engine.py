@@ -108,6 +108,7 @@ class QGBatch:
             if tuple(x.shape) != exp:
                 raise TypeError(f"Incorrect dimension of {name}_field. Expected dimension: {exp}")
         self.profiles = None          # host [B][4][kmax]: t0_s, t0_n, stat_s, stat_n
+        self.profiles_hemi = None
         self.u = self.v = self.theta = self.avort = self.qgpv = self.zm = self.ext = None
         self.qref_st = self.qref_cu = self.uref = self.ptref = None
         self.num_of_iter = None
@@ -153,6 +154,7 @@ class QGBatch:
     def interpolate_fields(self):
         p = self.plan
         prof = self.static_stability_profiles()
+        self.profiles_hemi = np.ascontiguousarray(prof)   # t0_s, t0_n, stat_s, stat_n before any averaging
         if p.kind == 0:  # NH18 uses the average of the two hemispheres everywhere (oopinterface.py:1567-1580)
             t0 = 0.5 * (prof[:, 0] + prof[:, 1])
             st = 0.5 * (prof[:, 2] + prof[:, 3])
