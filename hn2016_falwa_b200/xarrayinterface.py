@@ -256,8 +256,11 @@ class QGDataset:
                                       None if ncforce is None else ncforce[self._lo:self._hi]):
             for name, arr in out.items():
                 if name not in self._store:
-                    self._store[name] = np.empty((nloc,) + arr.shape[1:], dtype=arr.dtype)
-                self._store[name][lo:hi] = arr
+                    self._store[name] = np.empty((nloc,) + tuple(arr.shape[1:]), dtype=np.float64)
+                if hasattr(out, "copy_into"):     # pinned staging slot: drained by the runner's host threads
+                    out.copy_into(name, self._store[name][lo:hi])
+                else:
+                    self._store[name][lo:hi] = arr
         self._done.update(todo)
 
     def gather(self):
@@ -379,12 +382,13 @@ class QGDataset:
 
 class _DeviceRunner:
     """Runs chunks of snapshots through ``engine.QGBatch`` on the current CUDA device and yields host copies of the
-    requested variables.  The next chunk's inputs are uploaded on a side stream while the current chunk computes."""
-
-    _NAMES2D = None
+    requested variables.  User arrays are pageable NumPy (or lazily loaded) memory, so both directions go through
+    two pinned staging slots: a few host threads fill / drain them (multi-threaded memcpy) while the GPU works on the
+    neighbouring chunk, and the PCIe copies run on side streams."""
 
     def __init__(self, template, chunk=None):
         import torch
+        from concurrent.futures import ThreadPoolExecutor
         from . import engine
         self.torch, self.engine = torch, engine
         self.f = template
@@ -394,6 +398,13 @@ class _DeviceRunner:
             free = torch.cuda.mem_get_info()[0]
             chunk = int(max(1, min(256, 0.4 * free // per)))
         self.chunk = chunk
+        self.pool = ThreadPoolExecutor(max_workers=6)
+
+    def _threaded_copy(self, dst, src):
+        """dst[...] = src with the leading axis split over the pool (np.copyto releases the GIL)."""
+        n = dst.shape[0]
+        step = max(1, -(-n // 6))
+        return [self.pool.submit(np.copyto, dst[i:i + step], src[i:i + step]) for i in range(0, n, step)]
 
     def run(self, u, v, t, stages, want, ncforce=None):
         torch, engine = self.torch, self.engine
@@ -401,24 +412,48 @@ class _DeviceRunner:
         n = u.shape[0]
         nh_only = f.northern_hemisphere_results_only
         on_h = f._data_on_evenly_spaced_pseudoheight_grid
-        side = torch.cuda.Stream()
-
-        def upload(lo, hi):
-            with torch.cuda.stream(side):
-                arrs = [torch.from_numpy(np.ascontiguousarray(x[lo:hi], dtype=np.float64)).pin_memory().cuda(
-                    non_blocking=True) for x in (u, v, t)]
-                ev = torch.cuda.Event()
-                ev.record(side)
-            return arrs, ev
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        shape_in = (self.chunk,) + tuple(u.shape[1:])
+        pin_in = [[torch.empty(shape_in, dtype=torch.float64).pin_memory() for _ in range(3)] for _ in range(2)]
+        dev_in = [[torch.empty(shape_in, dtype=torch.float64, device="cuda") for _ in range(3)] for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        for e in ev_free:
+            e.record(main)
         bounds = [(lo, min(n, lo + self.chunk)) for lo in range(0, n, self.chunk)]
-        nxt = upload(*bounds[0])
+
+        def stage(c):   # host threads: pageable user arrays -> pinned slot
+            lo, hi = bounds[c]
+            futs = []
+            for dst, src in zip(pin_in[c & 1], (u, v, t)):
+                futs += self._threaded_copy(dst.numpy()[:hi - lo], src[lo:hi])
+            return futs
+
+        def upload(c, futs):
+            lo, hi = bounds[c]
+            for fu in futs:
+                fu.result()
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_free[c & 1])
+                for d, p in zip(dev_in[c & 1], pin_in[c & 1]):
+                    d[:hi - lo].copy_(p[:hi - lo], non_blocking=True)
+                ev_in[c & 1].record(s_in)
+
+        eq = f.equator_idx
+        pin_out, out_ev, drain = [dict(), dict()], [None, None], [[], []]
+        upload(0, stage(0))
+        nxt = stage(1) if len(bounds) > 1 else None
+        pending = None
         for c, (lo, hi) in enumerate(bounds):
-            (du, dv, dt_), ev = nxt
-            if c + 1 < len(bounds):
-                nxt = upload(*bounds[c + 1])
-            torch.cuda.current_stream().wait_event(ev)
-            b = engine.QGBatch(self.plan, du, dv, dt_, on_height_grid=on_h, northern_hemisphere_results_only=nh_only)
+            slot = c & 1
+            main.wait_event(ev_in[slot])
+            b = engine.QGBatch(self.plan, *(x[:hi - lo] for x in dev_in[slot]), on_height_grid=on_h,
+                               northern_hemisphere_results_only=nh_only)
             b.interpolate_fields()
+            if c + 1 < len(bounds):      # the pinned slot of chunk c+1 is filled by now (or we wait here), send it
+                upload(c + 1, nxt)
+                nxt = stage(c + 2) if c + 2 < len(bounds) else None
             if "ref" in stages:
                 b.compute_reference_states()
                 if self.plan.kind == 0 and (b.num_of_iter >= f.maxit).any():
@@ -429,24 +464,72 @@ class _DeviceRunner:
                     warnings.warn(msg)
             if "flux" in stages:
                 b.compute_lwa_and_barotropic_fluxes(ncforce=None if ncforce is None else ncforce[lo:hi])
-            out = {}
-            eq = f.equator_idx
-            for name in want:
-                if name == "static_stability":
-                    p = b.profiles
-                    out[name] = p[:, 2].copy() if self.plan.kind == 0 else np.stack([p[:, 2], p[:, 3]], axis=1)
-                    if self.plan.kind == 1 and nh_only:
-                        out[name] = p[:, 3].copy()
-                    continue
-                src = {"qgpv": b.qgpv, "interpolated_u": b.u, "interpolated_v": b.v, "interpolated_theta": b.theta,
-                       "qref": b.qref_cu, "uref": b.uref, "ptref": b.ptref, "lwa": b.lwa}.get(name)
-                if src is None:
-                    src = b.out(name)
-                a = src.cpu().numpy()
-                if nh_only and name not in ("qgpv", "interpolated_u", "interpolated_v", "interpolated_theta"):
-                    a = a[..., -eq:, :] if name in engine.OUT2D or name == "lwa" else a[..., -eq:]
-                out[name] = a
-            yield lo, hi, out
+            ev_free[slot].record(main)
+            done = torch.cuda.Event()
+            done.record(main)
+            # results of this chunk -> pinned slot (side stream) ...
+            for fu in drain[slot]:
+                fu.result()          # the slot's previous contents have been copied out
+            drain[slot] = []
+            host = {}
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                for name in want:
+                    if name == "static_stability":
+                        continue
+                    src = {"qgpv": b.qgpv, "interpolated_u": b.u, "interpolated_v": b.v, "interpolated_theta": b.theta,
+                           "qref": b.qref_cu, "uref": b.uref, "ptref": b.ptref, "lwa": b.lwa}.get(name)
+                    if src is None:
+                        src = b.out(name)
+                    if nh_only and name not in ("qgpv", "interpolated_u", "interpolated_v", "interpolated_theta"):
+                        src = src[..., -eq:, :] if name in engine.OUT2D or name == "lwa" else src[..., -eq:]
+                    src = src.contiguous()
+                    src.record_stream(s_out)
+                    buf = pin_out[slot].get(name)
+                    if buf is None or buf.shape[1:] != src.shape[1:]:
+                        buf = pin_out[slot][name] = torch.empty((self.chunk,) + tuple(src.shape[1:]),
+                                                                dtype=src.dtype).pin_memory()
+                    buf[:hi - lo].copy_(src, non_blocking=True)
+                    host[name] = buf[:hi - lo]
+                out_ev[slot] = torch.cuda.Event()
+                out_ev[slot].record(s_out)
+            if "static_stability" in want:
+                p = b.profiles
+                ss = p[:, 2].copy() if self.plan.kind == 0 else np.stack([p[:, 2], p[:, 3]], axis=1)
+                if self.plan.kind == 1 and nh_only:
+                    ss = p[:, 3].copy()
+                host["static_stability"] = ss
+            # ... and the PREVIOUS chunk, whose copy has had a whole chunk of compute to finish, is handed over
+            if pending is not None:
+                yield pending
+            pending = (lo, hi, _HostChunk(host, out_ev[slot], self, drain[slot]))
+        if pending is not None:
+            yield pending
+        for d in drain:
+            for fu in d:
+                fu.result()
+
+
+class _HostChunk(dict):
+    """Mapping name -> array of one chunk living in a pinned staging slot.  ``copy_into`` drains it into the caller's
+    store with the runner's host threads (and registers the futures that guard the slot's reuse)."""
+
+    def __init__(self, host, event, runner, drain):
+        super().__init__()
+        self._host, self._event, self._runner, self._drain = host, event, runner, drain
+        for k, v in host.items():
+            self[k] = v
+
+    def items(self):
+        self._event.synchronize()
+        for k, v in self._host.items():
+            yield k, (v.numpy() if hasattr(v, "numpy") and not isinstance(v, np.ndarray) else v)
+
+    def copy_into(self, name, dst):
+        self._event.synchronize()
+        v = self._host[name]
+        src = v.numpy() if not isinstance(v, np.ndarray) else v
+        self._drain.extend(self._runner._threaded_copy(dst, src))
 
 
 class _FieldLoopRunner:
