@@ -61,11 +61,13 @@ def test_qgfield_pipeline_matches_oracle(case, kind, method):
     np.testing.assert_array_equal(f.flux_vector_lambda_baro, f.adv_flux_f1 + f.adv_flux_f2 + f.adv_flux_f3)
 
 
-def test_golden_fixture_nhn22_era():
-    """Product path against the committed fixture generated from the reference's own unmodified Python."""
+@pytest.mark.parametrize("kind", ["nh18", "nhn22"])
+def test_golden_fixture_era(kind):
+    """Product path against the committed fixtures generated from the reference's own unmodified Python
+    (BASELINE.json configs 1 and 2: the repo's ERA-Interim 2005-01-23 00Z snapshot)."""
     import os
-    g = np.load(os.path.join(testdata.GOLDEN_DIR, "qgfield_nhn22_era_interim.npz"))
-    f = _cls("nhn22")(*testdata.load_era_snapshot())
+    g = np.load(os.path.join(testdata.GOLDEN_DIR, f"qgfield_{kind}_era_interim.npz"))
+    f = _cls(kind)(*testdata.load_era_snapshot())
     f.interpolate_fields(return_named_tuple=False)
     f.compute_reference_states(return_named_tuple=False)
     f.compute_lwa_and_barotropic_fluxes(return_named_tuple=False)
@@ -74,7 +76,9 @@ def test_golden_fixture_nhn22_era():
         a = np.asarray(getattr(f, name))
         a = a[levels][:, :, ::stride] if a.ndim == 3 else (a[:, ::stride] if a.shape[-1] > 200 else a)
         rtol, atol = TOL.get(name, (1e-8, 1e-9 * float(np.abs(g[name]).max())))
-        compare(f"golden/nhn22/{name}", a, g[name], rtol=rtol, atol=atol)
+        compare(f"golden/{kind}/{name}", a, g[name], rtol=rtol, atol=atol)
+    if kind == "nh18":
+        assert tuple(f._batch.num_of_iter[0]) == tuple(g["num_of_iter"])
 
 
 @pytest.mark.parametrize("kind", ["nh18", "nhn22"])
