@@ -171,23 +171,53 @@ nhn22_spectral_solve_kernel(SpectralCommon c, const SpectralProblem* __restrict_
     __syncthreads();
     // 3. per mode, a scalar tridiagonal solve in latitude (diagonally dominant since lam <= 0):
     //    b_i w(i-1) + a_i w(i+1) + (fact_i*lam - (a_i+b_i)) w(i) = gh(i)
+    //    Only m threads work here and the recurrence is sequential, so the operands of eight steps are loaded up
+    //    front (independent of the recurrence) and the chain itself runs on registers.
     for (int mu = tid; mu < m; mu += nt) {
         const double l = lam[mu];
+        double* __restrict__ gm = p.gh + (size_t)mu * n;
         double cprev = 0.0, dprev = 0.0;
-        for (int i = 0; i < n; ++i) {
-            const double a = c.ajk[i], b = c.bjk[i], fc = c.fact[i];
-            const double diag = fc * l - (a + b);
-            const double den = diag - ((i > 0) ? b * cprev : 0.0);
-            const double cc = a / den;
-            const double dd = (p.gh[(size_t)mu * n + i] - ((i > 0) ? b * dprev : 0.0)) / den;
-            p.cp[(size_t)i * m + mu] = cc;
-            p.gh[(size_t)mu * n + i] = dd;
-            cprev = cc; dprev = dd;
+        constexpr int U = 8;
+        for (int i0 = 0; i0 < n; i0 += U) {
+            double a[U], b[U], fc[U], g[U], cc[U], dd[U];
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int i = min(i0 + q, n - 1);
+                a[q] = c.ajk[i]; b[q] = c.bjk[i]; fc[q] = c.fact[i]; g[q] = gm[i];
+            }
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int i = i0 + q;
+                const double diag = fc[q] * l - (a[q] + b[q]);
+                const double den = diag - ((i > 0) ? b[q] * cprev : 0.0);
+                cc[q] = a[q] / den;
+                dd[q] = (g[q] - ((i > 0) ? b[q] * dprev : 0.0)) / den;
+                if (i < n) { cprev = cc[q]; dprev = dd[q]; }
+            }
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int i = i0 + q;
+                if (i < n) { p.cp[(size_t)i * m + mu] = cc[q]; gm[i] = dd[q]; }
+            }
         }
-        double w = p.gh[(size_t)mu * n + n - 1];
-        for (int i = n - 2; i >= 0; --i) {
-            w = p.gh[(size_t)mu * n + i] - p.cp[(size_t)i * m + mu] * w;
-            p.gh[(size_t)mu * n + i] = w;
+        double w = gm[n - 1];
+        for (int i1 = n - 2; i1 >= 0; i1 -= U) {
+            double g[U], cq[U];
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int i = max(i1 - q, 0);
+                g[q] = gm[i]; cq[q] = p.cp[(size_t)i * m + mu];
+            }
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int i = i1 - q;
+                if (i >= 0) { w = g[q] - cq[q] * w; g[q] = w; }
+            }
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int i = i1 - q;
+                if (i >= 0) gm[i] = g[q];
+            }
         }
     }
     __syncthreads();

@@ -535,19 +535,38 @@ sweep_post_kernel(const SweepArgs* __restrict__ probs) {
     }
     __syncthreads();
     for (int k = tid + 1; k <= kmax - 2; k += nt) {
-        double* tr = p.tref + (size_t)k * jd;
+        double* __restrict__ tr = p.tref + (size_t)k * jd;
+        const double* __restrict__ up = p.u + (size_t)(k + 1) * jd;
+        const double* __restrict__ um = p.u + (size_t)(k - 1) * jd;
         tr[0] = 0.; tr[1] = 0.;
-        for (int j = 2; j <= jd - 1; ++j) {
-            const double cor = 2. * p.om * p.sinrow[j - 1];
-            const double uz = (p.u[(size_t)(k + 1) * jd + j - 1] - p.u[(size_t)(k - 1) * jd + j - 1]) / (2. * p.dz);
-            double ty = -cor * uz * p.a * p.h * p.eref[k];
-            ty = ty / p.rr;
-            tr[j] = tr[j - 2] + 2. * ty * p.dp;
-        }
+        // thermal-wind marching tr[j] = tr[j-2] + ...: only kmax-2 threads and a sequential chain, so the operands
+        // of eight steps are fetched first and the chain runs on registers
+        double t0v = 0., t1v = 0.;   // tr[j-2], tr[j-1]
         double tg = 0., wt = 0.;
-        for (int j = 1; j <= jd; ++j) {
-            tg = tg + p.cosrow[j - 1] * tr[j - 1];
-            wt = wt + p.cosrow[j - 1];
+        tg = tg + p.cosrow[0] * 0.; wt = wt + p.cosrow[0];
+        tg = tg + p.cosrow[1] * 0.; wt = wt + p.cosrow[1];
+        constexpr int U = 8;
+        for (int j0 = 2; j0 <= jd - 1; j0 += U) {
+            double a[U], b[U], sn[U], cs[U], out[U];
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int j = min(j0 + q, jd - 1);
+                a[q] = up[j - 1]; b[q] = um[j - 1]; sn[q] = p.sinrow[j - 1]; cs[q] = p.cosrow[j];
+            }
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int j = j0 + q;
+                const double cor = 2. * p.om * sn[q];
+                const double uz = (a[q] - b[q]) / (2. * p.dz);
+                double ty = -cor * uz * p.a * p.h * p.eref[k];
+                ty = ty / p.rr;
+                const double v = t0v + 2. * ty * p.dp;
+                out[q] = v;
+                if (j <= jd - 1) { t0v = t1v; t1v = v; tg = tg + cs[q] * v; wt = wt + cs[q]; }
+            }
+#pragma unroll
+            for (int q = 0; q < U; ++q)
+                if (j0 + q <= jd - 1) tr[j0 + q] = out[q];
         }
         tg = tg / wt;
         const double tres = p.tb[k] - tg;
