@@ -14,7 +14,7 @@ python bench.py --steps 1 --warmup 1 --batch 1 --no-cpu-baseline > gpurun_out/${
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 1 --batch 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:${KREGEX} -s 2 -c 2 -o gpurun_out/${TAG}_prof \
+ncu --set full --clock-control none --import-source on -k regex:${KREGEX} -c 6 -o gpurun_out/${TAG}_prof \
     python bench.py --steps 1 --warmup 1 --batch 1 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
 ls -la gpurun_out | tail -20
