@@ -115,47 +115,71 @@ def algorithmic_bytes(nlon, nlat, nd, kmax, nlev, has_avort=True):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle pipeline on the host cores (reported baseline; see module docstring)
 # ------------------------------------------------------------------------------------------------
-def _cpu_one(args):
-    nlon, nlat, seed, threads = args
+_CPU_INPUT = {}
+
+
+def _cpu_init(nlon, nlat, threads):
+    """Pool initialiser: OpenMP width of this worker and its synthetic snapshot (generated once, reused every step)."""
     os.environ["OMP_NUM_THREADS"] = str(threads)
-    from oracle import pipeline
     from hn2016_falwa_b200.synthetic import synthetic_snapshot
-    inp = synthetic_snapshot(nlon=nlon, nlat=nlat, seed=seed)
+    _CPU_INPUT["inp"] = synthetic_snapshot(nlon=nlon, nlat=nlat, seed=1234 + os.getpid() % 97)
+
+
+def _cpu_one(_):
+    from oracle import pipeline
     t0 = time.perf_counter()
-    pipeline.run_qgfield("nhn22", *inp)
+    pipeline.run_qgfield("nhn22", *_CPU_INPUT["inp"])
     return time.perf_counter() - t0
 
 
+class CpuReference:
+    """The CPU oracle pipeline on the host cores: `workers` processes x (cores // workers) OpenMP threads."""
+
+    def __init__(self, nlon, nlat, workers):
+        import multiprocessing as mp
+        import subprocess
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+        self.cores = os.cpu_count() or 1
+        self.workers = max(1, min(workers, self.cores))
+        self.threads = max(1, self.cores // self.workers)
+        self.pool = mp.get_context("spawn").Pool(self.workers, initializer=_cpu_init,
+                                                 initargs=(nlon, nlat, self.threads))
+        self.pool.map(_cpu_one, [0] * 0)   # start the workers
+
+    def step(self, snapshots):
+        """-> snapshots/s of one step of `snapshots` pipeline runs (wall clock over the pool)."""
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_one, range(snapshots), chunksize=1)
+        return snapshots / (time.perf_counter() - t0)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
 def cpu_reference_rate(nlon, nlat, snapshots, workers):
-    """snapshots/s of the CPU oracle: `workers` processes x (cores // workers) OpenMP threads."""
-    import multiprocessing as mp
-    import subprocess
-    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
-    cores = os.cpu_count() or 1
-    workers = max(1, min(workers, cores, snapshots))
-    threads = max(1, cores // workers)
-    ctx = mp.get_context("spawn")
+    ref = CpuReference(nlon, nlat, workers)
+    ref.step(ref.workers)            # untimed: worker start-up + input synthesis
     t0 = time.perf_counter()
-    with ctx.Pool(workers) as pool:
-        per = pool.map(_cpu_one, [(nlon, nlat, 1234 + i, threads) for i in range(snapshots)])
+    rate = ref.step(snapshots)
     wall = time.perf_counter() - t0
-    # the rate counts only the pipeline time of the slowest worker chain (input synthesis excluded)
-    busy = max(sum(per[i::workers]) for i in range(workers))
-    return snapshots / busy, cores, workers, threads, wall
+    ref.close()
+    return rate, ref.cores, ref.workers, ref.threads, wall
 
 
 def run_reference(args, nlon, nlat, rank, world):
     if rank != 0:
         return
-    workers = 2 if nlon > 1000 else min(8, os.cpu_count() or 1)
-    per_step = workers if nlon > 1000 else 4 * workers
-    for _ in range(min(args.warmup, 0)):
-        pass  # nothing to warm up on the CPU arm beyond building the oracle library
-    rates, t_all = [], time.perf_counter()
-    for _ in range(max(1, args.steps)):
-        rate, cores, workers, threads, wall = cpu_reference_rate(nlon, nlat, per_step, workers)
-        rates.append(rate)
+    big = nlon > 1000
+    workers = 2 if big else min(8, os.cpu_count() or 1)
+    per_step = workers if big else 4 * workers
+    ref = CpuReference(nlon, nlat, workers)
+    for _ in range(max(1, args.warmup and 1)):
+        ref.step(ref.workers)        # warm-up: worker start-up, input synthesis, library load (one pass is enough on a CPU)
+    rates = [ref.step(per_step) for _ in range(max(1, args.steps))]
+    ref.close()
     value = float(np.mean(rates))
+    cores, workers, threads = ref.cores, ref.workers, ref.threads
     sample = f"{per_step} synthetic {nlon}x{nlat} snapshot(s) per step, {workers} processes x {threads} OpenMP threads"
     line = {
         "impl": "reference", "metric": "snapshots/sec, QGFieldNHN22 full pipeline", "value": value,
