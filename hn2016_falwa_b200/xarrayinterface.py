@@ -95,6 +95,10 @@ def _find(names, available, user_names, what):
     raise KeyError(f"no matching variable for '{what}' found")
 
 
+for _v in ("ua1", "ua2", "ep1", "ep2", "ep3", "stretch_term"):
+    _VARS[_v] = (("height", "ylat", "xlon"), ("height", "ylat_ref_states", "xlon"))
+
+
 class _FieldView:
     """Per-snapshot read-only view (``QGDataset.fields[i].lwa_baro`` ...), for code that iterates over fields."""
 
@@ -380,6 +384,74 @@ class QGDataset:
             return self._dataset(STAGE_VARS["flux"])
 
 
+def _per_field(qgds):
+    """One QGField object per snapshot of this rank's shard (the reference's structure), for the methods that are not
+    batched on the device."""
+    q = qgds
+    for i in range(q._hi - q._lo):
+        f = q._qgfield(q._xlon, q._ylat, q._plev, q._u[i], q._v[i], q._t[i], *q._qgfield_args, **q._qgfield_kwargs)
+        f.interpolate_fields(return_named_tuple=False)
+        yield i, f
+
+
+def _loop_method(self, names, call):
+    """Shared body of the per-field (not device-batched) QGDataset methods."""
+    nloc = self._hi - self._lo
+    for i, f in _per_field(self):
+        call(i, f)
+        for n in names:
+            a = np.asarray(getattr(f, n))
+            if n not in self._store or self._store[n].shape[0] != nloc:
+                self._store[n] = np.empty((nloc,) + a.shape)
+            self._store[n][i] = a
+
+
+def _compute_lwa_only(self, return_dataset=True):
+    """``compute_lwa_only`` of every field (xarrayinterface.py:566-585): LWA from QGPV and Qref alone, for snapshots whose
+    NH18 reference-state solver did not converge."""
+    def call(i, f):
+        f._raise_error_for_nonconvergence = False
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            f.compute_reference_states(return_named_tuple=False)
+        f.compute_lwa_only()
+    _loop_method(self, ("lwa_baro", "u_baro", "lwa"), call)
+    if return_dataset:
+        return self._dataset(("lwa_baro", "u_baro", "lwa"))
+
+
+def _compute_layerwise(self, ncforce=None, return_dataset=True):
+    """``compute_layerwise_lwa_fluxes`` of every field (xarrayinterface.py:587-630)."""
+    nc = None
+    if ncforce is not None:
+        nc = np.asarray(getattr(ncforce, "data", ncforce))
+        nc = nc.reshape((self._n,) + nc.shape[-3:])[self._lo:self._hi]
+    names = ("lwa", "ua1", "ua2", "ep1", "ep2", "ep3", "stretch_term")
+
+    def call(i, f):
+        f.compute_reference_states(return_named_tuple=False)
+        f.compute_layerwise_lwa_fluxes(ncforce=None if nc is None else nc[i])
+    _loop_method(self, names, call)
+    if return_dataset:
+        return self._dataset(names)
+
+
+def _compute_ncforce(self, heating_rate):
+    """``compute_ncforce_from_heating_rate`` of every field (xarrayinterface.py:632-661); returns (n, kmax, nlat, nlon)
+    with the leading dimensions restored when the whole batch is local."""
+    hr = np.asarray(getattr(heating_rate, "data", heating_rate))
+    hr = hr.reshape((self._n,) + hr.shape[-3:])[self._lo:self._hi]
+    out = [f.compute_ncforce_from_heating_rate(hr[i]) for i, f in _per_field(self)]
+    arr = np.asarray(out)
+    return arr.reshape(self._other_shape + arr.shape[1:]) if arr.shape[0] == self._n else arr
+
+
+QGDataset.compute_lwa_only = _compute_lwa_only
+QGDataset.compute_layerwise_lwa_fluxes = _compute_layerwise
+QGDataset.compute_ncforce_from_heating_rate = _compute_ncforce
+
+
 class _DeviceRunner:
     """Runs chunks of snapshots through ``engine.QGBatch`` on the current CUDA device and yields host copies of the
     requested variables.  User arrays are pageable NumPy (or lazily loaded) memory, so both directions go through
@@ -554,3 +626,93 @@ class _FieldLoopRunner:
                 val = getattr(f, name)
                 out[name] = np.asarray(val)[None] if not isinstance(val, tuple) else np.stack(val)[None]
             yield i, i + 1, out
+
+
+# ---- the steps after the path (falwa.xarrayinterface.integrate_budget / hemisphere_to_globe, :664-791) --------------
+_NAMES_TIME = ["time", "date", "datetime", "valid_time"]
+
+
+def _seconds(t):
+    t = np.asarray(t)
+    if np.issubdtype(t.dtype, np.datetime64):
+        return (t - t[0]) / np.timedelta64(1, "s")
+    return t.astype(np.float64)
+
+
+def integrate_budget(ds, var_names=None):
+    """Time-integrated LWA budget terms of equation (2) of NH18 (xarrayinterface.py:664-735): the change of ``lwa_baro``
+    over the interval, the trapezoidal time integrals of the three tendency terms and the residual.  Works on the
+    datasets returned by ``QGDataset.compute_lwa_and_barotropic_fluxes`` (xarray when installed, ``SimpleDataset``
+    otherwise).  A non-datetime time coordinate is taken to be in seconds."""
+    if xr is not None and isinstance(ds, xr.Dataset):  # pragma: no cover - same calls as the reference
+        names = {k: _find(v, ds, var_names, v[0]) for k, v in dict(
+            time=_NAMES_TIME, lwa=["lwa_baro"], czaf=["convergence_zonal_advective_flux"],
+            demf=["divergence_eddy_momentum_flux"], mhf=["meridional_heat_flux"]).items()}
+        start, stop = ds[names["time"]].values[0], ds[names["time"]].values[-1]
+        dlwa = ds[names["lwa"]].sel({names["time"]: stop}) - ds[names["lwa"]].sel({names["time"]: start})
+        terms = {k: ds[names[k]].integrate(coord=names["time"], datetime_unit="s") for k in ("czaf", "demf", "mhf")}
+        res = dlwa - terms["czaf"] - terms["demf"] - terms["mhf"]
+        attrs = dict(ds.attrs, integration_start=str(start), integration_stop=str(stop),
+                     integration_seconds=(stop - start) / np.timedelta64(1000000000))
+        return xr.Dataset({"delta_lwa": dlwa, "integrated_convergence_zonal_advective_flux": terms["czaf"],
+                           "integrated_divergence_eddy_momentum_flux": terms["demf"],
+                           "integrated_meridional_heat_flux": terms["mhf"], "residual": res}, ds.coords, attrs)
+    lwa = ds[_find(["lwa_baro"], ds, var_names, "lwa_baro")]
+    tname = _find(_NAMES_TIME, lwa.coords, var_names, "time")
+    axis = lwa.dims.index(tname)
+    tsec = _seconds(lwa.coords[tname])
+    rest = tuple(d for d in lwa.dims if d != tname)
+    coords = OrderedDict((k, v) for k, v in lwa.coords.items() if k != tname)
+
+    def integ(name):
+        return np.trapezoid(np.asarray(ds[_find([name], ds, var_names, name)].data), x=tsec, axis=axis)
+    dl = np.take(lwa.data, -1, axis=axis) - np.take(lwa.data, 0, axis=axis)
+    czaf, demf, mhf = (integ(n) for n in ("convergence_zonal_advective_flux", "divergence_eddy_momentum_flux",
+                                          "meridional_heat_flux"))
+    out = {"delta_lwa": dl, "integrated_convergence_zonal_advective_flux": czaf,
+           "integrated_divergence_eddy_momentum_flux": demf, "integrated_meridional_heat_flux": mhf,
+           "residual": dl - czaf - demf - mhf}
+    attrs = dict(ds.attrs, integration_start=str(lwa.coords[tname][0]), integration_stop=str(lwa.coords[tname][-1]),
+                 integration_seconds=float(tsec[-1] - tsec[0]))
+    return SimpleDataset(OrderedDict((k, SimpleDataArray(v, rest, coords, name=k)) for k, v in out.items()), attrs)
+
+
+def hemisphere_to_globe(ds, var_names=None):
+    """Mirror a hemispheric dataset (which must start or end at the equator) to the other hemisphere, negating the
+    meridional wind on the created half (xarrayinterface.py:738-791)."""
+    if xr is not None and isinstance(ds, xr.Dataset):  # pragma: no cover - same calls as the reference
+        yname = _find(_NAMES_YLAT, ds, var_names, "ylat")
+        eq0 = abs(float(ds[yname][0])) < 1e-4
+        assert eq0 or abs(float(ds[yname][-1])) < 1e-4, "equator not found on the hemisphere"
+        sd = ds.reindex({yname: ds[yname][slice(None, 0, -1) if eq0 else slice(-2, None, -1)]})
+        sd[yname] = -sd[yname]
+        try:
+            vname = _find(_NAMES_V, ds, var_names, "v")
+            sd[vname] = -sd[vname]
+        except KeyError:
+            pass
+        return xr.concat([sd, ds] if eq0 else [ds, sd], dim=yname)
+    first = next(iter(ds.values()))
+    yname = _find(_NAMES_YLAT, first.coords, var_names, "ylat")
+    ylat = np.asarray(first.coords[yname])
+    eq0 = abs(ylat[0]) < 1.0e-4
+    assert eq0 or abs(ylat[-1]) < 1.0e-4, \
+        "equator not found on the hemisphere; make sure latitudes either begin or end with 0° latitude"
+    sel = slice(None, 0, -1) if eq0 else slice(-2, None, -1)
+    try:
+        vname = _find(_NAMES_V, ds, var_names, "v")
+    except KeyError:
+        vname = None
+    out = SimpleDataset(attrs=ds.attrs)
+    for name, da in ds.items():
+        ax = da.dims.index(yname)
+        idx = [slice(None)] * da.data.ndim
+        idx[ax] = sel
+        mirrored = da.data[tuple(idx)]
+        if name == vname:
+            mirrored = -mirrored
+        data = np.concatenate([mirrored, da.data] if eq0 else [da.data, mirrored], axis=ax)
+        coords = OrderedDict(da.coords)
+        coords[yname] = np.concatenate([-ylat[sel], ylat] if eq0 else [ylat, -ylat[sel]])
+        out[name] = SimpleDataArray(data, da.dims, coords, name=name, attrs=da.attrs)
+    return out

@@ -50,3 +50,22 @@ def test_dataset_equals_single_fields_and_oracle(kind):
         assert stab.shape == (2, 2, 49)
     else:
         assert stab[0].name == "static_stability_n" and stab[0].shape == (2, 2, 49)
+
+
+def test_dataset_layerwise_and_lwa_only():
+    from hn2016_falwa_b200 import xarrayinterface as xi
+    from hn2016_falwa_b200.oopinterface import QGFieldNHN22, QGFieldNH18
+    ds, snaps = _make(2, 1)
+    q = xi.QGDataset(ds, qgfield=QGFieldNHN22)
+    out = q.compute_layerwise_lwa_fluxes()
+    assert set(out) == {"lwa", "ua1", "ua2", "ep1", "ep2", "ep3", "stretch_term"}
+    assert out["ua2"].shape == (2, 1, 49, 49, 96)
+    f = QGFieldNHN22(*snaps[1])
+    f.interpolate_fields(False); f.compute_reference_states(False); f.compute_layerwise_lwa_fluxes()
+    np.testing.assert_allclose(out["ep1"].data[1, 0], f.ep1, rtol=1e-9, atol=1e-10 * np.abs(f.ep1).max())  # histogram sums use atomics
+    hr = 1e-5 * np.ones((2, 1) + snaps[0][3].shape)
+    nc = q.compute_ncforce_from_heating_rate(hr)
+    assert nc.shape == (2, 1, 49, 49, 96)
+    q18 = xi.QGDataset(ds, qgfield=QGFieldNH18, qgfield_kwargs=dict(maxit=5, raise_error_for_nonconvergence=False))
+    lo = q18.compute_lwa_only()
+    assert lo["lwa"].shape == (2, 1, 49, 49, 96) and np.isfinite(lo["lwa_baro"].data).all()
