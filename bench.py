@@ -74,7 +74,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception as e:  # pragma: no cover
                 self.err = repr(e)
-            time.sleep(0.1)
+            time.sleep(0.01)
 
     def result(self):
         self.stop_flag = True
@@ -83,6 +83,26 @@ class ClockSampler(threading.Thread):
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": self.err or "no samples"}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(self.samples)}
+
+
+def bind_to_gpu_numa_node(index):
+    """Best effort: restrict this process to the CPUs NVML reports as local to GPU `index`, so that the pinned host
+    buffers (first touch) and the copy threads sit on the socket the GPU hangs off.  With 8 ranks on a two-socket box
+    the end-to-end rate is otherwise limited by cross-socket traffic."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:  # noqa: BLE001 - affinity is an optimisation only
+        pass
+    return None
 
 
 def make_batch(nlon, nlat, batch, seed):
@@ -206,6 +226,7 @@ def run_b200(args, nlon, nlat, rank, world, local_rank):
 
     _lib.require_cuda()
     torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(local_rank)   # pinned staging buffers are first-touched on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B = args.batch
