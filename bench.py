@@ -85,6 +85,9 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+_ORIG_AFFINITY = {}
+
+
 def bind_to_gpu_numa_node(index):
     """Best effort: restrict this process to the CPUs NVML reports as local to GPU `index`, so that the pinned host
     buffers (first touch) and the copy threads sit on the socket the GPU hangs off.  With 8 ranks on a two-socket box
@@ -97,6 +100,7 @@ def bind_to_gpu_numa_node(index):
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
         cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
         cpus &= set(os.sched_getaffinity(0))
+        _ORIG_AFFINITY.setdefault("cpus", os.sched_getaffinity(0))
         if cpus:
             os.sched_setaffinity(0, cpus)
             return sorted(cpus)
@@ -228,7 +232,19 @@ def run_b200(args, nlon, nlat, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     bind_to_gpu_numa_node(local_rank)   # pinned staging buffers are first-touched on the GPU's own NUMA node
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout when the first communicator comes up: send it to stderr so that
+        # stdout carries exactly one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     B = args.batch
     xlon, ylat, plev, u, v, t, shifts = make_batch(nlon, nlat, B, seed=1234 + rank)
     # plan via the public class (validates the grid exactly like the reference's constructor)
@@ -336,6 +352,8 @@ def run_b200(args, nlon, nlat, rank, world, local_rank):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
+            if "cpus" in _ORIG_AFFINITY:   # the CPU baseline uses every host core again
+                os.sched_setaffinity(0, _ORIG_AFFINITY["cpus"])
             snaps = 1 if nlon > 1000 else 8
             rate, cores, workers, threads, wall = cpu_reference_rate(nlon, nlat, snaps, workers=1 if nlon > 1000 else 8)
             cpu = {"value": rate, "unit": "snapshots/s", "cores": cores, "kind": "port",
