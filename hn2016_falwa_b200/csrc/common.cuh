@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <vector>
+#include <type_traits>
 #include <thread>
 #include <atomic>
 #include <algorithm>

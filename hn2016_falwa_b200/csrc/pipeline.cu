@@ -356,10 +356,29 @@ fused_flux_kernel(FusedFluxArgs p) {
 // row only (hs) and baro_post_kernel picks the neighbours; the two rows with special rules (the first row's
 // out-of-bounds uref and the boundary row jb, :173-178) are evaluated directly.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2)
+// per-level operands of the column walk (the special-row members exist only in the SPECIAL instantiation)
+struct ColumnLevelBase { double u0, v0, t0, a1, a2, u2, nc, ur, tr; };
+struct ColumnLevelSpecial : ColumnLevelBase { double um, vm, urm, bu1, bv1, bu0, bv0, bur1, bur0; };
+struct ColumnLevelPlain : ColumnLevelBase {
+    static constexpr double um = 0, vm = 0, urm = 0, bu1 = 0, bv1 = 0, bu0 = 0, bv0 = 0, bur1 = 0, bur0 = 0;
+};
+
+// SPECIAL = false walks every ordinary row (launch: 32 x 8 tiles over all rows; the two special rows return at once);
+// SPECIAL = true walks only the first row and the boundary row (launch: grid.y = 2), which need extra neighbour
+// loads — keeping those out of the ordinary instantiation saves 36 registers there (3 CTAs per SM instead of 2).
+template <bool SPECIAL>
+__global__ void __launch_bounds__(256, SPECIAL ? 2 : 3)
 flux_column_kernel(FusedFluxArgs p, double* __restrict__ hs /* [b][nhemi][nd][imax] */) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;  // hemispheric row 1..nd
+    const int jfirst = p.jb + 1, jbrow = (p.jb >= 1) ? p.jb : p.nd;
+    int j;
+    if (SPECIAL) {
+        if (blockIdx.y == 1 && jbrow == jfirst) return;
+        j = blockIdx.y == 0 ? jfirst : jbrow;
+    } else {
+        j = blockIdx.y * blockDim.y + threadIdx.y + 1;  // hemispheric row 1..nd
+        if (j == jfirst || j == jbrow) return;
+    }
     const int b = blockIdx.z / p.nhemi, hidx = blockIdx.z % p.nhemi;
     const bool south = hidx == 1;
     if (i >= p.imax || j > p.nd) return;
@@ -381,8 +400,8 @@ flux_column_kernel(FusedFluxArgs p, double* __restrict__ hs /* [b][nhemi][nd][im
     const int g = grow(j);
     const int jstart = jb + 1, jend = nd - 1;
     const bool in_range = (j >= jstart && j <= jend);
-    const bool first = (j == jstart);                      // ep3 needs the reference's uref(0,k) == uref(jd,k-1)
-    const bool brow = (jb >= 1) ? (j == jb) : (j == nd);   // boundary row jb, or its alias (i,nd,k-1) when jb = 0
+    const bool first = SPECIAL && (j == jstart);           // ep3 needs the reference's uref(0,k) == uref(jd,k-1)
+    const bool brow = SPECIAL && ((jb >= 1) ? (j == jb) : (j == nd));   // boundary row jb, or its alias (i,nd,k-1) when jb = 0
     const bool own_g = (j >= jstart);                      // rows whose G sum some neighbour needs
     const double c0 = p.cosphi[j], cm = p.cosphi[j - 1], cl = p.clat[g];
     const size_t o2 = (size_t)g * imax + i;
@@ -390,27 +409,32 @@ flux_column_kernel(FusedFluxArgs p, double* __restrict__ hs /* [b][nhemi][nd][im
     const size_t r1 = (size_t)grow(jb + 2) * imax + i, r0 = (size_t)grow(jb + 1) * imax + i;  // boundary row only
     const int gr1 = grow(jb + 2), gr0 = grow(jb + 1), gnd = grow(nd);
 
-    struct Lv { double u0, v0, t0, a1, a2, u2, nc, ur, tr, um, vm, urm, bu1, bv1, bu0, bv0, bur1, bur0; };
+    using Lv = typename std::conditional<SPECIAL, ColumnLevelSpecial, ColumnLevelPlain>::type;
     auto fetch = [&](int k) -> Lv {  // 1-based level k (2..kmax)
         Lv L;
         const size_t lev = (size_t)(k - 1) * plane;
         L.u0 = uu[lev + o2]; L.v0 = vv[lev + o2];
         L.ur = uref[(size_t)(k - 1) * nlat + g];
-        L.t0 = L.a1 = L.a2 = L.u2 = L.nc = L.tr = L.um = L.vm = L.urm = 0.0;
-        L.bu1 = L.bv1 = L.bu0 = L.bv0 = L.bur1 = L.bur0 = 0.0;
+        L.t0 = L.a1 = L.a2 = L.u2 = L.nc = L.tr = 0.0;
+        if constexpr (SPECIAL) {
+            L.um = L.vm = L.urm = 0.0;
+            L.bu1 = L.bv1 = L.bu0 = L.bv0 = L.bur1 = L.bur0 = 0.0;
+        }
         if (k < kmax) {
             if (in_range) {
                 L.t0 = pt[lev + o2]; L.tr = tref[(size_t)(k - 1) * nlat + g];
                 L.a1 = sa1[lev + o2]; L.a2 = sa2[lev + o2]; L.u2 = su2[lev + o2];
                 if (snc) L.nc = snc[lev + o2];
             }
-            if (first) {
-                L.um = uu[lev + om]; L.vm = vv[lev + om];
-                L.urm = (j - jb - 1 >= 1) ? uref[(size_t)(k - 1) * nlat + grow(j - 1)] : uref[(size_t)(k - 2) * nlat + gnd];
-            }
-            if (brow) {
-                L.bu1 = uu[lev + r1]; L.bv1 = vv[lev + r1]; L.bu0 = uu[lev + r0]; L.bv0 = vv[lev + r0];
-                L.bur1 = uref[(size_t)(k - 1) * nlat + gr1]; L.bur0 = uref[(size_t)(k - 1) * nlat + gr0];
+            if constexpr (SPECIAL) {
+                if (first) {
+                    L.um = uu[lev + om]; L.vm = vv[lev + om];
+                    L.urm = (j - jb - 1 >= 1) ? uref[(size_t)(k - 1) * nlat + grow(j - 1)] : uref[(size_t)(k - 2) * nlat + gnd];
+                }
+                if (brow) {
+                    L.bu1 = uu[lev + r1]; L.bv1 = vv[lev + r1]; L.bu0 = uu[lev + r0]; L.bv0 = vv[lev + r0];
+                    L.bur1 = uref[(size_t)(k - 1) * nlat + gr1]; L.bur0 = uref[(size_t)(k - 1) * nlat + gr0];
+                }
             }
         }
         return L;
@@ -1194,7 +1218,8 @@ extern "C" int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* P, int bat
         if (use_scan) {
             if ((rc = hsum.alloc((size_t)batch * nhemi * nd * nlon, st))) return rc;
             FALWA_KERNEL("flux_column_kernel", st);
-            flux_column_kernel<<<grid, block, 0, st>>>(p, hsum.d);
+            flux_column_kernel<false><<<grid, block, 0, st>>>(p, hsum.d);
+            flux_column_kernel<true><<<dim3(ceil_div(nlon, 256), 2, batch * nhemi), 256, 0, st>>>(p, hsum.d);
         } else {
             FALWA_KERNEL("fused_flux_bruteforce_kernel", st);
             fused_flux_kernel<true><<<grid, block, 0, st>>>(p);
