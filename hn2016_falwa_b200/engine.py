@@ -107,6 +107,7 @@ class QGBatch:
         for name, x in (("u", self.u_in), ("v", self.v_in), ("t", self.t_in)):
             if tuple(x.shape) != exp:
                 raise TypeError(f"Incorrect dimension of {name}_field. Expected dimension: {exp}")
+        self._means_host = self._means_dev = self._means_ev = None
         self.profiles = None          # host [B][4][kmax]: t0_s, t0_n, stat_s, stat_n
         self.profiles_hemi = None
         self.u = self.v = self.theta = self.avort = self.qgpv = self.zm = self.ext = None
@@ -126,13 +127,31 @@ class QGBatch:
         return torch.empty(shape, dtype=torch.float64, device=self.u_in.device)
 
     # ---- stage 1 -------------------------------------------------------------------------------
-    def hemispheric_theta_means(self):
-        """[B][2][nlev] cos-weighted hemispheric means of potential temperature (device reduction)."""
+    def launch_theta_means(self):
+        """Queue the hemispheric-mean reduction and its copy to pinned host memory without waiting for it, so that a
+        caller can queue other work (the previous batch's flux kernels) behind it and fit the splines meanwhile."""
+        if self._means_host is not None:
+            return
         p = self.plan
         means = self._new(self.B, 2, self.t_in.shape[1])
         check(self.lib.falwa_b200_theta_hemispheric_means(p.handle, self.B, dptr(self.t_in), dptr(means),
                                                           stream_ptr()), "theta_hemispheric_means")
-        return means.cpu().numpy()
+        # pinned staging from a small per-plan ring (cudaHostAlloc per batch would synchronise the device)
+        ring = p.__dict__.setdefault("_means_ring", {})
+        key = tuple(means.shape)
+        bufs = ring.setdefault(key, [torch.empty(key, dtype=torch.float64).pin_memory() for _ in range(4)])
+        p._means_next = (getattr(p, "_means_next", -1) + 1) % len(bufs)
+        self._means_host = bufs[p._means_next]
+        self._means_host.copy_(means, non_blocking=True)
+        self._means_dev = means                      # keep alive until the copy has run
+        self._means_ev = torch.cuda.Event()
+        self._means_ev.record()
+
+    def hemispheric_theta_means(self):
+        """[B][2][nlev] cos-weighted hemispheric means of potential temperature (device reduction)."""
+        self.launch_theta_means()
+        self._means_ev.synchronize()
+        return self._means_host.numpy().copy()
 
     def static_stability_profiles(self):
         """oopinterface.py:241-261 and :530-531: smoothing splines of the hemispheric-mean theta(z) and their
@@ -309,3 +328,25 @@ class HostStream:
             out["num_of_iter"][lo:hi] = b.num_of_iter
         self.s_out.synchronize()
         return out
+
+
+def run_stream(plan, batches, method=0, ncforce=None, on_height_grid=False, northern_hemisphere_results_only=False):
+    """Run a sequence of device-resident batches through the whole pipeline, yielding each finished ``QGBatch``.
+
+    ``batches`` yields (u, v, t) CUDA tensors [B][nlev][nlat][nlon].  The only host work on the critical path is the
+    static-stability spline (SciPy, ~0.17 ms per snapshot); here the hemispheric means of batch n+1 are queued BEFORE
+    the flux kernels of batch n, so the splines of n+1 are fitted while the GPU is busy with n's LWA / flux stage."""
+    prev = None
+    for u, v, t in batches:
+        b = QGBatch(plan, u, v, t, on_height_grid=on_height_grid,
+                    northern_hemisphere_results_only=northern_hemisphere_results_only)
+        b.launch_theta_means()
+        if prev is not None:
+            prev.compute_lwa_and_barotropic_fluxes(ncforce=ncforce, method=method)
+            yield prev
+        b.interpolate_fields()          # waits for the means only, fits the splines, queues stage 1
+        b.compute_reference_states()
+        prev = b
+    if prev is not None:
+        prev.compute_lwa_and_barotropic_fluxes(ncforce=ncforce, method=method)
+        yield prev
