@@ -43,7 +43,8 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU every 100 ms while the timed region runs."""
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (first sample at once, then
+    every 250 ms: denser NVML / nvidia-smi polling measurably slows the kernel launches of the step loop)."""
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
 
@@ -74,7 +75,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception as e:  # pragma: no cover
                 self.err = repr(e)
-            time.sleep(0.01)
+            time.sleep(0.25)   # every NVML query stalls the CUDA driver for a few ms: sample sparsely
 
     def result(self):
         self.stop_flag = True
