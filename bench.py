@@ -269,8 +269,8 @@ def run_b200(args, nlon, nlat, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
+    for _ in engine.run_stream(plan, ((du, dv, dt_) for _ in range(args.warmup)), method=args.method):
+        pass   # warm-up through the same pipelined path (allocator caches both batch slots, kernels loaded)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
