@@ -380,7 +380,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=4, help="snapshots per step per GPU")
+    ap.add_argument("--batch", type=int, default=8, help="snapshots per step per GPU")
     ap.add_argument("--chunk", type=int, default=1, help="snapshots per H2D/D2H chunk of the end-to-end run")
     ap.add_argument("--grid", default="0.25", choices=sorted(GRIDS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
