@@ -10,6 +10,9 @@
 #include <thread>
 #include <atomic>
 #include <algorithm>
+#include <cstring>
+#include <deque>
+#include <mutex>
 #include "../../include/falwa_b200.h"
 
 #define FALWA_CUDA_TRY(expr)                         \
@@ -129,6 +132,87 @@ __device__ __forceinline__ int area_bin(double qmax, double q, double dq, double
     return max(1, min(nb, 1 + (int)t));
 }
 
+// ---- small host <-> device transfers that bypass the copy engines ------------------------------------------------
+// The pipeline's per-batch tables (static-stability profiles, per-problem argument blocks, a few KB) used to travel
+// with cudaMemcpyAsync.  On a stream that overlaps with bulk PCIe traffic of other streams (HostStream / QGDataset:
+// hundreds of MB per chunk in each direction) those tiny copies queue in the SAME DMA engine behind the bulk
+// transfer, and every stage stalled ~10 ms for it.  Instead the host writes into a pinned, device-mapped ring and a
+// small kernel on the compute stream pulls the bytes over PCIe (and, in the other direction, kernels store results
+// straight into mapped host memory), so no copy engine is involved.
+struct PinnedRing {
+    static constexpr size_t kCap = 32u << 20;
+    struct Fence { size_t b, e; cudaEvent_t ev; };
+    char* base = nullptr;
+    size_t head = 0;
+    std::mutex mu;
+    std::deque<Fence> fences;
+    std::vector<cudaEvent_t> pool;
+
+    // -> host pointer (== device pointer under unified addressing) of `bytes` ring bytes, or nullptr when the request
+    // is too large for the ring (callers fall back to cudaMemcpyAsync).  Blocks only if the region is still in use.
+    void* take(size_t bytes, size_t* off) {
+        if (bytes > kCap / 4) return nullptr;
+        if (!base && cudaHostAlloc((void**)&base, kCap, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+            base = nullptr;
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        const size_t sz = (bytes + 255) & ~(size_t)255;
+        if (head + sz > kCap) head = 0;
+        const size_t b = head, e = head + sz;
+        for (auto it = fences.begin(); it != fences.end();) {
+            if (it->b < e && b < it->e) {
+                cudaEventSynchronize(it->ev);
+                pool.push_back(it->ev);
+                it = fences.erase(it);
+            } else ++it;
+        }
+        head = e;
+        *off = b;
+        return base + b;
+    }
+    // the ring bytes [off, off + bytes) are in use until everything queued on `st` so far has run
+    void fence(size_t off, size_t bytes, cudaStream_t st) {
+        cudaEvent_t ev;
+        if (!pool.empty()) { ev = pool.back(); pool.pop_back(); }
+        else if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return;
+        cudaEventRecord(ev, st);
+        fences.push_back({off, off + ((bytes + 255) & ~(size_t)255), ev});
+    }
+};
+inline PinnedRing& pinned_ring() {
+    static PinnedRing r;
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+pull_words_kernel(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ src, size_t n) {
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x)
+        dst[t] = src[t];
+}
+
+// dst (device) <- src (any host memory), stream-ordered; `src` may die when the call returns.
+inline int upload_bytes(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return 0;
+    PinnedRing& R = pinned_ring();
+    if (bytes % 8 == 0) {
+        std::lock_guard<std::mutex> lock(R.mu);
+        size_t off = 0;
+        if (void* stage = R.take(bytes, &off)) {
+            std::memcpy(stage, src, bytes);
+            const size_t n = bytes / 8;
+            const int blocks = (int)std::min<size_t>((n + 255) / 256, 296);
+            { FALWA_KERNEL("pull_words_kernel", st); pull_words_kernel<<<blocks, 256, 0, st>>>((unsigned long long*)dst, (const unsigned long long*)stage, n); }
+            FALWA_LAUNCH_CHECK();
+            R.fence(off, bytes, st);
+            return 0;
+        }
+    }
+    // pageable source: the copy is staged before the call returns
+    FALWA_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
 // Small stream-ordered device buffer filled from a host vector (tables of a few KB).
 struct DeviceTable {
     double* d = nullptr;
@@ -136,9 +220,7 @@ struct DeviceTable {
     int upload(const std::vector<double>& h, cudaStream_t stream) {
         s = stream;
         FALWA_CUDA_TRY(cudaMallocAsync((void**)&d, h.size() * sizeof(double), stream));
-        // pageable source: the copy is staged before the call returns, so `h` may die afterwards
-        FALWA_CUDA_TRY(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
-        return 0;
+        return upload_bytes(d, h.data(), h.size() * sizeof(double), stream);
     }
     ~DeviceTable() {
         if (d) cudaFreeAsync(d, s);

@@ -1066,7 +1066,7 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
             }
         DeviceScratch<SorArgs> dp;
         if ((rc = dp.alloc(nprob, st))) return rc;
-        FALWA_CUDA_TRY(cudaMemcpyAsync(dp.d, probs.data(), sizeof(SorArgs) * nprob, cudaMemcpyHostToDevice, st));
+        if ((rc = upload_bytes(dp.d, probs.data(), sizeof(SorArgs) * nprob, st))) return rc;
         FALWA_CUDA_TRY(cudaFuncSetAttribute(sor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
         const size_t smem = probs[0].u_in_smem ? sizeof(double) * njk : 0;
         { FALWA_KERNEL("sor_kernel", st); sor_kernel<<<nprob, 1024, smem, st>>>(dp.d); }
@@ -1107,8 +1107,8 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
         DeviceScratch<SweepArgs> dwp;
         if ((rc = dsp.alloc(nprob, st))) return rc;
         if ((rc = dwp.alloc(nprob, st))) return rc;
-        FALWA_CUDA_TRY(cudaMemcpyAsync(dsp.d, sp.data(), sizeof(SpectralProblem) * nprob, cudaMemcpyHostToDevice, st));
-        FALWA_CUDA_TRY(cudaMemcpyAsync(dwp.d, wp.data(), sizeof(SweepArgs) * nprob, cudaMemcpyHostToDevice, st));
+        if ((rc = upload_bytes(dsp.d, sp.data(), sizeof(SpectralProblem) * nprob, st))) return rc;
+        if ((rc = upload_bytes(dwp.d, wp.data(), sizeof(SweepArgs) * nprob, st))) return rc;
         { FALWA_KERNEL("nhn22_spectral_solve_kernel", st); nhn22_spectral_solve_kernel<<<nprob, 512, 0, st>>>(c, dsp.d); }
         FALWA_LAUNCH_CHECK();
         { FALWA_KERNEL("sweep_post_kernel", st); sweep_post_kernel<<<nprob, 512, 0, st>>>(dwp.d); }
@@ -1125,8 +1125,30 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
             ptref_st); }
         FALWA_LAUNCH_CHECK();
     }
-    FALWA_CUDA_TRY(cudaMemcpyAsync(num_of_iter_host, nit.d, sizeof(int) * nprob, cudaMemcpyDeviceToHost, st));
-    FALWA_CUDA_TRY(cudaStreamSynchronize(st));
+    if (P->kind != 0) {
+        // the direct solve has no iteration count: nothing to wait for, the host runs ahead of the device
+        std::fill(num_of_iter_host, num_of_iter_host + nprob, 0);
+        return 0;
+    }
+    // NH18: the caller's convergence check needs the SOR iteration counts now.  They come back through mapped host
+    // memory (not a copy engine, which may be busy with another stream's bulk transfer for milliseconds).
+    void* stage = nullptr;
+    {
+        PinnedRing& R = pinned_ring();
+        std::lock_guard<std::mutex> lock(R.mu);
+        size_t off = 0;
+        stage = R.take(sizeof(int) * nprob, &off);
+    }
+    if (stage) {
+        FALWA_KERNEL("pull_words_kernel", st);
+        pull_words_kernel<<<1, 256, 0, st>>>((unsigned long long*)stage, (const unsigned long long*)nit.d, (size_t)batch);
+        FALWA_LAUNCH_CHECK();
+        FALWA_CUDA_TRY(cudaStreamSynchronize(st));
+        std::memcpy(num_of_iter_host, stage, sizeof(int) * nprob);
+    } else {
+        FALWA_CUDA_TRY(cudaMemcpyAsync(num_of_iter_host, nit.d, sizeof(int) * nprob, cudaMemcpyDeviceToHost, st));
+        FALWA_CUDA_TRY(cudaStreamSynchronize(st));
+    }
     return 0;
 }
 

@@ -724,7 +724,7 @@ extern "C" int falwa_b200_compute_reference_states(const double* pv, const doubl
     FALWA_CUDA_TRY(cudaFuncSetAttribute(sor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     DeviceScratch<SorArgs> dp;
     if ((rc = dp.alloc(1, st))) return rc;
-    FALWA_CUDA_TRY(cudaMemcpyAsync(dp.d, &p, sizeof(SorArgs), cudaMemcpyHostToDevice, st));
+    { int rcu = upload_bytes(dp.d, &p, sizeof(SorArgs), st); if (rcu) return rcu; }
     { FALWA_KERNEL("sor_kernel", st); sor_kernel<<<1, 1024, smem, st>>>(dp.d); }
     FALWA_LAUNCH_CHECK();
     FALWA_CUDA_TRY(cudaMemcpyAsync(num_of_iter_host, nit.d, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -894,7 +894,7 @@ extern "C" int falwa_b200_upward_sweep(int jmax, int kmax, int nd, int jb, int j
     FALWA_LAUNCH_CHECK();
     DeviceScratch<SweepArgs> dprob;
     if ((rc = dprob.alloc(1, st))) return rc;
-    FALWA_CUDA_TRY(cudaMemcpyAsync(dprob.d, &p, sizeof(SweepArgs), cudaMemcpyHostToDevice, st));
+    { int rcu = upload_bytes(dprob.d, &p, sizeof(SweepArgs), st); if (rcu) return rcu; }
     { FALWA_KERNEL("sweep_post_kernel", st); sweep_post_kernel<<<1, 512, 0, st>>>(dprob.d); }
     FALWA_LAUNCH_CHECK();
     return 0;

@@ -48,6 +48,38 @@ def _register():
     _registered = True
 
 
+_SRC_TYPES = {torch.float64: 0, torch.float32: 1, torch.int16: 2}
+
+
+def needs_ingest(dtype, packing=None, flip_lat=False, flip_lev=False):
+    """False when the raw array already is what the pipeline reads (float64, ordered, not packed)."""
+    return dtype != torch.float64 or packing is not None or flip_lat or flip_lev
+
+
+def ingest_field(raw, packing=None, flip_lat=False, flip_lev=False, out=None):
+    """Archived values on the device -> the pipeline's float64 [B][level][lat][lon], latitude ascending, pressure
+    descending (Section D of falwa_b200.h).  ``raw``: CUDA tensor of float64 / float32 / int16 as it lies in the file;
+    ``packing`` = (scale_factor, add_offset[, fill_value]) of CF-packed variables, value = raw * scale + offset and
+    fill -> NaN, like xarray's decoder; ``flip_lat`` / ``flip_lev`` reverse those axes (the np.flip of
+    xarrayinterface.py:384-405)."""
+    assert raw.is_cuda and raw.dim() == 4 and raw.dtype in _SRC_TYPES, "ingest_field: [B][lev][lat][lon] f64/f32/i16"
+    raw = raw.contiguous()
+    if out is None:
+        out = torch.empty(raw.shape, dtype=torch.float64, device=raw.device)
+    assert out.dtype == torch.float64 and out.is_contiguous() and tuple(out.shape) == tuple(raw.shape)
+    assert out.data_ptr() != raw.data_ptr(), "ingest_field works out of place"
+    scale, offset, fill = 1.0, 0.0, None
+    if packing is not None:
+        scale, offset = float(packing[0]), float(packing[1])
+        fill = packing[2] if len(packing) > 2 else None
+    B, nl, ny, nx = (int(x) for x in raw.shape)
+    check(_lib.load().falwa_b200_ingest_field(
+        _SRC_TYPES[raw.dtype], B, nl, ny, nx, ctypes.c_void_p(raw.data_ptr()), scale, offset,
+        int(fill is not None), float(fill) if fill is not None else 0.0, int(bool(flip_lat)), int(bool(flip_lev)),
+        dptr(out), stream_ptr()), "ingest_field")
+    return out
+
+
 class Plan:
     """Grid-dependent device tables (falwa_b200_plan_create)."""
 
@@ -133,17 +165,17 @@ class QGBatch:
         if self._means_host is not None:
             return
         p = self.plan
-        means = self._new(self.B, 2, self.t_in.shape[1])
-        check(self.lib.falwa_b200_theta_hemispheric_means(p.handle, self.B, dptr(self.t_in), dptr(means),
-                                                          stream_ptr()), "theta_hemispheric_means")
-        # pinned staging from a small per-plan ring (cudaHostAlloc per batch would synchronise the device)
+        # the reduction kernel stores its B x 2 x nlev results straight into pinned (device-mapped) host memory from a
+        # small per-plan ring: no cudaHostAlloc per batch (it would synchronise the device) and no copy-engine
+        # transfer (it would queue behind another stream's bulk PCIe traffic)
         ring = p.__dict__.setdefault("_means_ring", {})
-        key = tuple(means.shape)
+        key = (self.B, 2, int(self.t_in.shape[1]))
         bufs = ring.setdefault(key, [torch.empty(key, dtype=torch.float64).pin_memory() for _ in range(4)])
         p._means_next = (getattr(p, "_means_next", -1) + 1) % len(bufs)
         self._means_host = bufs[p._means_next]
-        self._means_host.copy_(means, non_blocking=True)
-        self._means_dev = means                      # keep alive until the copy has run
+        check(self.lib.falwa_b200_theta_hemispheric_means(p.handle, self.B, dptr(self.t_in),
+                                                          ctypes.c_void_p(self._means_host.data_ptr()),
+                                                          stream_ptr()), "theta_hemispheric_means")
         self._means_ev = torch.cuda.Event()
         self._means_ev.record()
 
@@ -250,10 +282,15 @@ class HostStream:
       (optional, ``want_lwa3d``).
     """
 
-    def __init__(self, plan, chunk=1, want_lwa3d=True, method=0, on_height_grid=False, input_dtype=torch.float64):
+    def __init__(self, plan, chunk=1, want_lwa3d=True, method=0, on_height_grid=False, input_dtype=torch.float64,
+                 packing=None, flip_lat=False, flip_lev=False):
         self.plan, self.chunk, self.want_lwa3d, self.method = plan, int(chunk), want_lwa3d, method
         self.on_height_grid = on_height_grid
-        self.input_dtype = input_dtype   # float32 host inputs (ERA5's native precision) are widened on the device
+        # float32 or CF-packed int16 host inputs in file order cross PCIe as they are and are decoded / reordered on
+        # the device (ingest_field); ``packing`` = one (scale_factor, add_offset[, fill_value]) per field or None
+        self.input_dtype = input_dtype
+        self.packing = tuple(packing) if packing is not None else (None, None, None)
+        self.flip_lat, self.flip_lev = bool(flip_lat), bool(flip_lev)
         self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
         nl = plan.kmax if on_height_grid else plan.nlev
         shape = (self.chunk, nl, plan.nlat, plan.nlon)
@@ -261,6 +298,14 @@ class HostStream:
         self.ev_in = [torch.cuda.Event() for _ in range(2)]
         self.ev_free = [torch.cuda.Event() for _ in range(2)]
         self.h2d_bytes = self.d2h_bytes = 0
+        self.trace = None    # set to a list to collect (phase, chunk, start event, end event) for a timeline
+
+    def _mark(self, stream):
+        if self.trace is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        return e
 
     @staticmethod
     def pinned(shape, dtype=torch.float64):
@@ -278,10 +323,13 @@ class HostStream:
     def _h2d(self, slot, host, lo, hi):
         with torch.cuda.stream(self.s_in):
             self.s_in.wait_event(self.ev_free[slot])
+            e0 = self._mark(self.s_in)
             for dst, src in zip(self.slots[slot], host):
                 dst[:hi - lo].copy_(src[lo:hi], non_blocking=True)
                 self.h2d_bytes += (hi - lo) * dst[0].numel() * dst.element_size()
             self.ev_in[slot].record(self.s_in)
+            if e0 is not None:
+                self.trace.append(("h2d", lo, e0, self._mark(self.s_in)))
 
     def run(self, u, v, t, out=None, cycles=1):
         """u, v, t: pinned host tensors [N][nlev][nlat][nlon] of ``input_dtype`` (NumPy arrays are staged through
@@ -292,7 +340,10 @@ class HostStream:
         for x in (u, v, t):
             if not isinstance(x, torch.Tensor):
                 x = torch.from_numpy(np.ascontiguousarray(x))
-            x = x.to(self.input_dtype)
+            if x.dtype != self.input_dtype:
+                if not self.input_dtype.is_floating_point:
+                    raise TypeError(f"HostStream(input_dtype={self.input_dtype}) was given {x.dtype} values")
+                x = x.to(self.input_dtype)
             if not x.is_pinned():
                 x = x.pin_memory()
             host.append(x)
@@ -304,20 +355,37 @@ class HostStream:
         for e in self.ev_free:
             e.record(main)
         bounds = [(lo, min(n, lo + self.chunk)) for lo in range(0, n, self.chunk)] * int(cycles)
-        self._h2d(0, host, *bounds[0])
-        for c, (lo, hi) in enumerate(bounds):
-            slot = c & 1
-            if c + 1 < len(bounds):
-                self._h2d(slot ^ 1, host, *bounds[c + 1])
-            main.wait_event(self.ev_in[slot])
-            b = QGBatch(self.plan, *(x[:hi - lo].to(torch.float64) for x in self.slots[slot]),
-                        on_height_grid=self.on_height_grid)
-            b.run(method=self.method)
-            self.ev_free[slot].record(main)
+        marks = {}
+
+        def chunks():
+            """Device batches in order; called back by run_stream when stage 1 and 2 of the previous chunk are queued."""
+            self._h2d(0, host, *bounds[0])
+            for c, (lo, hi) in enumerate(bounds):
+                slot = c & 1
+                if c >= 1:   # the other slot was last read by stage 1 of chunk c-1, which is queued by now
+                    self.ev_free[slot ^ 1].record(main)
+                if c + 1 < len(bounds):
+                    self._h2d(slot ^ 1, host, *bounds[c + 1])
+                main.wait_event(self.ev_in[slot])
+                marks[c] = self._mark(main)
+                fields = [x[:hi - lo] for x in self.slots[slot]]
+                for i, pk in enumerate(self.packing):
+                    # (data on the height grid is read by all three stages: it must leave the input slot too)
+                    if needs_ingest(self.input_dtype, pk, self.flip_lat, self.flip_lev) or self.on_height_grid:
+                        fields[i] = ingest_field(fields[i], pk, self.flip_lat, self.flip_lev)
+                yield fields
+
+        # run_stream queues the hemispheric means of chunk c+1 before the flux stage of chunk c: the host fits the
+        # splines of c+1 while the device is busy, and the copies of the neighbouring chunks overlap both
+        for c, b in enumerate(run_stream(self.plan, chunks(), method=self.method, on_height_grid=self.on_height_grid)):
+            lo, hi = bounds[c]
             done = torch.cuda.Event()
             done.record(main)
+            if marks.get(c) is not None:
+                self.trace.append(("compute", lo, marks.pop(c), self._mark(main)))
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(done)
+                e0 = self._mark(self.s_out)
                 pairs = [("qref", b.qref_cu), ("uref", b.uref), ("ptref", b.ptref), ("out2d", b.out2d)]
                 if self.want_lwa3d:
                     pairs.append(("lwa", b.lwa))
@@ -325,6 +393,8 @@ class HostStream:
                     dev.record_stream(self.s_out)
                     out[name][lo:hi].copy_(dev, non_blocking=True)
                     self.d2h_bytes += dev.numel() * 8
+                if e0 is not None:
+                    self.trace.append(("d2h", lo, e0, self._mark(self.s_out)))
             out["num_of_iter"][lo:hi] = b.num_of_iter
         self.s_out.synchronize()
         return out

@@ -99,6 +99,60 @@ for _v in ("ua1", "ua2", "ep1", "ep2", "ep3", "stretch_term"):
     _VARS[_v] = (("height", "ylat", "xlon"), ("height", "ylat_ref_states", "xlon"))
 
 
+_DEVICE_DTYPES = (np.dtype(np.float64), np.dtype(np.float32), np.dtype(np.int16))
+
+
+def _packing_of(da):
+    """(scale_factor, add_offset[, fill_value]) of a variable that was opened WITHOUT CF decoding (the attributes are
+    still in ``attrs``; a decoded xarray variable keeps them in ``encoding`` instead), else None."""
+    attrs = getattr(da, "attrs", None) or {}
+    if "scale_factor" not in attrs and "add_offset" not in attrs:
+        return None
+    pk = (float(attrs.get("scale_factor", 1.0)), float(attrs.get("add_offset", 0.0)))
+    fill = attrs.get("_FillValue", attrs.get("missing_value"))
+    return pk + (float(fill),) if fill is not None else pk
+
+
+def _decode_host(raw, packing, flip_lat, flip_lev):
+    """xarray's CF decoding and the reference's np.flip (xarrayinterface.py:384-405) for a few snapshots on the host
+    (the template field, the per-field fallbacks); chunks of the batched path are decoded on the device instead."""
+    x = np.asarray(raw).astype(np.float64)
+    if packing is not None:
+        x = x * np.float64(packing[0])
+        x = x + np.float64(packing[1])
+        if len(packing) > 2:
+            x[np.asarray(raw).astype(np.float64) == packing[2]] = np.nan
+    if flip_lat:
+        x = np.flip(x, axis=-2)
+    if flip_lev:
+        x = np.flip(x, axis=-3)
+    return x
+
+
+class _LazyField:
+    """Snapshots [n][level][lat][lon] as they lie in the file (``raw``: float64 / float32 / packed int16, any axis
+    order of latitude and level) that read like the decoded, reordered float64 array: ``x[i]`` and ``x[lo:hi]`` decode on
+    the host; the device runner ships ``raw`` and decodes there (engine.ingest_field)."""
+
+    def __init__(self, raw, packing=None, flip_lat=False, flip_lev=False):
+        self.raw, self.packing, self.flip_lat, self.flip_lev = raw, packing, bool(flip_lat), bool(flip_lev)
+
+    shape = property(lambda self: self.raw.shape)
+    ndim = property(lambda self: self.raw.ndim)
+    dtype = np.dtype(np.float64)
+
+    def __len__(self):
+        return self.raw.shape[0]
+
+    def __getitem__(self, idx):
+        if isinstance(idx, slice):
+            return _LazyField(self.raw[idx], self.packing, self.flip_lat, self.flip_lev)
+        return _decode_host(self.raw[idx], self.packing, self.flip_lat, self.flip_lev)
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(_decode_host(self.raw, self.packing, self.flip_lat, self.flip_lev), dtype=dtype)
+
+
 class _FieldView:
     """Per-snapshot read-only view (``QGDataset.fields[i].lwa_baro`` ...), for code that iterates over fields."""
 
@@ -128,7 +182,7 @@ class QGDataset:
         self._qgfield = qgfield or QGFieldNH18
         self._qgfield_args = list(qgfield_args or [])
         self._qgfield_kwargs = dict(qgfield_kwargs or {})
-        u, v, t, dims, coords = self._extract(da_u, da_v, da_t, var_names)
+        u, v, t, dims, coords, packing = self._extract(da_u, da_v, da_t, var_names)
         name_p = _find(_NAMES_PLEV, coords, var_names, "plev")
         name_y = _find(_NAMES_YLAT, coords, var_names, "ylat")
         name_x = _find(_NAMES_XLON, coords, var_names, "xlon")
@@ -145,15 +199,14 @@ class QGDataset:
         shape = (n,) + tuple(u.shape[-3:])
         u, v, t = u.reshape(shape), v.reshape(shape), t.reshape(shape)
         ylat, plev, xlon = np.asarray(coords[name_y]), np.asarray(coords[name_p]), np.asarray(coords[name_x])
-        flip = []
-        if not np.all(np.diff(ylat) > 0):   # xarrayinterface.py:386-395: latitude ascending, pressure descending
+        # xarrayinterface.py:386-395: latitude ascending, pressure descending.  The fields themselves stay as they lie
+        # in the file (packed, unflipped): they are decoded and reordered on the device, chunk by chunk
+        flip_lat = not np.all(np.diff(ylat) > 0)
+        flip_lev = not np.all(np.diff(plev) < 0)
+        if flip_lat:
             ylat = np.flip(ylat)
-            flip.append(-2)
-        if not np.all(np.diff(plev) < 0):
+        if flip_lev:
             plev = np.flip(plev)
-            flip.append(-3)
-        if flip:
-            u, v, t = (np.flip(x, axis=flip) for x in (u, v, t))
         self._n = n
         if shard is None:
             shard = (0, 1)
@@ -165,7 +218,8 @@ class QGDataset:
                 pass
         self._rank, self._world = shard
         self._lo, self._hi = shard_bounds(n, *shard)
-        self._u, self._v, self._t = u[self._lo:self._hi], v[self._lo:self._hi], t[self._lo:self._hi]
+        self._u, self._v, self._t = (_LazyField(x[self._lo:self._hi], pk, flip_lat, flip_lev)
+                                     for x, pk in zip((u, v, t), packing))
         self._xlon, self._ylat, self._plev = xlon, ylat, plev
         self._keep_3d = keep_3d
         self._chunk = chunk
@@ -180,7 +234,8 @@ class QGDataset:
     # ------------------------------------------------------------------------------------------
     @staticmethod
     def _extract(da_u, da_v, da_t, var_names):
-        """-> u, v, t (NumPy, same shape), dims, coords from xarray objects or the Simple* stand-ins."""
+        """-> u, v, t (NumPy, same shape, storage dtype), dims, coords, packing from xarray objects or the Simple*
+        stand-ins."""
         def is_ds(x):
             return (xr is not None and isinstance(x, xr.Dataset)) or isinstance(x, SimpleDataset)
 
@@ -204,7 +259,14 @@ class QGDataset:
         assert tuple(da_u.dims) == tuple(da_v.dims), "dimensions of fields u and v don't match"
         assert tuple(da_u.dims) == tuple(da_t.dims), "dimensions of fields u and t don't match"
         coords = {k: np.asarray(getattr(c, "values", c)) for k, c in da_u.coords.items()}
-        return (np.asarray(da_u.data), np.asarray(da_v.data), np.asarray(da_t.data), tuple(da_u.dims), coords)
+        fields, packing = [], []
+        for da in (da_u, da_v, da_t):
+            a, pk = np.asarray(da.data), _packing_of(da)
+            if a.dtype not in _DEVICE_DTYPES:      # other storage types: decode here, ship float64
+                a, pk = _decode_host(a, pk, False, False), None
+            fields.append(a)
+            packing.append(pk)
+        return (*fields, tuple(da_u.dims), coords, packing)
 
     def _make_template(self):
         if self._template is None:
@@ -486,9 +548,15 @@ class _DeviceRunner:
         on_h = f._data_on_evenly_spaced_pseudoheight_grid
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
         main = torch.cuda.current_stream()
+        # the arrays as they lie in the file (float64 / float32 / packed int16, file order) cross PCIe unchanged; CF
+        # decoding and the latitude / level flips happen on the device (engine.ingest_field)
+        lazy = [x if isinstance(x, _LazyField) else _LazyField(np.asarray(x, dtype=np.float64)) for x in (u, v, t)]
+        u, v, t = (x.raw for x in lazy)
+        tdt = [torch.from_numpy(np.empty(0, dtype=x.dtype)).dtype for x in (u, v, t)]
+        ingest = [engine.needs_ingest(dt, x.packing, x.flip_lat, x.flip_lev) for dt, x in zip(tdt, lazy)]
         shape_in = (self.chunk,) + tuple(u.shape[1:])
-        pin_in = [[torch.empty(shape_in, dtype=torch.float64).pin_memory() for _ in range(3)] for _ in range(2)]
-        dev_in = [[torch.empty(shape_in, dtype=torch.float64, device="cuda") for _ in range(3)] for _ in range(2)]
+        pin_in = [[torch.empty(shape_in, dtype=dt).pin_memory() for dt in tdt] for _ in range(2)]
+        dev_in = [[torch.empty(shape_in, dtype=dt, device="cuda") for dt in tdt] for _ in range(2)]
         ev_in = [torch.cuda.Event() for _ in range(2)]
         ev_free = [torch.cuda.Event() for _ in range(2)]
         for e in ev_free:
@@ -520,8 +588,11 @@ class _DeviceRunner:
         for c, (lo, hi) in enumerate(bounds):
             slot = c & 1
             main.wait_event(ev_in[slot])
-            b = engine.QGBatch(self.plan, *(x[:hi - lo] for x in dev_in[slot]), on_height_grid=on_h,
-                               northern_hemisphere_results_only=nh_only)
+            fields = [x[:hi - lo] for x in dev_in[slot]]
+            for i, x in enumerate(lazy):
+                if ingest[i]:
+                    fields[i] = engine.ingest_field(fields[i], x.packing, x.flip_lat, x.flip_lev)
+            b = engine.QGBatch(self.plan, *fields, on_height_grid=on_h, northern_hemisphere_results_only=nh_only)
             b.interpolate_fields()
             if c + 1 < len(bounds):      # the pinned slot of chunk c+1 is filled by now (or we wait here), send it
                 upload(c + 1, nxt)

@@ -56,4 +56,14 @@ def load_era_snapshot():
     return (xlon, ylat, plev, *fields)
 
 
+def load_era_packed():
+    """The same snapshot as it lies in the files: -> longitude(240), latitude(121, DEscending), level(37, Ascending),
+    raw {u,v,t} int16 (37,121,240) and packing {u,v,t} = (scale_factor, add_offset)."""
+    z = np.load(ERA_NPZ)
+    raw = {v: z[v].copy() for v in "uvt"}
+    packing = {v: (float(z[v + "_scale"]), float(z[v + "_offset"])) for v in "uvt"}
+    return (z["longitude"].astype(np.float64), z["latitude"].astype(np.float64), z["level"].astype(np.float64),
+            raw, packing)
+
+
 from hn2016_falwa_b200.synthetic import ERA_PLEV, synthetic_snapshot  # noqa: E402,F401  (shared input generator)

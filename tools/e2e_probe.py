@@ -14,11 +14,15 @@ def host(dt):
         for b in range(B): h[b].copy_(torch.from_numpy(np.roll(x, 37 * b, axis=-1)))
         out.append(h)
     return out
-for dt in (torch.float64, torch.float32):
-    hin = host(dt)
+for dt in (torch.float64, torch.float32, torch.int16):
+    hin = host(dt if dt != torch.int16 else torch.float64)
+    kw = {}
+    if dt == torch.int16:
+        kw = dict(packing=[(0.01, 0.0)] * 3, flip_lat=True, flip_lev=True)
+        hin = [engine.HostStream.pinned(x.shape, dt).copy_((x / 0.01).round().clamp(-32767, 32767)) for x in hin]
     for lwa3d in (True, False):
         for chunk in (1, 2):
-            hs = engine.HostStream(plan, chunk=chunk, want_lwa3d=lwa3d, input_dtype=dt)
+            hs = engine.HostStream(plan, chunk=chunk, want_lwa3d=lwa3d, input_dtype=dt, **kw)
             out = hs.alloc_outputs(B)
             hs.run(*hin, out=out)
             torch.cuda.synchronize(); t0 = time.perf_counter()
