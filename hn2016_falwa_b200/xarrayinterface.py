@@ -528,7 +528,8 @@ class _DeviceRunner:
         self.f = template
         self.plan = template._plan
         if chunk is None:
-            per = 8 * self.plan.nlon * self.plan.nlat * (3 * self.plan.nlev + 10 * self.plan.kmax + 20)
+            # two input slots + decoded copies, and two batches in flight (stage 1-2 of one, stage 3 of the other)
+            per = 8 * self.plan.nlon * self.plan.nlat * (12 * self.plan.nlev + 20 * self.plan.kmax + 40)
             free = torch.cuda.mem_get_info()[0]
             chunk = int(max(1, min(256, 0.4 * free // per)))
         self.chunk = chunk
@@ -584,35 +585,18 @@ class _DeviceRunner:
         pin_out, out_ev, drain = [dict(), dict()], [None, None], [[], []]
         upload(0, stage(0))
         nxt = stage(1) if len(bounds) > 1 else None
-        pending = None
-        for c, (lo, hi) in enumerate(bounds):
+
+        def finish(c, b):
+            """Flux stage and copy-out of chunk c -> (lo, hi, _HostChunk).  Runs after the hemispheric means of chunk
+            c+1 are queued, so the host fits the splines of c+1 while the device works on this."""
+            lo, hi = bounds[c]
             slot = c & 1
-            main.wait_event(ev_in[slot])
-            fields = [x[:hi - lo] for x in dev_in[slot]]
-            for i, x in enumerate(lazy):
-                if ingest[i]:
-                    fields[i] = engine.ingest_field(fields[i], x.packing, x.flip_lat, x.flip_lev)
-            b = engine.QGBatch(self.plan, *fields, on_height_grid=on_h, northern_hemisphere_results_only=nh_only)
-            b.interpolate_fields()
-            if c + 1 < len(bounds):      # the pinned slot of chunk c+1 is filled by now (or we wait here), send it
-                upload(c + 1, nxt)
-                nxt = stage(c + 2) if c + 2 < len(bounds) else None
-            if "ref" in stages:
-                b.compute_reference_states()
-                if self.plan.kind == 0 and (b.num_of_iter >= f.maxit).any():
-                    msg = "The reference state does not converge for at least one snapshot of the batch."
-                    if f._raise_error_for_nonconvergence:
-                        raise ValueError(msg)
-                    import warnings
-                    warnings.warn(msg)
             if "flux" in stages:
                 b.compute_lwa_and_barotropic_fluxes(ncforce=None if ncforce is None else ncforce[lo:hi])
-            ev_free[slot].record(main)
             done = torch.cuda.Event()
             done.record(main)
-            # results of this chunk -> pinned slot (side stream) ...
             for fu in drain[slot]:
-                fu.result()          # the slot's previous contents have been copied out
+                fu.result()          # the pinned slot's previous contents have been copied out
             drain[slot] = []
             host = {}
             with torch.cuda.stream(s_out):
@@ -642,12 +626,43 @@ class _DeviceRunner:
                 if self.plan.kind == 1 and nh_only:
                     ss = p[:, 3].copy()
                 host["static_stability"] = ss
-            # ... and the PREVIOUS chunk, whose copy has had a whole chunk of compute to finish, is handed over
+            return lo, hi, _HostChunk(host, out_ev[slot], self, drain[slot])
+
+        prev = pending = None
+        for c, (lo, hi) in enumerate(bounds):
+            slot = c & 1
+            main.wait_event(ev_in[slot])
+            fields = [x[:hi - lo] for x in dev_in[slot]]
+            for i, x in enumerate(lazy):
+                if ingest[i] or on_h:    # (data on the height grid is read by all stages: it must leave the slot)
+                    fields[i] = engine.ingest_field(fields[i], x.packing, x.flip_lat, x.flip_lev)
+            b = engine.QGBatch(self.plan, *fields, on_height_grid=on_h, northern_hemisphere_results_only=nh_only)
+            b.launch_theta_means()
+            if prev is not None:
+                item = finish(*prev)
+                # the chunk BEFORE that one, whose copy has had a whole chunk of compute to finish, is handed over
+                if pending is not None:
+                    yield pending
+                pending = item
+            b.interpolate_fields()      # waits for the means only; the device is busy with the previous flux stage
+            ev_free[slot].record(main)  # stage 1 was the last reader of the input slot
+            if c + 1 < len(bounds):      # the pinned slot of chunk c+1 is filled by now (or we wait here), send it
+                upload(c + 1, nxt)
+                nxt = stage(c + 2) if c + 2 < len(bounds) else None
+            if "ref" in stages:
+                b.compute_reference_states()
+                if self.plan.kind == 0 and (b.num_of_iter >= f.maxit).any():
+                    msg = "The reference state does not converge for at least one snapshot of the batch."
+                    if f._raise_error_for_nonconvergence:
+                        raise ValueError(msg)
+                    import warnings
+                    warnings.warn(msg)
+            prev = (c, b)
+        if prev is not None:
+            item = finish(*prev)
             if pending is not None:
                 yield pending
-            pending = (lo, hi, _HostChunk(host, out_ev[slot], self, drain[slot]))
-        if pending is not None:
-            yield pending
+            yield item
         for d in drain:
             for fu in d:
                 fu.result()
