@@ -208,6 +208,18 @@ int falwa_b200_barotropic_eqvlat_lwa(int batch, int nlon, int nlat, int n_points
                                      const double* area, const double* ylat_host, const double* dmu_host,
                                      double planet_radius, double* qref, double* lwa, int partitioned, void* stream);
 
+/* The two halves separately, as the hemispheric callers of src/falwa/wrapper.py:89-574 use them.
+ * falwa_b200_eqvlat_2d: mode 0 = basis.eqvlat_fawa (basis.py:11-64): qref [batch][nlat]; aux = fawa [batch][nlat-1]
+ *   or NULL (output_fawa=False).  mode 1 = basis.eqvlat_vgrad (basis.py:67-134): aux = brac [batch][nlat] together
+ *   with vgrad [batch][nlat][nlon], or both NULL.
+ * falwa_b200_lwa_2d: basis.lwa (basis.py:137-205) with a prescribed Q(y): qref [batch][nlat] (device), dmu_host
+ *   [nlat]; ncforce and bigsigma [batch][nlat][nlon] both given or both NULL; lwa as above. */
+int falwa_b200_eqvlat_2d(int mode, int batch, int nlon, int nlat, int n_points, const double* vort,
+                         const double* area, const double* vgrad, const double* ylat_host, double planet_radius,
+                         double* qref, double* aux, void* stream);
+int falwa_b200_lwa_2d(int batch, int nlon, int nlat, const double* vort, const double* qref, const double* dmu_host,
+                      const double* ncforce, double* lwa, double* bigsigma, int partitioned, void* stream);
+
 /* ======================================================================================
  * Section D — ingest of archived fields (the data format in front of the path): raw values as stored in the file
  * -> float64 [batch][nlev][nlat][nlon], latitude ascending, pressure descending.  Replaces, on the device, xarray's

@@ -95,3 +95,113 @@ ANSWER_KEY = dict(
                39.32040089, 41.20590115, 39.32040089, 33.84846603, 25.32572766, 14.58645081, 5.34276464, 0.,
                8.64894682, 16.38582659, 24.10885087, 26.82811918, 24.10885087, 16.38582659, 8.64894682, 0.,
                5.34276464, 14.58645081, 25.32572766, 33.84846603, 39.32040089])
+
+
+# ---- the rest of basis.py / wrapper.py --------------------------------------------------------
+def _bin_sums(vort, area, n_points, weights=None):
+    """np.digitize membership of every grid point in the n_points uniform bins between min and max (the maximum
+    falls outside and is dropped) -> bin edges, area per bin, and optionally sum(area * weights) per bin; index 0 is
+    the never-populated bin below the minimum (basis.py:41-50, :100-120)."""
+    edges = np.linspace(np.amin(vort), np.amax(vort), n_points, endpoint=True)
+    inds = np.digitize(vort.ravel(), edges)
+    a = area.ravel()
+    keep = inds < n_points
+    asum = np.zeros(n_points)
+    np.add.at(asum, inds[keep], a[keep])
+    wsum = None
+    if weights is not None:
+        wsum = np.zeros(n_points)
+        np.add.at(wsum, inds[keep], (a * weights.ravel())[keep])
+    return edges, asum, wsum
+
+
+def _eqv_latitude(asum, planet_radius):
+    return np.rad2deg(np.arcsin(np.cumsum(asum) / (2 * pi * planet_radius ** 2) - 1.0))
+
+
+def eqvlat_fawa(ylat, vort, area, n_points, planet_radius=EARTH_RADIUS, output_fawa=True):
+    """basis.py:11-64.  FAWA = -(cbar + cref)/(2 pi a) on rows 1..nlat-1, with cref the cumulative area-weighted
+    vorticity interpolated to ylat and cbar the trapezoidal sum of zonal-mean vorticity x row area from the pole."""
+    edges, asum, wsum = _bin_sums(vort, area, n_points, weights=vort if output_fawa else None)
+    lat = _eqv_latitude(asum, planet_radius)
+    qref = np.interp(ylat, lat, edges)
+    if not output_fawa:
+        return qref, None
+    cref = np.interp(ylat, lat, np.cumsum(wsum))
+    rowint = vort.mean(axis=-1) * area.sum(axis=1)
+    cbar = np.zeros_like(cref)
+    for j in range(ylat.size - 2, 0, -1):
+        cbar[j] = cbar[j + 1] + 0.5 * (rowint[j + 1] + rowint[j])
+    return qref, -(cbar[1:] + cref[1:]) / (2 * pi * planet_radius)
+
+
+def eqvlat_vgrad(ylat, vort, area, n_points, planet_radius=EARTH_RADIUS, vgrad=None):
+    """basis.py:67-134: bracket = mean over the two neighbouring bins of the area-weighted bin average of vgrad."""
+    edges, asum, wsum = _bin_sums(vort, area, n_points, weights=vgrad)
+    lat = _eqv_latitude(asum, planet_radius)
+    q_part = np.interp(ylat, lat, edges)
+    if vgrad is None:
+        return q_part, None
+    dp = np.divide(wsum, asum, out=np.zeros_like(wsum), where=asum != 0.)
+    brac = np.zeros(n_points)
+    brac[1:-1] = 0.5 * (dp[:-2] + dp[2:])
+    return q_part, np.interp(ylat, lat, brac)
+
+
+def lwa_full(nlon, nlat, vort, q_part, dmu, return_partitioned_lwa=False, ncforce=None):
+    """basis.py:137-205 including the partitioned output (anticyclonic, cyclonic) and the non-conservative term."""
+    parts = np.zeros((2, nlat, nlon))
+    sigma = np.zeros((nlat, nlon)) if ncforce is not None else None
+    rows = np.arange(nlat)[:, np.newaxis]
+    w = dmu[:, np.newaxis]
+    for j in range(nlat - 1):
+        e = vort - q_part[j]
+        anti = np.where((e < 0) & (rows > j), -1.0, 0.0)
+        cyc = np.where((e > 0) & (rows <= j), 1.0, 0.0)
+        parts[0, j] = np.sum(e * anti * w, axis=0)
+        parts[1, j] = np.sum(e * cyc * w, axis=0)
+        if ncforce is not None:
+            sigma[j] = np.sum(ncforce * (anti + cyc) * w, axis=0)
+    return (parts if return_partitioned_lwa else parts.sum(axis=0)), sigma
+
+
+def hemispheric(ylat, field, area, dmu, nlat_s=None, n_points=None, planet_radius=EARTH_RADIUS, sign=-1.0,
+                negate_back=True, vgrad=None, ncforce=None, with_lwa=True, vgrad_whole=False):
+    """The common structure of wrapper.py:89-574: southern rows as they are, northern rows flipped and multiplied by
+    ``sign``; the northern qref (and bracket) flipped back and, for ``negate_back``, negated.  Returns dict(qref,
+    lwa_result, brac_result, capsigma) with None for what was not asked."""
+    nlat, nlon = field.shape
+    nlat_s = nlat // 2 if nlat_s is None else nlat_s
+    n_points = nlat_s if n_points is None else n_points
+    back = -1.0 if negate_back else 1.0
+    south, north = field[:nlat_s], (sign * field[::-1])[:nlat_s]
+    gs = gn = None
+    if vgrad is not None:
+        gs = vgrad[:nlat_s]
+        gn = gs if vgrad_whole else (-vgrad[::-1])[:nlat_s]
+    fn = eqvlat_vgrad if vgrad is not None else (lambda *a, **k: eqvlat_fawa(*a, output_fawa=False, **k))
+    kw = (lambda g: dict(vgrad=g)) if vgrad is not None else (lambda g: {})
+    q1, b1 = fn(ylat[:nlat_s], south, area[:nlat_s], n_points, planet_radius=planet_radius, **kw(gs))
+    q2, b2 = fn(ylat[:nlat_s], north, area[:nlat_s], n_points, planet_radius=planet_radius, **kw(gn))
+    qref = np.zeros(nlat)
+    qref[:nlat_s], qref[-nlat_s:] = q1, back * q2[::-1]
+    out = dict(qref=qref, lwa_result=None, brac_result=None, capsigma=None)
+    if vgrad is not None:
+        brac = np.zeros(nlat)
+        brac[:nlat_s], brac[-nlat_s:] = b1, back * b2[::-1]
+        out["brac_result"] = brac
+    if with_lwa:
+        out["lwa_result"], out["capsigma"] = hemispheric_lwa(field, qref, dmu, nlat_s, ncforce)
+    return out
+
+
+def hemispheric_lwa(field, qref, dmu, nlat_s, ncforce=None):
+    nlat, nlon = field.shape
+    res = np.zeros((nlat, nlon))
+    sig = np.zeros((nlat, nlon)) if ncforce is not None else None
+    for sl in (slice(None, nlat_s), slice(nlat - nlat_s, None)):
+        l, s = lwa_full(nlon, nlat_s, field[sl], qref[sl], dmu[sl], ncforce=None if ncforce is None else ncforce[sl])
+        res[sl] = l
+        if sig is not None:
+            sig[sl] = s
+    return res, sig

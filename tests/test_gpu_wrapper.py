@@ -1,0 +1,102 @@
+"""GPU parity of hn2016_falwa_b200.basis / .wrapper (the reference's falwa.basis / falwa.wrapper)
+with the golden vectors of the reference's own modules (tests/golden/wrapper_2d.npz) and the oracle.
+
+Tolerances: the area histograms are accumulated with floating-point atomics (order-dependent in the last bits), so
+quantities derived from them carry rtol 1e-10; the LWA line integrals for a GIVEN qref are sequential sums in the
+reference's order and must agree to the last bit."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import basis2d, testdata
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(testdata.GOLDEN_DIR, "wrapper_2d.npz"))
+Y, PV, AREA, DMU = G["ylat"], G["pv"], G["area"], G["dmu"]
+NLAT, NLON = PV.shape
+
+
+def close(a, b, rtol=1e-10):
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=rtol * np.abs(b).max())
+
+
+def test_basis_eqvlat_fawa_vgrad():
+    from hn2016_falwa_b200 import basis
+    q, f = basis.eqvlat_fawa(Y, PV, AREA, NLAT)
+    assert q.shape == (NLAT,) and f.shape == (NLAT - 1,)
+    close(q, G["fawa_qref"]); close(f, G["fawa_fawa"], 1e-9)
+    q, f = basis.eqvlat_fawa(Y, PV, AREA, 31, output_fawa=False)
+    assert f is None
+    close(q, G["fawa_qref_31"])
+    q, b = basis.eqvlat_vgrad(Y, PV, AREA, NLAT, vgrad=G["vgrad"])
+    close(q, G["vgrad_q"]); close(b, G["vgrad_brac"], 1e-9)
+    q, b = basis.eqvlat_vgrad(Y, PV, AREA, 40)
+    assert b is None
+    close(q, G["vgrad_q_none"])
+
+
+def test_basis_lwa_is_bit_exact_for_a_given_qref():
+    from hn2016_falwa_b200 import basis
+    parts, sig = basis.lwa(NLON, NLAT, PV, G["fawa_qref"], DMU, return_partitioned_lwa=True, ncforce=G["ncforce"])
+    np.testing.assert_array_equal(parts, G["lwa_parts"])
+    np.testing.assert_array_equal(sig, G["lwa_sigma"])
+    total, none = basis.lwa(NLON, NLAT, PV, G["fawa_qref"], DMU)
+    assert none is None
+    np.testing.assert_array_equal(total, G["lwa_parts"][0] + G["lwa_parts"][1])
+
+
+def test_basis_batched_and_device_tensors():
+    import torch
+    from hn2016_falwa_b200 import basis
+    fields = np.stack([PV, PV[:, ::-1].copy(), 0.5 * PV])
+    q, f = basis.eqvlat_fawa(Y, torch.from_numpy(fields).cuda(), AREA, NLAT)
+    assert q.is_cuda and tuple(q.shape) == (3, NLAT) and tuple(f.shape) == (3, NLAT - 1)
+    for i in range(3):
+        qo, fo = basis2d.eqvlat_fawa(Y, fields[i], AREA, NLAT)
+        close(q[i].cpu().numpy(), qo); close(f[i].cpu().numpy(), fo, 1e-9)
+
+
+def test_wrappers_against_reference_golden():
+    from hn2016_falwa_b200 import wrapper
+    q, l = wrapper.barotropic_eqlat_lwa(Y, PV, AREA, DMU, NLAT)
+    close(q, G["w_baro_qref"]); close(l, G["w_baro_lwa"], 1e-9)
+    l, none = wrapper.barotropic_input_qref_to_compute_lwa(Y, G["fawa_qref"], PV, AREA, DMU)
+    assert none is None
+    np.testing.assert_array_equal(l, G["w_baro_input_qref_lwa"])
+    close(wrapper.eqvlat_hemispheric(Y, PV, AREA), G["w_eqvlat_hemi"])
+    q, l = wrapper.qgpv_eqlat_lwa(Y, PV, AREA, DMU)
+    close(q, G["w_qgpv_qref"]); close(l, G["w_qgpv_lwa"], 1e-9)
+    q, l, c = wrapper.qgpv_eqlat_lwa_ncforce(Y, PV, G["ncforce"], AREA, DMU, n_points=30)
+    close(q, G["w_ncf_qref"]); close(l, G["w_ncf_lwa"], 1e-9); close(c, G["w_ncf_capsigma"], 1e-9)
+    o = wrapper.qgpv_eqlat_lwa_options(Y, PV, AREA, DMU, ncforce=G["ncforce"])
+    assert set(o) == {"qref", "lwa_result", "capsigma"}
+    close(o["qref"], G["w_opt_qref"]); close(o["lwa_result"], G["w_opt_lwa"], 1e-9)
+    close(o["capsigma"], G["w_opt_capsigma"], 1e-9)
+    np.testing.assert_array_equal(wrapper.qgpv_input_qref_to_compute_lwa(Y, G["w_qgpv_qref"], PV, AREA, DMU),
+                                  G["w_input_qref_lwa"])
+    q, l = wrapper.theta_lwa(Y, G["theta"], AREA, DMU)
+    close(q, G["w_theta_qref"]); close(l, G["w_theta_lwa"], 1e-9)
+
+
+def test_wrappers_that_fail_upstream_follow_the_oracle():
+    """eqvlat_bracket_hemispheric and qgpv_eqlat_lwa_options(vgrad=...) raise TypeError upstream; here they do what
+    their docstrings say (basis.eqvlat_vgrad per hemisphere)."""
+    from hn2016_falwa_b200 import wrapper
+    q, b = wrapper.eqvlat_bracket_hemispheric(Y, PV, AREA, vgrad=G["vgrad"])
+    o = basis2d.hemispheric(Y, PV, AREA, DMU, negate_back=False, vgrad=G["vgrad"], with_lwa=False, vgrad_whole=True)
+    close(q, o["qref"]); close(b, o["brac_result"], 1e-9)
+    r = wrapper.qgpv_eqlat_lwa_options(Y, PV, AREA, DMU, vgrad=G["vgrad"], ncforce=G["ncforce"])
+    o = basis2d.hemispheric(Y, PV, AREA, DMU, vgrad=G["vgrad"], ncforce=G["ncforce"])
+    assert set(r) == {"qref", "lwa_result", "brac_result", "capsigma"}
+    close(r["qref"], o["qref"]); close(r["brac_result"], o["brac_result"], 1e-9)
+    close(r["lwa_result"], o["lwa_result"], 1e-9); close(r["capsigma"], o["capsigma"], 1e-9)
+
+
+def test_errors():
+    from hn2016_falwa_b200 import basis
+    with pytest.raises(AssertionError):
+        basis.eqvlat_fawa(Y[:-1], PV, AREA, NLAT)
+    with pytest.raises(ValueError):
+        basis.eqvlat_fawa(Y, PV, AREA, 1)
