@@ -27,7 +27,7 @@ _SIGNATURES = {
     "falwa_b200_barotropic_eqvlat_lwa": [c_i] * 4 + [c_dp] * 4 + [c_d] + [c_dp] * 2 + [c_i, c_dp],
     "falwa_b200_eqvlat_2d": [c_i] * 5 + [c_dp] * 4 + [c_d] + [c_dp] * 3,
     "falwa_b200_lwa_2d": [c_i] * 3 + [c_dp] * 6 + [c_i, c_dp],
-    "falwa_b200_ingest_field": [c_i] * 5 + [c_dp, c_d, c_d, c_i, c_d, c_i, c_i, c_dp, c_dp],
+    "falwa_b200_ingest_field": [c_i] * 5 + [c_dp, c_i, c_d, c_d, c_i, c_d, c_i, c_i, c_dp, c_dp],
     "falwa_b200_compute_lwa_only_nhn22": [c_dp] * 3 + [c_i] * 6 + [c_d] * 7 + [c_dp] * 4 + [c_i, c_dp],
 }
 

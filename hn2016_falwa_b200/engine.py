@@ -51,17 +51,18 @@ def _register():
 _SRC_TYPES = {torch.float64: 0, torch.float32: 1, torch.int16: 2}
 
 
-def needs_ingest(dtype, packing=None, flip_lat=False, flip_lev=False):
-    """False when the raw array already is what the pipeline reads (float64, ordered, not packed)."""
-    return dtype != torch.float64 or packing is not None or flip_lat or flip_lev
+def needs_ingest(dtype, packing=None, flip_lat=False, flip_lev=False, byteswap=False):
+    """False when the raw array already is what the pipeline reads (native float64, ordered, not packed)."""
+    return dtype != torch.float64 or packing is not None or flip_lat or flip_lev or byteswap
 
 
-def ingest_field(raw, packing=None, flip_lat=False, flip_lev=False, out=None):
+def ingest_field(raw, packing=None, flip_lat=False, flip_lev=False, out=None, byteswap=False):
     """Archived values on the device -> the pipeline's float64 [B][level][lat][lon], latitude ascending, pressure
     descending (Section D of falwa_b200.h).  ``raw``: CUDA tensor of float64 / float32 / int16 as it lies in the file;
     ``packing`` = (scale_factor, add_offset[, fill_value]) of CF-packed variables, value = raw * scale + offset and
     fill -> NaN, like xarray's decoder; ``flip_lat`` / ``flip_lev`` reverse those axes (the np.flip of
-    xarrayinterface.py:384-405)."""
+    xarrayinterface.py:384-405); ``byteswap``: the values are stored big-endian (NetCDF-3 files) and ``raw`` is the
+    same bytes viewed as the native type."""
     assert raw.is_cuda and raw.dim() == 4 and raw.dtype in _SRC_TYPES, "ingest_field: [B][lev][lat][lon] f64/f32/i16"
     raw = raw.contiguous()
     if out is None:
@@ -74,7 +75,7 @@ def ingest_field(raw, packing=None, flip_lat=False, flip_lev=False, out=None):
         fill = packing[2] if len(packing) > 2 else None
     B, nl, ny, nx = (int(x) for x in raw.shape)
     check(_lib.load().falwa_b200_ingest_field(
-        _SRC_TYPES[raw.dtype], B, nl, ny, nx, ctypes.c_void_p(raw.data_ptr()), scale, offset,
+        _SRC_TYPES[raw.dtype], B, nl, ny, nx, ctypes.c_void_p(raw.data_ptr()), int(bool(byteswap)), scale, offset,
         int(fill is not None), float(fill) if fill is not None else 0.0, int(bool(flip_lat)), int(bool(flip_lev)),
         dptr(out), stream_ptr()), "ingest_field")
     return out
@@ -283,14 +284,14 @@ class HostStream:
     """
 
     def __init__(self, plan, chunk=1, want_lwa3d=True, method=0, on_height_grid=False, input_dtype=torch.float64,
-                 packing=None, flip_lat=False, flip_lev=False):
+                 packing=None, flip_lat=False, flip_lev=False, byteswap=False):
         self.plan, self.chunk, self.want_lwa3d, self.method = plan, int(chunk), want_lwa3d, method
         self.on_height_grid = on_height_grid
         # float32 or CF-packed int16 host inputs in file order cross PCIe as they are and are decoded / reordered on
         # the device (ingest_field); ``packing`` = one (scale_factor, add_offset[, fill_value]) per field or None
         self.input_dtype = input_dtype
         self.packing = tuple(packing) if packing is not None else (None, None, None)
-        self.flip_lat, self.flip_lev = bool(flip_lat), bool(flip_lev)
+        self.flip_lat, self.flip_lev, self.byteswap = bool(flip_lat), bool(flip_lev), bool(byteswap)
         self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
         nl = plan.kmax if on_height_grid else plan.nlev
         shape = (self.chunk, nl, plan.nlat, plan.nlon)
@@ -371,8 +372,9 @@ class HostStream:
                 fields = [x[:hi - lo] for x in self.slots[slot]]
                 for i, pk in enumerate(self.packing):
                     # (data on the height grid is read by all three stages: it must leave the input slot too)
-                    if needs_ingest(self.input_dtype, pk, self.flip_lat, self.flip_lev) or self.on_height_grid:
-                        fields[i] = ingest_field(fields[i], pk, self.flip_lat, self.flip_lev)
+                    if needs_ingest(self.input_dtype, pk, self.flip_lat, self.flip_lev, self.byteswap) \
+                            or self.on_height_grid:
+                        fields[i] = ingest_field(fields[i], pk, self.flip_lat, self.flip_lev, byteswap=self.byteswap)
                 yield fields
 
         # run_stream queues the hemispheric means of chunk c+1 before the flux stage of chunk c: the host fits the

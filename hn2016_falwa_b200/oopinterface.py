@@ -48,7 +48,9 @@ class QGFieldBase(ABC):
         self._raise_error_for_nonconvergence = raise_error_for_nonconvergence
         self._nonconvergent_uref = False
         self._data_on_evenly_spaced_pseudoheight_grid = data_on_evenly_spaced_pseudoheight_grid
-        plev = np.asarray(plev)
+        # coordinates are widened to float64 whatever their storage type (files hold float32 / int32 coordinates; the
+        # reference would carry that precision into its float32 natives, this pipeline is float64 throughout)
+        plev = np.asarray(plev, dtype=np.float64)
         if data_on_evenly_spaced_pseudoheight_grid:  # oopinterface.py:110-115
             self.plev = plev
             self.kmax = plev.size
@@ -66,8 +68,8 @@ class QGFieldBase(ABC):
         t_field = self._convert_masked_data(t_field, "t_field")
         ylat = self._convert_masked_data(ylat, "ylat")
         self._input_ylat, self.need_latitude_interpolation, self._ylat, self.equator_idx, self._clat = \
-            self._check_and_flip_ylat(np.asarray(ylat))
-        self.xlon = np.asarray(xlon)
+            self._check_and_flip_ylat(np.asarray(ylat, dtype=np.float64))
+        self.xlon = np.asarray(xlon, dtype=np.float64)
         self.nlev, self.nlat, self.nlon = plev.size, np.asarray(ylat).size, self.xlon.size
         expected = (self.nlev, self.nlat, self.nlon)
         for field, name in ((u_field, "u_field"), (v_field, "v_field"), (t_field, "theta_field")):

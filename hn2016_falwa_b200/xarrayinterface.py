@@ -137,6 +137,16 @@ class _LazyField:
     def __init__(self, raw, packing=None, flip_lat=False, flip_lev=False):
         self.raw, self.packing, self.flip_lat, self.flip_lev = raw, packing, bool(flip_lat), bool(flip_lev)
 
+    @property
+    def byteswap(self):
+        """stored in the other byte order (NetCDF-3 files are big-endian): swapped on the device"""
+        return not self.raw.dtype.isnative
+
+    @property
+    def raw_native(self):
+        """the same bytes viewed as the native type (what torch and the pinned staging buffers can hold)"""
+        return self.raw.view(self.raw.dtype.newbyteorder("=")) if self.byteswap else self.raw
+
     shape = property(lambda self: self.raw.shape)
     ndim = property(lambda self: self.raw.ndim)
     dtype = np.dtype(np.float64)
@@ -262,7 +272,7 @@ class QGDataset:
         fields, packing = [], []
         for da in (da_u, da_v, da_t):
             a, pk = np.asarray(da.data), _packing_of(da)
-            if a.dtype not in _DEVICE_DTYPES:      # other storage types: decode here, ship float64
+            if a.dtype.newbyteorder("=") not in _DEVICE_DTYPES:      # other storage types: decode here, ship float64
                 a, pk = _decode_host(a, pk, False, False), None
             fields.append(a)
             packing.append(pk)
@@ -552,9 +562,9 @@ class _DeviceRunner:
         # the arrays as they lie in the file (float64 / float32 / packed int16, file order) cross PCIe unchanged; CF
         # decoding and the latitude / level flips happen on the device (engine.ingest_field)
         lazy = [x if isinstance(x, _LazyField) else _LazyField(np.asarray(x, dtype=np.float64)) for x in (u, v, t)]
-        u, v, t = (x.raw for x in lazy)
+        u, v, t = (x.raw_native for x in lazy)
         tdt = [torch.from_numpy(np.empty(0, dtype=x.dtype)).dtype for x in (u, v, t)]
-        ingest = [engine.needs_ingest(dt, x.packing, x.flip_lat, x.flip_lev) for dt, x in zip(tdt, lazy)]
+        ingest = [engine.needs_ingest(dt, x.packing, x.flip_lat, x.flip_lev, x.byteswap) for dt, x in zip(tdt, lazy)]
         shape_in = (self.chunk,) + tuple(u.shape[1:])
         pin_in = [[torch.empty(shape_in, dtype=dt).pin_memory() for dt in tdt] for _ in range(2)]
         dev_in = [[torch.empty(shape_in, dtype=dt, device="cuda") for dt in tdt] for _ in range(2)]
@@ -635,7 +645,7 @@ class _DeviceRunner:
             fields = [x[:hi - lo] for x in dev_in[slot]]
             for i, x in enumerate(lazy):
                 if ingest[i] or on_h:    # (data on the height grid is read by all stages: it must leave the slot)
-                    fields[i] = engine.ingest_field(fields[i], x.packing, x.flip_lat, x.flip_lev)
+                    fields[i] = engine.ingest_field(fields[i], x.packing, x.flip_lat, x.flip_lev, byteswap=x.byteswap)
             b = engine.QGBatch(self.plan, *fields, on_height_grid=on_h, northern_hemisphere_results_only=nh_only)
             b.launch_theta_means()
             if prev is not None:

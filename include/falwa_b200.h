@@ -225,12 +225,13 @@ int falwa_b200_lwa_2d(int batch, int nlon, int nlat, const double* vort, const d
  * -> float64 [batch][nlev][nlat][nlon], latitude ascending, pressure descending.  Replaces, on the device, xarray's
  * CF decoding (value = raw * scale_factor + add_offset in float64, _FillValue -> NaN) and the np.flip reordering of
  * src/falwa/xarrayinterface.py:384-405 (recipe for the packed test snapshot: tests/test_output_results.py:26-45).
- * src_type: 0 float64, 1 float32, 2 int16.  Pass scale = 1, offset = 0 for unpacked values.  src, dst: device
- * pointers, same shape, not overlapping.
+ * src_type: 0 float64, 1 float32, 2 int16; big_endian != 0: the stored values are big-endian (NetCDF-3 classic /
+ * 64-bit-offset files).  Pass scale = 1, offset = 0 for unpacked values.  src, dst: device pointers, same shape,
+ * not overlapping.
  * ====================================================================================== */
-int falwa_b200_ingest_field(int src_type, int batch, int nlev, int nlat, int nlon, const void* src, double scale,
-                            double offset, int has_fill, double fill_value, int flip_lat, int flip_lev, double* dst,
-                            void* stream);
+int falwa_b200_ingest_field(int src_type, int batch, int nlev, int nlat, int nlon, const void* src, int big_endian,
+                            double scale, double offset, int has_fill, double fill_value, int flip_lat, int flip_lev,
+                            double* dst, void* stream);
 
 /* Diagnostics used by bench.py (not on the data path): number of kernels launched by this library so far;
  * optional per-kernel timing with CUDA events on the launching stream.  profile_read synchronises the device
