@@ -204,35 +204,47 @@ lwa_scan_kernel(ScanArgs p) {
     const int i0 = blockIdx.x * kScanCols;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
 
-    // ---- stage tables and the (nd x 8) tile --------------------------------------------------
-    for (int t = tid; t < M; t += blockDim.x) {
-        s_thr[t] = p.thr[pk * nd + t];
-        s_urt[t] = p.urt[pk * nd + t];
-        s_rowof[t] = p.rowof[pk * nd + t];
-    }
-    for (int jj = tid; jj <= nd + 1; jj += blockDim.x) {
-        s_cos[jj] = p.cosphi[jj];
-        s_nxt[jj] = p.nxt[pk * (nd + 2) + jj];
-    }
-    for (int c = tid; c <= kScanCells; c += blockDim.x) s_cell[c] = p.cell[pk * (kScanCells + 1) + c];
-    const double srch_lo = p.srch[pk * 2 + 0], srch_inv = p.srch[pk * 2 + 1];
+    // ---- stage the (nd x 8) tile and the tables ------------------------------------------------
+    // All global loads of the tile are issued before anything waits on them (one DRAM round trip for the whole
+    // tile instead of one per group of rows); the table loads (L2 hits) travel behind them.
     {
         const int col = tid % kScanCols, rr = tid / kScanCols;
         const bool colok = (i0 + col) < p.imax;
         const size_t base = (size_t)b * p.in_batch + (size_t)(k - 1) * p.in_plane + i0 + col;
-        for (int r = rr; r < nd; r += (kScanCols * 32) / kScanCols) {
-            const size_t g = base + (size_t)(fr.in_row0 + fr.in_rstep * r) * p.imax;
-            double q = 0.0, u = 0.0, c = 0.0;
-            if (colok) {
-                q = fr.sg * ld_stream(&p.pv[g]);
-                u = ld_stream(&p.uu[g]);
-                if (HAS_NC) c = ld_stream(&p.nc[g]);
+        double qv[kScanRMax], uv[kScanRMax], cv[HAS_NC ? kScanRMax : 1];
+#pragma unroll
+        for (int c = 0; c < kScanRMax; ++c) {
+            const int r = rr + 32 * c;
+            qv[c] = 0.0; uv[c] = 0.0;
+            if (HAS_NC) cv[c] = 0.0;
+            if (colok && r < nd) {
+                const size_t g = base + (size_t)(fr.in_row0 + fr.in_rstep * r) * p.imax;
+                qv[c] = ld_stream(&p.pv[g]);
+                uv[c] = ld_stream(&p.uu[g]);
+                if (HAS_NC) cv[c] = ld_stream(&p.nc[g]);
             }
-            s_q[col * ndp + r] = q;
-            s_u[col * ndp + r] = u;
-            if (HAS_NC) s_n[col * ndp + r] = c;
+        }
+        for (int t = tid; t < M; t += blockDim.x) {
+            s_thr[t] = p.thr[pk * nd + t];
+            s_urt[t] = p.urt[pk * nd + t];
+            s_rowof[t] = p.rowof[pk * nd + t];
+        }
+        for (int jj = tid; jj <= nd + 1; jj += blockDim.x) {
+            s_cos[jj] = p.cosphi[jj];
+            s_nxt[jj] = p.nxt[pk * (nd + 2) + jj];
+        }
+        for (int c = tid; c <= kScanCells; c += blockDim.x) s_cell[c] = p.cell[pk * (kScanCells + 1) + c];
+#pragma unroll
+        for (int c = 0; c < kScanRMax; ++c) {
+            const int r = rr + 32 * c;
+            if (r < nd) {
+                s_q[col * ndp + r] = fr.sg * qv[c];
+                s_u[col * ndp + r] = uv[c];
+                if (HAS_NC) s_n[col * ndp + r] = cv[c];
+            }
         }
     }
+    const double srch_lo = p.srch[pk * 2 + 0], srch_inv = p.srch[pk * 2 + 1];
     __syncthreads();
 
     // ---- per-warp column work ----------------------------------------------------------------
@@ -343,6 +355,7 @@ lwa_scan_kernel(ScanArgs p) {
         if (s < R && t < M) {
             const int j = s_rowof[t];
             // rows entering at t: nxt(jj) == t  <=>  m_{t-1} <= jj < m_t  (a single row when Qref is monotone)
+#pragma unroll 1
             for (int jj = t ? (int)s_rowof[t - 1] : 1; jj < j; ++jj) {
                 const int e = E_[jj - 1];
                 if (e != t) {
@@ -354,12 +367,15 @@ lwa_scan_kernel(ScanArgs p) {
             }
             // rows leaving (cyclonic) / entering (anticyclonic) at t: E(jj) == t
             const int x0 = cn[t], xe = cn[t + 1];
+#pragma unroll 1
             for (int a = x0 + 1; a < xe; ++a) {   // ascending row order inside the bin (insertion sort, bins are tiny)
                 const short v = pm[a];
                 int c = a - 1;
+#pragma unroll 1
                 for (; c >= x0 && pm[c] > v; --c) pm[c + 1] = pm[c];
                 pm[c + 1] = v;
             }
+#pragma unroll 1
             for (int x = x0; x < xe; ++x) {
                 const int r = pm[x];
                 const double q = q_[r], u = u_[r], cs = s_cos[r + 1];
