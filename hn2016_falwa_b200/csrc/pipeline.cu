@@ -23,7 +23,7 @@ enum Out2D {
 struct falwa_plan {
     int kind, nlon, nlat, nlev, kmax, jb, nd, jd, npart, maxit;
     double a, omega, dz, h, rr, cp, tol, rjac, prefactor, dphi, dlambda;
-    std::vector<double> height;
+    std::vector<double> height, sinlat;   // host copies (tables built per call)
     double* d_tab = nullptr;
     int* d_lo = nullptr;
     // offsets into d_tab
@@ -199,7 +199,12 @@ struct FusedFluxArgs {
     const double *cosphi, *sinphi, *aaw, *ep11a, *vw;
     const double *f11;                          // BRUTE = false: [b][2][kmax] = (R/H) e^{-kappa z/H} 2 dz / (tg(k+1)-tg(k-1))
     double *lwa, *out2d;
+    double* l3d;   // optional layer-wise outputs [b][L3_COUNT][kmax][nlat][nlon] (compute_layerwise_lwa_fluxes)
 };
+
+// slots of the layer-wise output (oopinterface.py:1063-1156: astar1, astar2, ncforce, ua1, ua2, ep1, ep2, ep3; then
+// the stretching term written by zderiv_kernel)
+enum Layer3D { L_ASTAR1 = 0, L_ASTAR2, L_NCF, L_UA1, L_UA2, L_EP1, L_EP2, L_EP3, L_STRETCH, L_LWA, L3_COUNT };
 
 // BRUTE = true: the reference's O(nd^2) double loop inline (method 1).  BRUTE = false: a1 / a2 / ua2 / ncforce3d
 // come from lwa_scan_kernel (flux_scan.cu) and this kernel is a pure column walk ("flux_column").
@@ -320,6 +325,21 @@ fused_flux_kernel(FusedFluxArgs p) {
             e2 = (uu[r1] - uref[(size_t)(k - 1) * nlat + grow(jb + 2)]) * p.cosjb * p.cosjb * (sg * vv[r1]);
             e3 = (uu[r0] - uref[(size_t)(k - 1) * nlat + grow(jb + 1)]) * p.cosjbm1 * p.cosjbm1 * (sg * vv[r0]);
             if (jb == 0) wk = (k >= 3) ? p.vw[k - 2] : 0.0;  // aliased into level k-1; level 1 is not averaged
+        }
+        if (p.l3d) {   // layer-wise fields in the global frame, southern sign rules of oopinterface.py:1117-1148
+            double* L = p.l3d + (size_t)b * L3_COUNT * plane * kmax + lev + o2;
+            const size_t fs = plane * kmax;
+            L[L_ASTAR1 * fs] = a1;
+            L[L_ASTAR2 * fs] = a2;
+            L[L_LWA * fs] = a1 + a2;    // the layer-wise store keeps the sum, not its magnitude (oopinterface.py:1099)
+            L[L_NCF * fs] = south ? -ncf : ncf;
+            L[L_UA1 * fs] = x_ua1;
+            L[L_UA2 * fs] = u2;
+            L[L_EP1 * fs] = e1;
+            // the boundary-row values of a jb = 0 run land on (i, nd, k-1): one level down
+            double* Le = (brow && jb == 0) ? L - plane : L;
+            Le[L_EP2 * fs] = south ? -e3 : e2;
+            Le[L_EP3 * fs] = south ? -e2 : e3;
         }
         s_a1 = acc(s_a1, a1);
         s_a2 = acc(s_a2, a2);
@@ -729,6 +749,7 @@ extern "C" int falwa_b200_plan_create(falwa_plan** out, int kind, int nlon, int 
     P->o_fac = push_tab(tab, std::vector<double>(theta_factor_host, theta_factor_host + nlev));
     P->o_clat = push_tab(tab, std::vector<double>(clat_host, clat_host + nlat));
     P->o_sinlat = push_tab(tab, std::vector<double>(sinlat_host, sinlat_host + nlat));
+    P->sinlat.assign(sinlat_host, sinlat_host + nlat);
     // interpolation tables (scipy interp1d linear, extrapolating)
     std::vector<double> whi(kmax), wlo(kmax);
     std::vector<int> lo(kmax);
@@ -1155,16 +1176,10 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
 // LWA and barotropic fluxes of both hemispheres.
 //   lwa [batch][kmax][nlat][nlon]; out2d [batch][15][nlat][nlon] (slot order: enum Out2D / falwa_b200.h)
 //   ncforce may be NULL (treated as zeros).  method: 0 = automatic, 1 = brute force.
-extern "C" int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* P, int batch, const double* qgpv,
-                                                    const double* u, const double* v, const double* theta,
-                                                    const double* ncforce, const double* profiles_host,
-                                                    const double* qref_cu, const double* uref_st,
-                                                    const double* ptref_st, int north_only, double* lwa,
-                                                    double* out2d, int method, void* stream) {
-    if (!P || !qgpv || !u || !v || !theta || !profiles_host || !qref_cu || !uref_st || !ptref_st || !lwa || !out2d)
-        return FALWA_ERR_NULL;
-    if (batch < 1) return FALWA_ERR_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
+static int lwa_fluxes_impl(const falwa_plan* P, int batch, const double* qgpv, const double* u, const double* v,
+                           const double* theta, const double* ncforce, const double* profiles_host,
+                           const double* qref_cu, const double* uref_st, const double* ptref_st, int north_only,
+                           double* lwa, double* out2d, int method, double* l3d, cudaStream_t st) {
     const double* d = P->d_tab;
     const double pi = host_pi(), dp = pi / (double)(P->nlat - 1);
     const int nlon = P->nlon, nlat = P->nlat, kmax = P->kmax, nd = P->nd, jb = P->jb;
@@ -1198,7 +1213,7 @@ extern "C" int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* P, int bat
     p.clat = d + P->o_clat;
     p.sa1 = p.sa2 = p.su2 = p.snc = nullptr;
     p.f11 = prof.d + (size_t)batch * 4 * kmax;
-    p.lwa = lwa; p.out2d = out2d;
+    p.lwa = lwa; p.out2d = out2d; p.l3d = l3d;
     if (north_only) {  // rows the northern launch does not cover stay zero
         FALWA_CUDA_TRY(cudaMemsetAsync(lwa, 0, sizeof(double) * (size_t)batch * f3, st));
         FALWA_CUDA_TRY(cudaMemsetAsync(out2d, 0, sizeof(double) * (size_t)batch * O_COUNT * nlat * nlon, st));
@@ -1237,7 +1252,11 @@ extern "C" int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* P, int bat
     {
         dim3 block(32, 8);
         dim3 grid(ceil_div(nlon, 32), ceil_div(nd, 8), batch * nhemi);
-        if (use_scan) {
+        if (l3d) {   // layer-wise stores: the plain per-level kernel (scan pieces or the double loop inline)
+            FALWA_KERNEL("fused_flux_layerwise_kernel", st);
+            if (use_scan) fused_flux_kernel<false><<<grid, block, 0, st>>>(p);
+            else fused_flux_kernel<true><<<grid, block, 0, st>>>(p);
+        } else if (use_scan) {
             if ((rc = hsum.alloc((size_t)batch * nhemi * nd * nlon, st))) return rc;
             FALWA_KERNEL("flux_column_kernel", st);
             flux_column_kernel<false><<<grid, block, 0, st>>>(p, hsum.d);
@@ -1249,7 +1268,150 @@ extern "C" int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* P, int bat
         FALWA_LAUNCH_CHECK();
     }
     { FALWA_KERNEL("baro_post_kernel", st); baro_post_kernel<<<dim3(ceil_div(P->nlon, 256), P->nlat, batch), 256, 0, st>>>(
-        P->nlon, P->nlat, P->a, P->dphi, P->dlambda, d + P->o_clat, out2d, use_scan ? hsum.d : nullptr, nhemi, nd, jb); }
+        P->nlon, P->nlat, P->a, P->dphi, P->dlambda, d + P->o_clat, out2d, (use_scan && !l3d) ? hsum.d : nullptr, nhemi, nd, jb); }
+    FALWA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* P, int batch, const double* qgpv,
+                                                    const double* u, const double* v, const double* theta,
+                                                    const double* ncforce, const double* profiles_host,
+                                                    const double* qref_cu, const double* uref_st,
+                                                    const double* ptref_st, int north_only, double* lwa,
+                                                    double* out2d, int method, void* stream) {
+    if (!P || !qgpv || !u || !v || !theta || !profiles_host || !qref_cu || !uref_st || !ptref_st || !lwa || !out2d)
+        return FALWA_ERR_NULL;
+    if (batch < 1) return FALWA_ERR_ARG;
+    return lwa_fluxes_impl(P, batch, qgpv, u, v, theta, ncforce, profiles_host, qref_cu, uref_st, ptref_st, north_only,
+                           lwa, out2d, method, nullptr, (cudaStream_t)stream);
+}
+
+namespace falwa {
+
+// f e^{z/H} d/dz [ e^{-z/H} g / (d theta~/dz) ]  (utilities.py:305-344: centred differences, one-sided at both ends;
+// hemispheric static stability, the equator row takes the average of the two).  One thread per (lon, lat) column.
+//   MODE 0: g = a field given on the pressure levels (interpolated like interpolate_fields) or on the height grid:
+//           the non-conservative forcing from a heating rate (oopinterface.py:985-1019), out = + the expression.
+//   MODE 1: g = v (theta - theta_ref) |cos(lat)|: the layer-wise stretching term (oopinterface.py:1021-1061),
+//           out = - the expression.
+struct ZDerivArgs {
+    int nlon, nlat, nlev, kmax, eq, interp;
+    const double *gin, *vv, *pt, *tref;       // MODE 0: gin [b][nlev or kmax][nlat][nlon]; MODE 1: v, theta, tref
+    const int* lo; const double *whi, *wlo;   // interpolation tables of the plan
+    const double *prof;                       // [b][4][kmax]: t0_s, t0_n, stat_s, stat_n
+    const double *dens, *mult, *clat;         // [kmax], [kmax][nlat], [nlat]
+    double dz;
+    double* out; size_t out_batch;            // out + b * out_batch: [kmax][nlat][nlon]
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+zderiv_kernel(ZDerivArgs a) {
+    const size_t plane = (size_t)a.nlon * a.nlat;
+    const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= plane) return;
+    const int b = blockIdx.y, g = (int)(col / a.nlon);
+    const double* ss = a.prof + ((size_t)b * 4 + 2) * a.kmax;
+    const double* sn = ss + a.kmax;
+    auto stab = [&](int k) { return g < a.eq - 1 ? ss[k] : (g == a.eq - 1 ? 0.5 * (ss[k] + sn[k]) : sn[k]); };
+    auto x_at = [&](int k) -> double {
+        double gv;
+        if (MODE == 0) {
+            const double* in = a.gin + (size_t)b * plane * (a.interp ? a.nlev : a.kmax);
+            if (a.interp) {
+                const int l = a.lo[k];
+                gv = a.whi[k] * in[(size_t)(l + 1) * plane + col] + a.wlo[k] * in[(size_t)l * plane + col];
+            } else gv = in[(size_t)k * plane + col];
+        } else {
+            const size_t o = (size_t)b * plane * a.kmax + (size_t)k * plane + col;
+            gv = a.vv[o] * (a.pt[o] - a.tref[((size_t)b * a.kmax + k) * a.nlat + g]) * a.clat[g];
+        }
+        return a.dens[k] * gv / stab(k);
+    };
+    double* out = a.out + (size_t)b * a.out_batch + col;
+    const double sgn = MODE == 1 ? -1.0 : 1.0;
+    const int kmax = a.kmax;
+    double xm = x_at(0), x0 = x_at(1);
+    out[0] = sgn * (a.mult[g] * (x0 - xm) / a.dz);
+    for (int k = 1; k < kmax - 1; ++k) {
+        const double xp = x_at(k + 1);
+        out[(size_t)k * plane] = sgn * ((xp - xm) / (2 * a.dz) * a.mult[(size_t)k * a.nlat + g]);
+        xm = x0; x0 = xp;
+    }
+    out[(size_t)(kmax - 1) * plane] = sgn * (a.mult[(size_t)(kmax - 1) * a.nlat + g] * (x0 - xm) / a.dz);
+}
+
+// host tables of zderiv_kernel: dens[kmax] = e^{-z/H}, mult[kmax][nlat] = 2 Omega sin(lat) e^{z/H}, then the profiles
+static int zderiv_tables(const falwa_plan* P, int batch, const double* profiles_host, DeviceTable& T, ZDerivArgs& a,
+                         cudaStream_t st) {
+    const int kmax = P->kmax, nlat = P->nlat;
+    std::vector<double> h((size_t)kmax + (size_t)kmax * nlat + (size_t)batch * 4 * kmax);
+    const std::vector<double>& sinlat = P->sinlat;
+    for (int k = 0; k < kmax; ++k) {
+        const double z = P->height[k];
+        h[k] = std::exp(-z / P->h);
+        const double ez = std::exp(z / P->h);
+        for (int j = 0; j < nlat; ++j) h[(size_t)kmax + (size_t)k * nlat + j] = 2 * P->omega * sinlat[j] * ez;
+    }
+    std::copy(profiles_host, profiles_host + (size_t)batch * 4 * kmax, h.begin() + kmax + (size_t)kmax * nlat);
+    int rc = T.upload(h, st);
+    if (rc) return rc;
+    a.nlon = P->nlon; a.nlat = nlat; a.nlev = P->nlev; a.kmax = kmax; a.eq = nlat / 2 + 1;
+    a.lo = P->d_lo; a.whi = P->d_tab + P->o_whi; a.wlo = P->d_tab + P->o_wlo; a.clat = P->d_tab + P->o_clat;
+    a.dens = T.d; a.mult = T.d + kmax; a.prof = T.d + kmax + (size_t)kmax * nlat; a.dz = P->dz;
+    return 0;
+}
+
+}  // namespace falwa
+
+// compute_layerwise_lwa_fluxes of a batch (oopinterface.py:1063-1156, :1021-1061).
+//   out3d [batch][10][kmax][nlat][nlon]: astar1, astar2, ncforce, ua1, ua2, ep1, ep2, ep3, stretch_term, lwa in the global
+//   frame (southern hemisphere: ep2 / ep3 swapped and negated, ncforce negated; the equator row is the southern value).
+//   The other arguments are those of falwa_b200_lwa_and_barotropic_fluxes.
+extern "C" int falwa_b200_layerwise_lwa_fluxes(const falwa_plan* P, int batch, const double* qgpv, const double* u,
+                                               const double* v, const double* theta, const double* ncforce,
+                                               const double* profiles_host, const double* qref_cu,
+                                               const double* uref_st, const double* ptref_st, int north_only,
+                                               double* out3d, int method, void* stream) {
+    if (!P || !qgpv || !u || !v || !theta || !profiles_host || !qref_cu || !uref_st || !ptref_st || !out3d)
+        return FALWA_ERR_NULL;
+    if (batch < 1) return FALWA_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t plane = (size_t)P->nlat * P->nlon, f3 = plane * P->kmax;
+    int rc;
+    DeviceScratch<double> lwa, out2d;
+    if ((rc = lwa.alloc((size_t)batch * f3, st))) return rc;
+    if ((rc = out2d.alloc((size_t)batch * O_COUNT * plane, st))) return rc;
+    FALWA_CUDA_TRY(cudaMemsetAsync(out3d, 0, sizeof(double) * (size_t)batch * L3_COUNT * f3, st));
+    if ((rc = lwa_fluxes_impl(P, batch, qgpv, u, v, theta, ncforce, profiles_host, qref_cu, uref_st, ptref_st,
+                              north_only, lwa.d, out2d.d, method, out3d, st))) return rc;
+    DeviceTable T;
+    ZDerivArgs a{};
+    if ((rc = zderiv_tables(P, batch, profiles_host, T, a, st))) return rc;
+    a.vv = v; a.pt = theta; a.tref = ptref_st;
+    a.out = out3d + (size_t)L_STRETCH * f3; a.out_batch = (size_t)L3_COUNT * f3;
+    { FALWA_KERNEL("zderiv_kernel", st); zderiv_kernel<1><<<dim3(ceil_div((long long)plane, 256), batch), 256, 0, st>>>(a); }
+    FALWA_LAUNCH_CHECK();
+    return 0;
+}
+
+// compute_ncforce_from_heating_rate of a batch (oopinterface.py:985-1019): heating_rate [batch][nlev][nlat][nlon] on the
+// pressure levels (on_height_grid = 0; interpolated like the fields) or [batch][kmax][nlat][nlon] on the height grid;
+// ncforce [batch][kmax][nlat][nlon].
+extern "C" int falwa_b200_ncforce_from_heating_rate(const falwa_plan* P, int batch, const double* heating_rate,
+                                                    int on_height_grid, const double* profiles_host, double* ncforce,
+                                                    void* stream) {
+    if (!P || !heating_rate || !profiles_host || !ncforce) return FALWA_ERR_NULL;
+    if (batch < 1) return FALWA_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t plane = (size_t)P->nlat * P->nlon;
+    DeviceTable T;
+    ZDerivArgs a{};
+    int rc;
+    if ((rc = zderiv_tables(P, batch, profiles_host, T, a, st))) return rc;
+    a.gin = heating_rate; a.interp = on_height_grid ? 0 : 1;
+    a.out = ncforce; a.out_batch = plane * P->kmax;
+    { FALWA_KERNEL("zderiv_kernel", st); zderiv_kernel<0><<<dim3(ceil_div((long long)plane, 256), batch), 256, 0, st>>>(a); }
     FALWA_LAUNCH_CHECK();
     return 0;
 }

@@ -29,6 +29,8 @@ OUT2D = {  # slot order of falwa_b200.h (enum FALWA_OUT2D_*)
     "convergence_zonal_advective_flux": 11, "divergence_eddy_momentum_flux": 12, "flux_vector_lambda_baro": 13,
     "flux_vector_phi_baro": 14}
 N_OUT2D = 15
+LAYER3D = {"astar1": 0, "astar2": 1, "ncforce": 2, "ua1": 3, "ua2": 4, "ep1": 5, "ep2": 6, "ep3": 7, "stretch_term": 8,
+           "lwa": 9}
 FUSE_ZONAL_STATS = False
 
 _registered = False
@@ -45,6 +47,8 @@ def _register():
     _lib.register("falwa_b200_reference_states", [c_dp, c_i] + [c_dp] * 5 + [c_i] + [c_dp] * 4 + [c_dp] * 4)
     _lib.register("falwa_b200_lwa_and_barotropic_fluxes",
                   [c_dp, c_i] + [c_dp] * 9 + [c_i, c_dp, c_dp, c_i, c_dp])
+    _lib.register("falwa_b200_layerwise_lwa_fluxes", [c_dp, c_i] + [c_dp] * 9 + [c_i, c_dp, c_i, c_dp])
+    _lib.register("falwa_b200_ncforce_from_heating_rate", [c_dp, c_i, c_dp, c_i, c_dp, c_dp, c_dp])
     _registered = True
 
 
@@ -203,15 +207,21 @@ class QGBatch:
             fit(b)
         return prof
 
-    def interpolate_fields(self):
-        p = self.plan
+    def compute_profiles(self):
+        """Static-stability profiles of the batch (the only host arithmetic of the path: the reference's spline)."""
+        if self.profiles is not None:
+            return
         prof = self.static_stability_profiles()
         self.profiles_hemi = np.ascontiguousarray(prof)   # t0_s, t0_n, stat_s, stat_n before any averaging
-        if p.kind == 0:  # NH18 uses the average of the two hemispheres everywhere (oopinterface.py:1567-1580)
+        if self.plan.kind == 0:  # NH18 uses the average of the two hemispheres everywhere (oopinterface.py:1567-1580)
             t0 = 0.5 * (prof[:, 0] + prof[:, 1])
             st = 0.5 * (prof[:, 2] + prof[:, 3])
             prof = np.stack([t0, t0, st, st], axis=1)
         self.profiles = np.ascontiguousarray(prof)
+
+    def interpolate_fields(self):
+        p = self.plan
+        self.compute_profiles()
         shape = (self.B, p.kmax, p.nlat, p.nlon)
         if self.on_height_grid:
             self.u, self.v = self.u_in, self.v_in
@@ -259,6 +269,36 @@ class QGBatch:
             p.handle, self.B, dptr(self.qgpv), dptr(self.u), dptr(self.v), dptr(self.theta), dptr(nc),
             hptr(self.profiles), dptr(self.qref_cu), dptr(self.uref), dptr(self.ptref), self.north_only,
             dptr(self.lwa), dptr(self.out2d), int(method), stream_ptr()), "lwa_and_barotropic_fluxes")
+
+    def compute_layerwise_lwa_fluxes(self, ncforce=None, method=0):
+        """Layer-wise flux terms of the batch (oopinterface.py:1063-1156): -> device tensor [B][10][kmax][nlat][nlon] in
+        the slot order of ``LAYER3D``."""
+        p = self.plan
+        if self.qref_cu is None:
+            raise ValueError("Reference states have not been computed yet.")
+        nc = None
+        if ncforce is not None:
+            nc = self._to_device(ncforce)
+            assert tuple(nc.shape) == tuple(self.theta.shape)
+        self.layer3d = self._new(self.B, len(LAYER3D), p.kmax, p.nlat, p.nlon)
+        check(self.lib.falwa_b200_layerwise_lwa_fluxes(
+            p.handle, self.B, dptr(self.qgpv), dptr(self.u), dptr(self.v), dptr(self.theta), dptr(nc),
+            hptr(self.profiles), dptr(self.qref_cu), dptr(self.uref), dptr(self.ptref), self.north_only,
+            dptr(self.layer3d), int(method), stream_ptr()), "layerwise_lwa_fluxes")
+        return self.layer3d
+
+    def ncforce_from_heating_rate(self, heating_rate):
+        """q-dot on the height grid from the heating rate on the input levels, [B][nlev][nlat][nlon] ->
+        [B][kmax][nlat][nlon] (oopinterface.py:985-1019)."""
+        p = self.plan
+        if self.profiles is None:
+            raise ValueError("QGField.interpolate_fields has to be called first.")
+        hr = self._to_device(heating_rate)
+        assert tuple(hr.shape) == tuple(self.t_in.shape), "heating_rate must have the shape of the input fields"
+        out = self._new(self.B, p.kmax, p.nlat, p.nlon)
+        check(self.lib.falwa_b200_ncforce_from_heating_rate(p.handle, self.B, dptr(hr), 0, hptr(self.profiles),
+                                                            dptr(out), stream_ptr()), "ncforce_from_heating_rate")
+        return out
 
     def out(self, name):
         """2-D output `name` as a [B][nlat][nlon] device view."""

@@ -21,19 +21,6 @@ from .constant import P_GROUND, SCALE_HEIGHT, CP, DRY_GAS_CONSTANT, EARTH_RADIUS
 from . import f90_modules
 
 
-def _z_derivative_of_prod(stat_n, stat_s, kmax, equator_idx, dz, density_decay, gfunc, multiplier):
-    """f e^{z/H} d/dz [e^{-z/H} g / static_stability] with hemispheric static stability (utilities.py:305-344)."""
-    stab = np.concatenate([np.ones((kmax, equator_idx - 1)) * stat_s[:, np.newaxis],
-                           np.ones((kmax, 1)) * 0.5 * (stat_s + stat_n)[:, np.newaxis],
-                           np.ones((kmax, equator_idx - 1)) * stat_n[:, np.newaxis]], axis=1)
-    x = density_decay[:, np.newaxis, np.newaxis] * gfunc / stab[:, :, np.newaxis]
-    z = np.zeros_like(x)
-    z[1:-1] = (x[2:] - x[:-2]) / (2 * dz) * multiplier[1:-1, :, np.newaxis]
-    z[0] = multiplier[0, :, np.newaxis] * (x[1] - x[0]) / dz
-    z[-1] = multiplier[-1, :, np.newaxis] * (x[-1] - x[-2]) / dz
-    return z
-
-
 class QGFieldBase(ABC):
     """Local wave activity and flux analysis in the quasi-geostrophic framework (abstract; instantiate
     ``QGFieldNH18`` or ``QGFieldNHN22``).  Parameters: see falwa.oopinterface.QGFieldBase (oopinterface.py:40-91)."""
@@ -268,64 +255,23 @@ class QGFieldBase(ABC):
     # ---- layer-wise (un-averaged) flux terms: the next step of the path (oopinterface.py:985-1156) ------------
     def compute_ncforce_from_heating_rate(self, heating_rate):
         """q-dot = f e^{z/H} d/dz (e^{-z/H} theta-dot / (d theta/dz)) on the height grid from the diabatic heating rate
-        on pressure levels, shape (nlev, nlat, nlon) (oopinterface.py:985-1019, utilities.py:305-344).  Input
-        preparation on the host, like the reference."""
+        on pressure levels, shape (nlev, nlat, nlon) (oopinterface.py:985-1019, utilities.py:305-344): vertical
+        interpolation and the z-derivative in one kernel (falwa_b200_ncforce_from_heating_rate)."""
         if self._batch.profiles is None:
             raise ValueError("QGField.interpolate_fields has to be called first.")
-        hr = interp1d(self._plev_to_height, np.asarray(heating_rate), axis=0, bounds_error=False, kind="linear",
-                      fill_value="extrapolate")(self.height)
-        p = self._batch.profiles[0]   # NH18 stores the hemispheric average in both slots (oopinterface.py:1567-1572)
-        mult = 2 * self.omega * np.sin(np.deg2rad(self._ylat[np.newaxis, :])) * np.exp(
-            self.height[:, np.newaxis] / self.scale_height)
-        return _z_derivative_of_prod(p[3], p[2], self.kmax, self.equator_idx, self.dz,
-                                     np.exp(-self.height / self.scale_height), hr, mult)
+        hr = np.ascontiguousarray(heating_rate, dtype=np.float64)
+        return self._batch.ncforce_from_heating_rate(hr[None])[0].cpu().numpy()
 
     def compute_layerwise_lwa_fluxes(self, ncforce=None, method=0):
         """Layer-wise LWA flux terms ua1, ua2, ep1, ep2, ep3, the stretching term and (optionally) ncforce, as 3-D
-        fields (oopinterface.py:1063-1156).  Runs the F2PY-compatible CUDA entry point per hemisphere on the
-        device-resident fields; ``lwa`` afterwards is astar1 + astar2 like the reference's layer-wise store."""
+        fields (oopinterface.py:1063-1156): one batched call (falwa_b200_layerwise_lwa_fluxes) on the device-resident
+        fields; ``lwa`` afterwards is astar1 + astar2 like the reference's layer-wise store."""
         b = self._batch
         if b.qref_cu is None or not self._reference_states_computed:
             raise ValueError("Reference states have not been computed yet.")
-        eq, jd, nlat = self.equator_idx, self._jd, self._nlat_analysis
-        pv, uu, vv, pt = b.qgpv[0], b.u[0], b.v[0], b.theta[0]
-        if ncforce is None:
-            nc = torch.zeros_like(pv)
-        else:
-            nc = torch.from_numpy(np.ascontiguousarray(ncforce, dtype=np.float64)).cuda()
-            assert tuple(nc.shape) == tuple(pv.shape)
-        qcu, ur, tr = b.qref_cu[0], b.uref[0], b.ptref[0]
-        prof = b.profiles[0]
-        kw = dict(jb=self._eq_boundary_index, is_nhem=True, a=self.planet_radius, om=self.omega, dz=self.dz,
-                  h=self.scale_height, rr=self.dry_gas_constant, cp=self.cp, prefac=self.prefactor, method=method)
-        names = ("astar1", "astar2", "ncforce", "ua1", "ua2", "ep1", "ep2", "ep3")
-        full = {n: np.zeros((self.nlon, nlat, self.kmax), order="F") for n in names}
-        outs = f90_modules.compute_flux_dirinv_nshem(
-            pv=pv.contiguous(), uu=uu.contiguous(), vv=vv.contiguous(), pt=pt.contiguous(), ncforce=nc.contiguous(),
-            tn0=prof[1], qref=qcu[:, -eq:].contiguous(), uref=ur[:, -jd:].contiguous(), tref=tr[:, -jd:].contiguous(),
-            **kw)
-        for n, a in zip(names, outs[:8]):
-            full[n][:, -eq:, :] = a
-        if not self.northern_hemisphere_results_only:   # oopinterface.py:1112-1148
-            outs = f90_modules.compute_flux_dirinv_nshem(
-                pv=(-pv.flip(1)).contiguous(), uu=uu.flip(1).contiguous(), vv=(-vv.flip(1)).contiguous(),
-                pt=pt.flip(1).contiguous(), ncforce=nc.flip(1).contiguous(), tn0=prof[0],
-                qref=(-qcu[:, :eq].flip(1)).contiguous(), uref=ur[:, :jd].flip(1).contiguous(),
-                tref=tr[:, :jd].flip(1).contiguous(), **kw)
-            a1, a2, ncs, ua1, ua2, ep1, ep3s, ep2s = outs[:8]      # ep2 / ep3 come back swapped ...
-            for n, a in (("astar1", a1), ("astar2", a2), ("ncforce", -ncs), ("ua1", ua1), ("ua2", ua2), ("ep1", ep1),
-                         ("ep2", -ep2s), ("ep3", -ep3s)):            # ... and negated, like ncforce
-                full[n][:, :eq, :] = a[:, ::-1, :]
-        full["lwa"] = full["astar1"] + full["astar2"]
-        # stretching term (layer-wise ep4): -f e^{z/H} d/dz(e^{-z/H} v (theta - theta_ref) cos(phi) / stat)
-        ph = b.profiles[0]
-        g = (vv * (pt - tr[:, :, None]) * torch.from_numpy(self._clat).to(vv.device)[None, :, None]).cpu().numpy()
-        mult = 2 * self.omega * np.sin(np.deg2rad(self._ylat[np.newaxis, :])) * np.exp(
-            self.height[:, np.newaxis] / self.scale_height)
-        inner = _z_derivative_of_prod(ph[3], ph[2], self.kmax, eq, self.dz, np.exp(-self.height / self.scale_height),
-                                      g, mult)
-        self._layerwise = {n: np.swapaxes(full[n], 0, 2) for n in ("lwa", "ua1", "ua2", "ep1", "ep2", "ep3", "ncforce")}
-        self._layerwise["stretch_term"] = -inner
+        nc = None if ncforce is None else np.ascontiguousarray(ncforce, dtype=np.float64)[None]
+        out = b.compute_layerwise_lwa_fluxes(ncforce=nc, method=method)[0].cpu().numpy()
+        self._layerwise = {n: out[i] for n, i in engine.LAYER3D.items() if n not in ("astar1", "astar2")}
         self._layerwise_fluxes_computed = True
 
     def _layer(self, name):

@@ -494,12 +494,26 @@ def _compute_lwa_only(self, return_dataset=True):
 
 
 def _compute_layerwise(self, ncforce=None, return_dataset=True):
-    """``compute_layerwise_lwa_fluxes`` of every field (xarrayinterface.py:587-630)."""
+    """``compute_layerwise_lwa_fluxes`` of every field (xarrayinterface.py:587-630).  Batched on the device (stages 1-2
+    are recomputed there, then falwa_b200_layerwise_lwa_fluxes per chunk) unless the inputs need the constructor's
+    latitude regridding."""
     nc = None
     if ncforce is not None:
         nc = np.asarray(getattr(ncforce, "data", ncforce))
         nc = nc.reshape((self._n,) + nc.shape[-3:])[self._lo:self._hi]
     names = ("lwa", "ua1", "ua2", "ep1", "ep2", "ep3", "stretch_term")
+    tpl = self._make_template() if self._hi > self._lo else None
+    if self._runner is None and tpl is not None and not tpl.need_latitude_interpolation:
+        nloc = self._hi - self._lo
+        runner = _DeviceRunner(tpl, self._chunk, layerwise=True)
+        for lo, hi, out in runner.run(self._u, self._v, self._t, ("interp", "ref", "layerwise"), list(names), nc):
+            for name, arr in out.items():
+                if name not in self._store or self._store[name].shape[0] != nloc:
+                    self._store[name] = np.empty((nloc,) + tuple(arr.shape[1:]), dtype=np.float64)
+                out.copy_into(name, self._store[name][lo:hi])
+        if return_dataset:
+            return self._dataset(names)
+        return None
 
     def call(i, f):
         f.compute_reference_states(return_named_tuple=False)
@@ -514,8 +528,26 @@ def _compute_ncforce(self, heating_rate):
     with the leading dimensions restored when the whole batch is local."""
     hr = np.asarray(getattr(heating_rate, "data", heating_rate))
     hr = hr.reshape((self._n,) + hr.shape[-3:])[self._lo:self._hi]
-    out = [f.compute_ncforce_from_heating_rate(hr[i]) for i, f in _per_field(self)]
-    arr = np.asarray(out)
+    tpl = self._make_template() if self._hi > self._lo else None
+    if self._runner is None and tpl is not None and not tpl.need_latitude_interpolation:
+        # device-batched: only the temperature is needed (static stability), then one kernel per chunk
+        import torch
+        from . import engine
+        nloc = self._hi - self._lo
+        chunk = self._chunk or _DeviceRunner(tpl).chunk
+        arr = np.empty((nloc, tpl.kmax) + hr.shape[-2:])
+        on_h = tpl._data_on_evenly_spaced_pseudoheight_grid
+        for lo in range(0, nloc, chunk):
+            hi = min(nloc, lo + chunk)
+            x = self._t[lo:hi]
+            raw = torch.from_numpy(np.ascontiguousarray(x.raw_native)).cuda()
+            t = engine.ingest_field(raw, x.packing, x.flip_lat, x.flip_lev, byteswap=x.byteswap) \
+                if engine.needs_ingest(raw.dtype, x.packing, x.flip_lat, x.flip_lev, x.byteswap) else raw
+            b = engine.QGBatch(tpl._plan, t, t, t, on_height_grid=on_h)
+            b.compute_profiles()
+            arr[lo:hi] = b.ncforce_from_heating_rate(np.ascontiguousarray(hr[lo:hi], dtype=np.float64)).cpu().numpy()
+    else:
+        arr = np.asarray([f.compute_ncforce_from_heating_rate(hr[i]) for i, f in _per_field(self)])
     return arr.reshape(self._other_shape + arr.shape[1:]) if arr.shape[0] == self._n else arr
 
 
@@ -530,7 +562,7 @@ class _DeviceRunner:
     two pinned staging slots: a few host threads fill / drain them (multi-threaded memcpy) while the GPU works on the
     neighbouring chunk, and the PCIe copies run on side streams."""
 
-    def __init__(self, template, chunk=None):
+    def __init__(self, template, chunk=None, layerwise=False):
         import torch
         from concurrent.futures import ThreadPoolExecutor
         from . import engine
@@ -539,7 +571,8 @@ class _DeviceRunner:
         self.plan = template._plan
         if chunk is None:
             # two input slots + decoded copies, and two batches in flight (stage 1-2 of one, stage 3 of the other)
-            per = 8 * self.plan.nlon * self.plan.nlat * (12 * self.plan.nlev + 20 * self.plan.kmax + 40)
+            per = 8 * self.plan.nlon * self.plan.nlat * (12 * self.plan.nlev + (40 if layerwise else 20) * self.plan.kmax
+                                                         + 40)
             free = torch.cuda.mem_get_info()[0]
             chunk = int(max(1, min(256, 0.4 * free // per)))
         self.chunk = chunk
@@ -603,6 +636,9 @@ class _DeviceRunner:
             slot = c & 1
             if "flux" in stages:
                 b.compute_lwa_and_barotropic_fluxes(ncforce=None if ncforce is None else ncforce[lo:hi])
+            layer = None
+            if "layerwise" in stages:
+                layer = b.compute_layerwise_lwa_fluxes(ncforce=None if ncforce is None else ncforce[lo:hi])
             done = torch.cuda.Event()
             done.record(main)
             for fu in drain[slot]:
@@ -614,12 +650,17 @@ class _DeviceRunner:
                 for name in want:
                     if name == "static_stability":
                         continue
-                    src = {"qgpv": b.qgpv, "interpolated_u": b.u, "interpolated_v": b.v, "interpolated_theta": b.theta,
-                           "qref": b.qref_cu, "uref": b.uref, "ptref": b.ptref, "lwa": b.lwa}.get(name)
-                    if src is None:
-                        src = b.out(name)
+                    if layer is not None:     # layer-wise store (its lwa is astar1 + astar2, oopinterface.py:1099-1100)
+                        src = layer[:, engine.LAYER3D[name]]
+                    else:
+                        src = {"qgpv": b.qgpv, "interpolated_u": b.u, "interpolated_v": b.v,
+                               "interpolated_theta": b.theta, "qref": b.qref_cu, "uref": b.uref, "ptref": b.ptref,
+                               "lwa": b.lwa}.get(name)
+                        if src is None:
+                            src = b.out(name)
                     if nh_only and name not in ("qgpv", "interpolated_u", "interpolated_v", "interpolated_theta"):
-                        src = src[..., -eq:, :] if name in engine.OUT2D or name == "lwa" else src[..., -eq:]
+                        src = src[..., -eq:, :] if name in engine.OUT2D or name == "lwa" or layer is not None \
+                            else src[..., -eq:]
                     src = src.contiguous()
                     src.record_stream(s_out)
                     buf = pin_out[slot].get(name)

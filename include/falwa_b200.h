@@ -197,6 +197,22 @@ int falwa_b200_lwa_and_barotropic_fluxes(const falwa_plan* plan, int batch, cons
                                          const double* uref_st, const double* ptref_st, int north_only,
                                          double* lwa, double* out2d, int method, void* stream);
 
+/* compute_layerwise_lwa_fluxes of a batch (oopinterface.py:1063-1156, stretching term :1021-1061; utilities.py:
+ * 305-344).  out3d [batch][10][kmax][nlat][nlon]: astar1, astar2, ncforce, ua1, ua2, ep1, ep2, ep3, stretch_term,
+ * lwa (= astar1 + astar2) in the global frame (southern hemisphere: ep2 / ep3 swapped and negated, ncforce negated; the equator row holds the
+ * southern value).  Other arguments as for falwa_b200_lwa_and_barotropic_fluxes. */
+int falwa_b200_layerwise_lwa_fluxes(const falwa_plan* plan, int batch, const double* qgpv, const double* u,
+                                    const double* v, const double* theta, const double* ncforce,
+                                    const double* profiles_host, const double* qref_cu, const double* uref_st,
+                                    const double* ptref_st, int north_only, double* out3d, int method, void* stream);
+
+/* compute_ncforce_from_heating_rate of a batch (oopinterface.py:985-1019): heating_rate [batch][nlev][nlat][nlon] on the
+ * pressure levels (interpolated like the fields) or, with on_height_grid != 0, [batch][kmax][nlat][nlon];
+ * ncforce [batch][kmax][nlat][nlon]. */
+int falwa_b200_ncforce_from_heating_rate(const falwa_plan* plan, int batch, const double* heating_rate,
+                                         int on_height_grid, const double* profiles_host, double* ncforce,
+                                         void* stream);
+
 /* ======================================================================================
  * Section C — 2-D (barotropic) path: BarotropicField.equivalent_latitudes / .lwa for a batch of fields
  * (replaces src/falwa/barotropic_field.py:104-125 -> basis.eqvlat_fawa(output_fawa=False), basis.lwa;

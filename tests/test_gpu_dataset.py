@@ -62,10 +62,22 @@ def test_dataset_layerwise_and_lwa_only():
     assert out["ua2"].shape == (2, 1, 49, 49, 96)
     f = QGFieldNHN22(*snaps[1])
     f.interpolate_fields(False); f.compute_reference_states(False); f.compute_layerwise_lwa_fluxes()
-    np.testing.assert_allclose(out["ep1"].data[1, 0], f.ep1, rtol=1e-9, atol=1e-10 * np.abs(f.ep1).max())  # histogram sums use atomics
-    hr = 1e-5 * np.ones((2, 1) + snaps[0][3].shape)
+    for name in ("lwa", "ua1", "ua2", "ep1", "ep2", "ep3", "stretch_term"):   # (histogram sums use atomics)
+        want = np.asarray(getattr(f, name))
+        np.testing.assert_allclose(out[name].data[1, 0], want, rtol=1e-9, atol=1e-10 * np.abs(want).max())
+    # heating rate -> ncforce (device-batched) -> layer-wise fluxes with the non-conservative term
+    hr = 1e-5 * np.random.default_rng(4).standard_normal((2, 1) + snaps[0][3].shape)
+    # (the reference hands heating_rate.sel(coord) to the field as it is — xarrayinterface.py:655-660 — so it is
+    # given in the field's orientation, unlike u, v, t)
     nc = q.compute_ncforce_from_heating_rate(hr)
     assert nc.shape == (2, 1, 49, 49, 96)
+    want = f.compute_ncforce_from_heating_rate(hr[1, 0])
+    np.testing.assert_allclose(nc[1, 0], want, rtol=1e-10, atol=1e-12 * np.abs(want).max())
+    out = q.compute_layerwise_lwa_fluxes(ncforce=nc)
+    f.compute_layerwise_lwa_fluxes(ncforce=want)
+    for name in ("lwa", "ua2", "ep3"):
+        w = np.asarray(getattr(f, name))
+        np.testing.assert_allclose(out[name].data[1, 0], w, rtol=1e-9, atol=1e-10 * np.abs(w).max())
     q18 = xi.QGDataset(ds, qgfield=QGFieldNH18, qgfield_kwargs=dict(maxit=5, raise_error_for_nonconvergence=False))
     lo = q18.compute_lwa_only()
     assert lo["lwa"].shape == (2, 1, 49, 49, 96) and np.isfinite(lo["lwa_baro"].data).all()
