@@ -850,9 +850,21 @@ extern "C" int falwa_b200_plan_create(falwa_plan** out, int kind, int nlon, int 
     }
     P->ntab = tab.size();
     cudaError_t e = cudaMalloc((void**)&P->d_tab, tab.size() * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&P->d_lo, kmax * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&P->d_lo, 3 * kmax * sizeof(int));
     if (e == cudaSuccess) e = cudaMemcpy(P->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(P->d_lo, lo.data(), kmax * sizeof(int), cudaMemcpyHostToDevice);
+    {   // prefetch schedule of the fused stage-1 kernel: after output level k, the next two input levels (in order of
+        // need) that are not part of bracket(k); -1 when there is none.  d_lo = lo[kmax], pf1[kmax], pf2[kmax].
+        lo.resize(3 * (size_t)kmax, -1);
+        for (int k = 0; k < kmax; ++k) {
+            int found = 0, F[2] = {-1, -1};
+            for (int k2 = k + 1; k2 < kmax && found < 2; ++k2)
+                for (int lev = lo[k2]; lev <= lo[k2] + 1 && found < 2; ++lev)
+                    if (lev != lo[k] && lev != lo[k] + 1 && lev != F[0]) F[found++] = lev;
+            lo[kmax + k] = F[0];
+            lo[2 * (size_t)kmax + k] = F[1];
+        }
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(P->d_lo, lo.data(), 3 * kmax * sizeof(int), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {  // keep stream-ordered scratch cached between calls
         int dev = 0;
         cudaMemPool_t pool;

@@ -429,10 +429,15 @@ theta_hemi_kernel(int nlat, int nlev, int jd, const double* __restrict__ rowmean
 // registers — its own u, v, theta plus u at (j+1), (j-1) and v at (i+1), (i-1), whose input levels the neighbouring
 // threads load as their own (L1/L2 hits) — evaluated with exactly the arithmetic of interp_kernel, so the stencil
 // sees bit-identical values to the unfused path.  QGPV of level k-1 is emitted at iteration k (it needs theta(k)).
-// The input levels of the next bracket are loaded one iteration ahead (register prefetch).
+// Input levels are prefetched into two tagged register slots following a host-built schedule (lo[kmax .. 3 kmax):
+// the next two levels, in order of need, that the current bracket does not hold), i.e. ~2.5 output levels ahead where
+// the pressure levels are sparse and a full bracket ahead near the ground where they are dense.  All tags are uniform
+// across the grid, so the slot bookkeeping is branch-uniform register renaming.  The four level records fit the 128
+// registers of 2 CTAs x 256 threads per SM without spills.
 // ---------------------------------------------------------------------------------------------
+constexpr int kStage1Rows = 8;
 template <int MODE>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(32 * kStage1Rows, 2)
 interp_qgpv_kernel(int nlon, int nlat, int nlev, int kmax, int jd, const double* __restrict__ uin,
                    const double* __restrict__ vin, const double* __restrict__ tin, const int* __restrict__ lo,
                    const double* __restrict__ whi, const double* __restrict__ wlo, const double* __restrict__ fac,
@@ -460,28 +465,33 @@ interp_qgpv_kernel(int nlon, int nlat, int nlev, int kmax, int jd, const double*
     auto load = [&](int l) -> Lev {
         Lev r;
         const size_t off = (size_t)l * plane;
-        r.u = ld_stream(&uin[off + col]); r.v = ld_stream(&vin[off + col]); r.t = ld_stream(&tin[off + col]) * fac[l];
+        // raw values only: any arithmetic here would make the warp wait for the load it has just issued
+        r.u = ld_stream(&uin[off + col]); r.v = ld_stream(&vin[off + col]); r.t = ld_stream(&tin[off + col]);
         r.up = uin[off + cup]; r.um = uin[off + cum]; r.vp = vin[off + cvp]; r.vm = vin[off + cvm];
         return r;
     };
-    int cur = lo[0];
+    const int* pf1 = lo + kmax;
+    const int* pf2 = lo + 2 * kmax;
+    int cur = lo[0], lp = -1, lq = -1;
     Lev L0 = load(cur), L1 = load(cur + 1);
-    Lev P = L1;              // prefetched level `pre`
-    int pre = -1;
+    Lev P = L1, Q = L1;      // prefetch slots holding levels lp, lq
     double am = 0.0, ac = 0.0, av_prev = 0.0;   // alt(k-2), alt(k-1), avort(k-1)
     for (int k = 0; k < kmax; ++k) {
         const int l = lo[k];
         if (l != cur) {      // advance the bracket (the tables only ever move upward)
-            if (l == cur + 1) { L0 = L1; L1 = (pre == l + 1) ? P : load(l + 1); }
-            else { L0 = (pre == l) ? P : load(l); L1 = load(l + 1); }
-            cur = l;
+            Lev n0, n1;
+            if (l == cur + 1) n0 = L1; else if (l == lp) n0 = P; else if (l == lq) n0 = Q; else n0 = load(l);
+            if (l + 1 == lp) n1 = P; else if (l + 1 == lq) n1 = Q; else n1 = load(l + 1);
+            L0 = n0; L1 = n1; cur = l;
         }
-        if (k + 1 < kmax) {  // issue the loads of the next bracket now; they land while this level is evaluated
-            const int ln = lo[k + 1];
-            if (ln != cur) { pre = (ln == cur + 1) ? ln + 1 : ln; P = load(pre); }
+        {   // keep the two slots filled with what the schedule asks for; the loads land while levels are evaluated
+            const int w1 = pf1[k], w2 = pf2[k];
+            if (w1 >= 0 && w1 != lp && w1 != lq) { if (lp != w2) { P = load(w1); lp = w1; } else { Q = load(w1); lq = w1; } }
+            if (w2 >= 0 && w2 != lp && w2 != lq) { if (lp != w1) { P = load(w2); lp = w2; } else { Q = load(w2); lq = w2; } }
         }
         const double a1 = whi[k], a0 = wlo[k];
-        const double u = a1 * L1.u + a0 * L0.u, v = a1 * L1.v + a0 * L0.v, th = a1 * L1.t + a0 * L0.t;
+        const double u = a1 * L1.u + a0 * L0.u, v = a1 * L1.v + a0 * L0.v;
+        const double th = a1 * (L1.t * fac[cur + 1]) + a0 * (L0.t * fac[cur]);   // T -> theta per input level first
         const size_t off = (size_t)k * plane;
         st_stream(&uo[off + col], u);
         st_stream(&vo[off + col], v);
@@ -515,7 +525,8 @@ int interp_qgpv_launch(int mode, int nlon, int nlat, int nlev, int kmax, int jd,
                        double* to, double* pv, double* avort, cudaStream_t st) {
     const QgpvTables tb = view_tables(d_tables, nlat, kmax);
     const size_t plane = (size_t)nlon * nlat;
-    dim3 block(32, 8), grid(ceil_div(nlon, 32), ceil_div(nlat, 8), batch);
+    const int bx = tune_int("FALWA_STAGE1_BX", 32), by = 32 * kStage1Rows / bx;
+    dim3 block(bx, by), grid(ceil_div(nlon, bx), ceil_div(nlat, by), batch);
     QgpvStats stt;
     stt.part = nullptr; stt.ext = nullptr; stt.nwx = 0;
     {
