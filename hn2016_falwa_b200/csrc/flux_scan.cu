@@ -348,15 +348,22 @@ lwa_scan_kernel(ScanArgs p) {
     double S1c = 0, S2c = 0, S1a = 0, S2a = 0, T3 = 0, T4 = 0, T5 = 0;
     double a2l[kScanRMax], u2l[kScanRMax], ncl[kScanRMax];
     const double ab = p.ab;
+    int jprev = 1, xcarry = 0;   // threshold row and bin end of the previous step (carried in registers)
 #pragma unroll
     for (int s = 0; s < kScanRMax; ++s) {
         a2l[s] = 0.0; u2l[s] = 0.0; ncl[s] = 0.0;
         const int t = lane * R + s;
         if (s < R && t < M) {
+            // everything that does not depend on the two loops is loaded first, so that its shared-memory latency
+            // overlaps with them (the compiler cannot hoist these loads above the loops' shared-memory stores)
             const int j = s_rowof[t];
+            const int jfirst = (s == 0) ? (t ? (int)s_rowof[t - 1] : 1) : jprev;
+            const int x0 = (s == 0) ? cn[t] : xcarry, xe = cn[t + 1];
+            const double Q = s_thr[t], ur = s_urt[t], cj = s_cos[j];
+            jprev = j; xcarry = xe;
             // rows entering at t: nxt(jj) == t  <=>  m_{t-1} <= jj < m_t  (a single row when Qref is monotone)
 #pragma unroll 1
-            for (int jj = t ? (int)s_rowof[t - 1] : 1; jj < j; ++jj) {
+            for (int jj = jfirst; jj < j; ++jj) {
                 const int e = E_[jj - 1];
                 if (e != t) {
                     const double q = q_[jj - 1], u = u_[jj - 1], cs = s_cos[jj];
@@ -366,7 +373,6 @@ lwa_scan_kernel(ScanArgs p) {
                 }
             }
             // rows leaving (cyclonic) / entering (anticyclonic) at t: E(jj) == t
-            const int x0 = cn[t], xe = cn[t + 1];
 #pragma unroll 1
             for (int a = x0 + 1; a < xe; ++a) {   // ascending row order inside the bin (insertion sort, bins are tiny)
                 const short v = pm[a];
@@ -384,7 +390,6 @@ lwa_scan_kernel(ScanArgs p) {
                 if (HAS_NC) T5 -= n_[r] * cs;
             }
             // a1 = ab (S1c - Q S2c),  a2 = ab (Q S2a - S1a),  ua2 = ab cos_j (T3 - Q T4) - uref_j (a1 + a2)
-            const double Q = s_thr[t], ur = s_urt[t], cj = s_cos[j];
             const double a1 = __fma_rn(-Q, S2c, S1c) * ab, a2 = __fma_rn(Q, S2a, -S1a) * ab;
             o_[j - 1] = a1;
             a2l[s] = a2;
