@@ -120,16 +120,26 @@ area_hist3_kernel(int nlon, int nlat, int kmax, int nb, const double* __restrict
             // 16-byte vector loads, eight points (four double2 per field) in flight per lane: the lanes of a warp
             // read different rows, so every access is its own sector and memory-level parallelism has to come
             // from the thread itself
-            for (; i + 8 <= i1; i += 8) {
-                double2 a[4], c[4];
+            // software-pipelined: the next eight points are requested before the current eight are binned
+            double2 a[4], c[4], na[4], nc[4];
+            auto fetch8 = [&](int at, double2* A, double2* C) {
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
-                    a[v] = __ldg(reinterpret_cast<const double2*>(pv + row + i) + v);
-                    if (WITH_V) c[v] = __ldg(reinterpret_cast<const double2*>(avort + row + i) + v);
-                    else c[v] = make_double2(0., 0.);
+                    A[v] = __ldg(reinterpret_cast<const double2*>(pv + row + at) + v);
+                    if (WITH_V) C[v] = __ldg(reinterpret_cast<const double2*>(avort + row + at) + v);
+                    else C[v] = make_double2(0., 0.);
                 }
+            };
+            if (i + 8 <= i1) fetch8(i, a, c);
+            for (; i + 8 <= i1; i += 8) {
+                const bool more = (i + 16 <= i1);
+                if (more) fetch8(i + 8, na, nc);
 #pragma unroll
                 for (int v = 0; v < 4; ++v) { point(a[v].x, c[v].x); point(a[v].y, c[v].y); }
+                if (more) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) { a[v] = na[v]; c[v] = nc[v]; }
+                }
             }
         }
         for (; i < i1; ++i) point(pv[row + i], WITH_V ? avort[row + i] : 0.0);
