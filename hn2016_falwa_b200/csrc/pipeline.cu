@@ -999,11 +999,11 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
     }
     FALWA_LAUNCH_CHECK();
     {
-        int slabs = std::max(1, std::min(nlat, (148 * tune_int("FALWA_HIST_CTAS", 8) + (kmax - 3)) / (kmax - 2) / std::max(1, std::min(batch, 4))));
+        int slabs = std::max(1, std::min(nlat, (148 * tune_int("FALWA_HIST_CTAS", 12) + (kmax - 3)) / (kmax - 2) / std::max(1, std::min(batch, 4))));
         const int rows = ceil_div(nlat, slabs);
         slabs = ceil_div(nlat, rows);
         const size_t smem = sizeof(double) * 4 * 2 * nb;
-        const int hrun = tune_int("FALWA_HIST_RUN", 32);
+        const int hrun = tune_int("FALWA_HIST_RUN", 64);
         dim3 hgrid(slabs, kmax - 2, batch);
         FALWA_KERNEL("area_hist3_kernel", st);
         if (P->kind == 0) {  // NH18: pv histogram with circulation sums (SOR boundary condition), no vorticity histogram
