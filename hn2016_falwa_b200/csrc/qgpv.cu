@@ -395,14 +395,30 @@ interp_kernel(int nlon, int nlat, int nlev, int kmax, const double* __restrict__
 __global__ void __launch_bounds__(256)
 theta_rowmean_kernel(int nlon, int nlat, int nlev, const double* __restrict__ tin, const double* __restrict__ fac,
                      const double* __restrict__ clat, double* __restrict__ rowmean, size_t in_stride) {
-    __shared__ double red[33];
-    const int j = blockIdx.x, l = blockIdx.y, b = blockIdx.z;
+    // one warp per latitude row (8 rows per CTA), 16-byte loads, four independent partial sums per lane so that
+    // several loads are in flight; the order of the additions is fixed (lane-strided, then the shuffle tree)
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5), l = blockIdx.y, b = blockIdx.z, lane = threadIdx.x & 31;
+    if (j >= nlat) return;
     const double* row = tin + (size_t)b * in_stride + ((size_t)l * nlat + j) * nlon;
     const double f = fac[l], c = clat[j];
-    double s = 0.0;
-    for (int i = threadIdx.x; i < nlon; i += blockDim.x) s += (ld_stream(&row[i]) * f) * c;
-    s = block_sum(s, red);
-    if (threadIdx.x == 0) rowmean[((size_t)b * nlev + l) * nlat + j] = s / (double)nlon;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if ((nlon & 1) == 0 && ((uintptr_t)row & 15) == 0) {
+        const double2* r2 = reinterpret_cast<const double2*>(row);
+        const int n2 = nlon >> 1;
+        int i = lane;
+        for (; i + 96 < n2; i += 128) {
+            const double2 a = __ldcs(r2 + i), bq = __ldcs(r2 + i + 32), cq = __ldcs(r2 + i + 64), d = __ldcs(r2 + i + 96);
+            s0 += (a.x * f) * c + (a.y * f) * c;
+            s1 += (bq.x * f) * c + (bq.y * f) * c;
+            s2 += (cq.x * f) * c + (cq.y * f) * c;
+            s3 += (d.x * f) * c + (d.y * f) * c;
+        }
+        for (; i < n2; i += 32) { const double2 a = __ldcs(r2 + i); s0 += (a.x * f) * c + (a.y * f) * c; }
+    } else {
+        for (int i = lane; i < nlon; i += 32) s0 += (ld_stream(&row[i]) * f) * c;
+    }
+    const double s = warp_sum((s0 + s1) + (s2 + s3));
+    if (lane == 0) rowmean[((size_t)b * nlev + l) * nlat + j] = s / (double)nlon;
 }
 
 __global__ void __launch_bounds__(128)
@@ -560,7 +576,7 @@ int interp_launch(int nlon, int nlat, int nlev, int kmax, int batch, const doubl
 
 int theta_means_launch(int nlon, int nlat, int nlev, int jd, int batch, const double* tin, const double* fac,
                        const double* clat, double* rowmean, double* out, cudaStream_t st) {
-    { FALWA_KERNEL("theta_rowmean_kernel", st); theta_rowmean_kernel<<<dim3(nlat, nlev, batch), 256, 0, st>>>(nlon, nlat, nlev, tin, fac, clat, rowmean,
+    { FALWA_KERNEL("theta_rowmean_kernel", st); theta_rowmean_kernel<<<dim3(ceil_div(nlat, 8), nlev, batch), 256, 0, st>>>(nlon, nlat, nlev, tin, fac, clat, rowmean,
                                                                   (size_t)nlon * nlat * nlev); }
     FALWA_LAUNCH_CHECK();
     { FALWA_KERNEL("theta_hemi_kernel", st); theta_hemi_kernel<<<dim3(nlev, 2, batch), 128, 0, st>>>(nlat, nlev, jd, rowmean, clat, out); }
