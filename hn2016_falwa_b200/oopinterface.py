@@ -150,7 +150,7 @@ class QGFieldBase(ABC):
     def _host(self, key, tensor):
         """device tensor of batch 1 -> cached NumPy array"""
         if key not in self._cache:
-            self._cache[key] = tensor[0].cpu().numpy()
+            self._cache[key] = engine.to_host(tensor[0])
         return self._cache[key]
 
     def _nh_slice(self, a, lat_axis):
