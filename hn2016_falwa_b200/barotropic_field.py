@@ -6,7 +6,7 @@ from math import pi
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, engine
 from ._lib import check, dptr, hptr, stream_ptr
 
 
@@ -87,9 +87,9 @@ class BarotropicField:
     @property
     def equivalent_latitudes(self):
         """Q(y) at the input latitudes, (nlat,)."""
-        return self._b.equivalent_latitudes[0].cpu().numpy()
+        return engine.to_host(self._b.equivalent_latitudes[0])
 
     @property
     def lwa(self):
         """Local wave activity, (nlat, nlon) (or (2, nlat, nlon) when partitioned)."""
-        return self._b.lwa[0].cpu().numpy()
+        return engine.to_host(self._b.lwa[0])

@@ -260,7 +260,7 @@ class QGFieldBase(ABC):
         if self._batch.profiles is None:
             raise ValueError("QGField.interpolate_fields has to be called first.")
         hr = np.ascontiguousarray(heating_rate, dtype=np.float64)
-        return self._batch.ncforce_from_heating_rate(hr[None])[0].cpu().numpy()
+        return engine.to_host(self._batch.ncforce_from_heating_rate(hr[None])[0])
 
     def compute_layerwise_lwa_fluxes(self, ncforce=None, method=0):
         """Layer-wise LWA flux terms ua1, ua2, ep1, ep2, ep3, the stretching term and (optionally) ncforce, as 3-D
@@ -270,7 +270,7 @@ class QGFieldBase(ABC):
         if b.qref_cu is None or not self._reference_states_computed:
             raise ValueError("Reference states have not been computed yet.")
         nc = None if ncforce is None else np.ascontiguousarray(ncforce, dtype=np.float64)[None]
-        out = b.compute_layerwise_lwa_fluxes(ncforce=nc, method=method)[0].cpu().numpy()
+        out = engine.to_host(b.compute_layerwise_lwa_fluxes(ncforce=nc, method=method)[0])
         self._layerwise = {n: out[i] for n, i in engine.LAYER3D.items() if n not in ("astar1", "astar2")}
         self._layerwise_fluxes_computed = True
 
