@@ -154,3 +154,21 @@ def test_netcdf3_file_through_dataset_and_back(tmp_path):
         assert f.variables["lwa"].dimensions == ("time", "height", "ylat", "xlon")
         np.testing.assert_array_equal(f.variables["lwa_baro"][:], np.asarray(out["lwa_baro"].data, dtype=np.float32))
         assert f.protocol == b"QGFieldNHN22"
+
+
+def test_example_workflow_script(tmp_path):
+    """examples/lwa_budget_nhn22.py: three packed NetCDF-3 files in, one result file out."""
+    import importlib.util
+    import os
+    from scipy.io import netcdf_file
+    from tests.test_netcdf_io import write_packed_era_file
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("lwa_budget_nhn22", os.path.join(root, "examples", "lwa_budget_nhn22.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    paths = [write_packed_era_file(str(tmp_path / f"{n}.nc"), names=n, nt=3) for n in "uvt"]
+    out = str(tmp_path / "budget.nc")
+    mod.main(*paths, out)
+    with netcdf_file(out, "r", mmap=False) as f:
+        assert f.variables["lwa_baro"][:].shape == (3, 121, 240) and f.variables["qref"][:].shape == (3, 49, 121)
+        assert np.isfinite(f.variables["lwa_baro"][:]).all() and f.variables["lwa_baro"][:].max() > 1.0
