@@ -13,7 +13,6 @@ from collections import namedtuple
 from typing import NamedTuple, Optional
 
 import numpy as np
-import torch
 from scipy.interpolate import interp1d
 
 from . import engine

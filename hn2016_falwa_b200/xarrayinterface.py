@@ -11,7 +11,6 @@ xarray is optional (it is absent from the build image).  With xarray installed t
 return ``xarray`` objects exactly like the reference; without it the same classes accept / return ``SimpleDataArray``
 / ``SimpleDataset`` (dims + coords + NumPy data), which is also what the tests use.
 """
-import itertools
 from collections import OrderedDict
 
 import numpy as np
