@@ -18,8 +18,9 @@
 //
 // Kernel layout: one CTA per (snapshot, hemisphere, level, tile of 8 longitudes); the tile is staged through shared
 // memory with coalesced 64-byte row segments and transposed so that each warp owns one column with lanes over rows.
-// The scatter is a deterministic per-warp counting sort on int16 keys (__match_any_sync resolves duplicates, so no
-// shared-memory atomics: fp64 ATOMS is a CAS loop at 2 cycles/lane); rows whose E equals nxt (not displaced across a
+// The scatter is a per-warp counting sort on int16 keys: the slot inside a bin comes from a native 32-bit shared-memory
+// atomic and the few bins that hold more than one row are insertion-sorted, so every floating-point sum runs in a
+// fixed order (no fp64 atomics anywhere: fp64 ATOMS is a CAS loop); rows whose E equals nxt (not displaced across a
 // Qref contour) contribute nothing and are skipped.  Each lane then owns R consecutive thresholds, accumulates the
 // six running sums sequentially, and a single warp scan of the lane totals supplies the offsets (the outputs are
 // linear in the sums).  Results are staged back through the same shared memory and written with coalesced stores.
