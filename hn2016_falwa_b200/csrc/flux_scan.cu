@@ -362,9 +362,44 @@ lwa_scan_kernel(ScanArgs p) {
             const int x0 = (s == 0) ? cn[t] : xcarry, xe = cn[t + 1];
             const double Q = s_thr[t], ur = s_urt[t], cj = s_cos[j];
             jprev = j; xcarry = xe;
-            // rows entering at t: nxt(jj) == t  <=>  m_{t-1} <= jj < m_t  (a single row when Qref is monotone)
+            // Common case: ONE row enters at t (nxt(jj) == t  <=>  m_{t-1} <= jj < m_t; a single row when Qref is
+            // monotone) and at most ONE displaced row sits in bin t.  Their operands are fetched up front and applied
+            // with predicated straight-line code, so a step is two dependent rounds of shared-memory loads instead of
+            // six; the rare extra rows follow in rolled loops.  Adding 0.0 for the inactive cases keeps every sum
+            // bit-identical to the plain loops (same terms, same order).
+            const bool ent = jfirst < j;
+            const int ei = ent ? jfirst : j;                       // any valid row when nothing enters
+            const int e1 = E_[ei - 1];
+            const double qe = q_[ei - 1], ue = u_[ei - 1], ce = s_cos[ei];
+            double ne = 0.0;
+            if (HAS_NC) ne = n_[ei - 1];
+            const bool binr = x0 < xe;
+            int r0 = binr ? (int)pm[x0] : 0;
+            if (__builtin_expect(xe - x0 >= 2, 0)) {               // ascending row order inside the bin (rare)
 #pragma unroll 1
-            for (int jj = jfirst; jj < j; ++jj) {
+                for (int a = x0 + 1; a < xe; ++a) {
+                    const short v = pm[a];
+                    int c = a - 1;
+#pragma unroll 1
+                    for (; c >= x0 && pm[c] > v; --c) pm[c + 1] = pm[c];
+                    pm[c + 1] = v;
+                }
+                r0 = pm[x0];
+            }
+            const double qb = q_[r0], ub = u_[r0], cb = s_cos[r0 + 1];
+            const int nb0 = s_nxt[r0 + 1];
+            double nbv = 0.0;
+            if (HAS_NC) nbv = n_[r0];
+            {   // first entering row
+                const bool cyc = ent && (e1 > t), anti = ent && (e1 < t), d = cyc || anti;
+                const double qc = qe * ce, qu = qe * ue;
+                S1c += cyc ? qc : 0.0; S2c += cyc ? ce : 0.0;
+                S1a -= anti ? qc : 0.0; S2a -= anti ? ce : 0.0;
+                T3 += d ? qu : 0.0; T4 += d ? ue : 0.0;
+                if (HAS_NC) T5 += d ? ne * ce : 0.0;
+            }
+#pragma unroll 1
+            for (int jj = jfirst + 1; jj < j; ++jj) {              // further entering rows (exception rows, t = 0)
                 const int e = E_[jj - 1];
                 if (e != t) {
                     const double q = q_[jj - 1], u = u_[jj - 1], cs = s_cos[jj];
@@ -373,17 +408,16 @@ lwa_scan_kernel(ScanArgs p) {
                     if (HAS_NC) T5 += n_[jj - 1] * cs;
                 }
             }
-            // rows leaving (cyclonic) / entering (anticyclonic) at t: E(jj) == t
-#pragma unroll 1
-            for (int a = x0 + 1; a < xe; ++a) {   // ascending row order inside the bin (insertion sort, bins are tiny)
-                const short v = pm[a];
-                int c = a - 1;
-#pragma unroll 1
-                for (; c >= x0 && pm[c] > v; --c) pm[c + 1] = pm[c];
-                pm[c + 1] = v;
+            {   // first row leaving (cyclonic) / entering (anticyclonic) at t: E(jj) == t
+                const bool cyc = binr && (t > nb0), anti = binr && !(t > nb0);
+                const double qc = qb * cb, qu = qb * ub;
+                S1c -= cyc ? qc : 0.0; S2c -= cyc ? cb : 0.0;
+                S1a += anti ? qc : 0.0; S2a += anti ? cb : 0.0;
+                T3 -= binr ? qu : 0.0; T4 -= binr ? ub : 0.0;
+                if (HAS_NC) T5 -= binr ? nbv * cb : 0.0;
             }
 #pragma unroll 1
-            for (int x = x0; x < xe; ++x) {
+            for (int x = x0 + 1; x < xe; ++x) {
                 const int r = pm[x];
                 const double q = q_[r], u = u_[r], cs = s_cos[r + 1];
                 if (t > s_nxt[r + 1]) { S1c -= q * cs; S2c -= cs; } else { S1a += q * cs; S2a += cs; }
