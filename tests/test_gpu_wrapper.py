@@ -100,3 +100,15 @@ def test_errors():
         basis.eqvlat_fawa(Y[:-1], PV, AREA, NLAT)
     with pytest.raises(ValueError):
         basis.eqvlat_fawa(Y, PV, AREA, 1)
+
+
+def test_even_latitude_count_and_explicit_hemisphere_size():
+    from hn2016_falwa_b200 import basis, wrapper
+    y, pv, area, dmu, th = (G["even_" + k] for k in ("ylat", "pv", "area", "dmu", "theta"))
+    q, l = wrapper.qgpv_eqlat_lwa(y, pv, area, dmu)
+    close(q, G["even_qgpv_qref"]); close(l, G["even_qgpv_lwa"], 1e-9)
+    q, l = wrapper.theta_lwa(y, th, area, dmu, nlat_s=20, n_points=25)
+    close(q, G["even_theta_qref"]); close(l, G["even_theta_lwa"], 1e-9)
+    assert np.all(l[20:28] == 0.0)
+    q, f = basis.eqvlat_fawa(y, pv, area, 48)
+    close(q, G["even_fawa_qref"]); close(f, G["even_fawa"], 1e-9)
