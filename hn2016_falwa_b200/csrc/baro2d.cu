@@ -31,39 +31,92 @@ baro_minmax_kernel(int npts, const double* __restrict__ vort, unsigned long long
 
 // area per vorticity bin: inds = np.digitize(vort, bins) in 1..n-1 are kept (basis.py:47-48)
 // WEIGHTED: a second histogram of area * w (w = the field itself for basis.eqvlat_fawa's cq, basis.py:49-50; the
-// Laplacian-type field of basis.eqvlat_vgrad, basis.py:119-120) into hist[B][n .. 2n)
+// Laplacian-type field of basis.eqvlat_vgrad, basis.py:119-120) into the slots [n .. 2n).
+//
+// Bit-reproducible: no floating-point atomics.  Every warp owns a contiguous range of grid points and a private
+// shared-memory histogram; the lanes of a 32-point batch that fall into the same bin are combined by the lowest such
+// lane in lane order (__match_any_sync + shuffles), the warp histograms are added in warp order into a per-CTA
+// partial, and baro_hist_combine_kernel adds the partials in CTA order.  The reference's own test relies on
+// eqvlat_vgrad giving identical Q(y) with and without vgrad (tests/test_basis.py:41-58).
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(256)
 baro_hist_kernel(int nlon, int nlat, int n, const double* __restrict__ vort, const double* __restrict__ area,
                  const double* __restrict__ wfield, const unsigned long long* __restrict__ ext,
-                 double* __restrict__ hist /* [B][n] or [B][2n] */) {
-    extern __shared__ double sh[];  // [n] or [2n]
-    const int b = blockIdx.y;
+                 double* __restrict__ partial /* [B][gridDim.x][NH * n] */) {
+    extern __shared__ double sh[];  // [warps][NH * n]
+    constexpr int NH = WEIGHTED ? 2 : 1;
+    const unsigned FULL = 0xffffffffu;
+    const int b = blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const size_t npts = (size_t)nlon * nlat;
     const double* v = vort + (size_t)b * npts;
     const double* wf = WEIGHTED ? wfield + (size_t)b * npts : nullptr;
-    constexpr int NH = WEIGHTED ? 2 : 1;
-    for (int t = threadIdx.x; t < NH * n; t += blockDim.x) sh[t] = 0.0;
+    for (int t = threadIdx.x; t < nw * NH * n; t += blockDim.x) sh[t] = 0.0;
     __syncthreads();
+    double* hw = sh + (size_t)w * NH * n;
     const double vmax = ordered_to_f64(ext[b * 2 + 0]), vmin = ordered_to_f64(ext[b * 2 + 1]);
     const double step = (vmax - vmin) / (double)(n - 1);
     const double rstep = 1. / step;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < npts; t += (size_t)gridDim.x * blockDim.x) {
-        const double x = v[t];
-        // searchsorted(bins, x, side='right'): number of bins <= x.  Guess from the uniform spacing, then settle
-        // against the exact numpy bin edges.
-        int idx = min(max(__double2int_rz((x - vmin) * rstep) + 1, 0), n);
-        while (idx > 0 && linspace_at(vmin, vmax, step, n, idx - 1) > x) --idx;
-        while (idx < n && linspace_at(vmin, vmax, step, n, idx) <= x) ++idx;
-        if (idx >= 1 && idx <= n - 1) {
-            const double a = area[t];
-            atomicAdd(&sh[idx], a);
-            if (WEIGHTED) atomicAdd(&sh[n + idx], a * wf[t]);
+    const size_t nwarps = (size_t)gridDim.x * nw, gw = (size_t)blockIdx.x * nw + w;
+    const size_t chunk = ((npts + nwarps - 1) / nwarps + 31) / 32 * 32;
+    const size_t t0 = gw * chunk, t1 = (t0 + chunk < npts) ? t0 + chunk : npts;
+    for (size_t base = t0; base < t1; base += 32) {
+        const size_t t = base + lane;
+        int idx = 0;
+        double a = 0.0, wa = 0.0;
+        if (t < t1) {
+            const double x = v[t];
+            // searchsorted(bins, x, side='right'): number of bins <= x.  Guess from the uniform spacing, then
+            // settle against the exact numpy bin edges.
+            idx = min(max(__double2int_rz((x - vmin) * rstep) + 1, 0), n);
+            while (idx > 0 && linspace_at(vmin, vmax, step, n, idx - 1) > x) --idx;
+            while (idx < n && linspace_at(vmin, vmax, step, n, idx) <= x) ++idx;
         }
+        const bool keep = (idx >= 1 && idx <= n - 1);
+        if (keep) {
+            a = area[t];
+            if (WEIGHTED) wa = a * wf[t];
+        }
+        const unsigned m = __match_any_sync(FULL, keep ? idx : n + lane);   // dropped points group with nobody
+        const int cnt = __popc(m), leader = __ffs(m) - 1;
+        const int maxc = __reduce_max_sync(FULL, cnt);
+        double sa = a, sw = wa;
+        if (maxc == 32) {        // (uniform) the whole batch lies in one bin: fixed shuffle tree
+            sa = warp_sum(a);
+            if (WEIGHTED) sw = warp_sum(wa);
+        } else if (maxc > 1) {   // (uniform) add the members of every group in lane order
+            sa = 0.0; sw = 0.0;
+            for (int k = 0; k < maxc; ++k) {
+                const unsigned f = __fns(m, 0, k + 1);
+                const int src = (f < 32u) ? (int)f : lane;
+                const double av = __shfl_sync(FULL, a, src);
+                double wv = 0.0;
+                if (WEIGHTED) wv = __shfl_sync(FULL, wa, src);
+                if (k < cnt) { sa += av; sw += wv; }
+            }
+        }
+        if (keep && lane == leader) {
+            hw[idx] += sa;
+            if (WEIGHTED) hw[n + idx] += sw;
+        }
+        __syncwarp();
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < NH * n; t += blockDim.x)
-        if (sh[t] != 0.0) atomicAdd(&hist[(size_t)b * NH * n + t], sh[t]);
+    double* out = partial + ((size_t)b * gridDim.x + blockIdx.x) * NH * n;
+    for (int t = threadIdx.x; t < NH * n; t += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < nw; ++q) s += sh[(size_t)q * NH * n + t];
+        out[t] = s;
+    }
+}
+
+// hist[b][i] = sum of the CTA partials in CTA order
+__global__ void __launch_bounds__(256)
+baro_hist_combine_kernel(int nslot, int nblk, const double* __restrict__ partial, double* __restrict__ hist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (i >= nslot) return;
+    double s = 0.0;
+    for (int c = 0; c < nblk; ++c) s += partial[((size_t)b * nblk + c) * nslot + i];
+    hist[(size_t)b * nslot + i] = s;
 }
 
 // zonal mean of the field and zonal sum of the area per row (basis.py:39, :58-59); one warp per row
@@ -220,10 +273,14 @@ static int eqvlat_2d_launch(int mode, int batch, int nlon, int nlat, int n_point
     if ((rc = hist.alloc((size_t)batch * nh * n_points, st, true))) return rc;
     if ((rc = rows.alloc((size_t)(batch + 1) * nlat, st, true))) return rc;
     { FALWA_KERNEL("init_ext_kernel", st); init_ext_kernel<<<ceil_div(batch * 2, 128), 128, 0, st>>>(ext.d, batch * 2); }
-    const int nblk = std::max(1, std::min(ceil_div(npts, 256 * 8), 148 * 8 / std::max(1, std::min(batch, 148 * 8))));
+    const int nblk = std::max(1, std::min(ceil_div(npts, 256 * 8), std::max(8, 148 * 8 / std::max(1, batch))));
     { FALWA_KERNEL("baro_minmax_kernel", st); baro_minmax_kernel<<<dim3(nblk, batch), 256, 0, st>>>(npts, vort, ext.d); }
     FALWA_LAUNCH_CHECK();
-    const size_t smem_h = sizeof(double) * nh * n_points;
+    // warps per CTA of the histogram kernel: as many private histograms as fit into shared memory
+    int hwarps = 8;
+    while (hwarps > 1 && sizeof(double) * hwarps * nh * n_points > 200 * 1024) hwarps >>= 1;
+    const size_t smem_h = sizeof(double) * hwarps * nh * n_points;
+    if (smem_h > 220 * 1024) return FALWA_ERR_UNSUPPORTED;
     const size_t smem_q = sizeof(double) * (2 * (size_t)n_points + nlat);
     if (smem_h > 48 * 1024) {
         FALWA_CUDA_TRY(cudaFuncSetAttribute(baro_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_h));
@@ -231,11 +288,15 @@ static int eqvlat_2d_launch(int mode, int batch, int nlon, int nlat, int n_point
     }
     if (smem_q > 48 * 1024)
         FALWA_CUDA_TRY(cudaFuncSetAttribute(baro_qref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
+    DeviceScratch<double> partial;
+    if ((rc = partial.alloc((size_t)batch * nblk * nh * n_points, st))) return rc;
     {
         FALWA_KERNEL("baro_hist_kernel", st);
-        if (aux) baro_hist_kernel<true><<<dim3(nblk, batch), 256, smem_h, st>>>(nlon, nlat, n_points, vort, area, wfield, ext.d, hist.d);
-        else baro_hist_kernel<false><<<dim3(nblk, batch), 256, smem_h, st>>>(nlon, nlat, n_points, vort, area, nullptr, ext.d, hist.d);
+        if (aux) baro_hist_kernel<true><<<dim3(nblk, batch), 32 * hwarps, smem_h, st>>>(nlon, nlat, n_points, vort, area, wfield, ext.d, partial.d);
+        else baro_hist_kernel<false><<<dim3(nblk, batch), 32 * hwarps, smem_h, st>>>(nlon, nlat, n_points, vort, area, nullptr, ext.d, partial.d);
     }
+    FALWA_LAUNCH_CHECK();
+    { FALWA_KERNEL("baro_hist_combine_kernel", st); baro_hist_combine_kernel<<<dim3(ceil_div(nh * n_points, 256), batch), 256, 0, st>>>(nh * n_points, nblk, partial.d, hist.d); }
     FALWA_LAUNCH_CHECK();
     if (aux && mode == 0) {
         FALWA_KERNEL("baro_rowstats_kernel", st);

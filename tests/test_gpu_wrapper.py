@@ -112,3 +112,36 @@ def test_even_latitude_count_and_explicit_hemisphere_size():
     assert np.all(l[20:28] == 0.0)
     q, f = basis.eqvlat_fawa(y, pv, area, 48)
     close(q, G["even_fawa_qref"]); close(f, G["even_fawa"], 1e-9)
+
+
+def test_reference_basis_tests_on_the_gpu():
+    """The reference's own tests/test_basis.py, run against hn2016_falwa_b200.basis: LWA of a zonally symmetric field
+    is exactly zero; eqvlat_vgrad gives a non-decreasing Q(y) that is IDENTICAL with and without vgrad (which needs
+    the area histogram to be bit-reproducible from launch to launch)."""
+    from math import pi
+    from hn2016_falwa_b200 import basis
+    from hn2016_falwa_b200.constant import EARTH_RADIUS
+    test_vort = (np.ones((5, 5)) * np.array([1, 2, 3, 4, 5])).swapaxes(0, 1)
+    res, _ = basis.lwa(5, 5, test_vort, np.array([1, 2, 3, 4, 5]), np.ones(5))
+    assert np.array_equal(res, np.zeros((5, 5)))
+    nlat, nlon, planet_radius = 241, 480, 1.
+    ylat = np.linspace(-90, 90, nlat, endpoint=True)
+    xlon = np.linspace(0, 360, nlon, endpoint=False)
+    vort = np.sin(3. * np.deg2rad(xlon[np.newaxis, :])) * np.cos(np.deg2rad(ylat[:, np.newaxis]))
+    dummy_vgrad = 3. / (planet_radius * np.cos(np.deg2rad(ylat[:, np.newaxis]))) \
+        * np.cos(np.deg2rad(3. * xlon[np.newaxis, :])) * np.cos(np.deg2rad(ylat[:, np.newaxis])) \
+        - 1. / planet_radius * np.sin(np.deg2rad(ylat[:, np.newaxis])) * np.sin(np.deg2rad(3. * xlon[np.newaxis, :]))
+    dphi = np.deg2rad(np.diff(ylat)[0])
+    area = 2. * pi * planet_radius ** 2 * (np.cos(np.deg2rad(ylat[:, np.newaxis])) * dphi) / float(nlon) \
+        * np.ones((nlat, nlon))
+    q1, vg = basis.eqvlat_vgrad(ylat, vort, area, nlat, planet_radius=EARTH_RADIUS, vgrad=dummy_vgrad)
+    q2, none = basis.eqvlat_vgrad(ylat, vort, area, nlat, planet_radius=EARTH_RADIUS, vgrad=None)
+    assert np.all(np.diff(q1) >= 0.)
+    assert q1.tolist() == q2.tolist()
+    assert none is None and vg is not None and vg.shape == q1.shape
+    qo, vo = basis2d.eqvlat_vgrad(ylat, vort, area, nlat, planet_radius=EARTH_RADIUS, vgrad=dummy_vgrad)
+    close(q1, qo); close(vg, vo, 1e-9)
+    # launch-to-launch reproducibility of the whole 2-D path
+    a = basis.eqvlat_fawa(ylat, vort, area, nlat, planet_radius=EARTH_RADIUS)
+    b = basis.eqvlat_fawa(ylat, vort, area, nlat, planet_radius=EARTH_RADIUS)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
