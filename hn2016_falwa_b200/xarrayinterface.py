@@ -268,6 +268,13 @@ class QGDataset:
         assert tuple(da_u.dims) == tuple(da_v.dims), "dimensions of fields u and v don't match"
         assert tuple(da_u.dims) == tuple(da_t.dims), "dimensions of fields u and t don't match"
         coords = {k: np.asarray(getattr(c, "values", c)) for k, c in da_u.coords.items()}
+        # the reference merges the three arrays with join="exact" (xarrayinterface.py:358): coordinates must agree
+        for other in (da_v, da_t):
+            for k, c in other.coords.items():
+                if k in coords and k in da_u.dims:
+                    c = np.asarray(getattr(c, "values", c))
+                    if c.shape != coords[k].shape or not np.array_equal(c, coords[k]):
+                        raise ValueError(f"coordinate '{k}' of the u, v, t fields differs (an exact match is required)")
         fields, packing = [], []
         for da in (da_u, da_v, da_t):
             a, pk = np.asarray(da.data), _packing_of(da)
