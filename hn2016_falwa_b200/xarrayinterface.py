@@ -604,14 +604,15 @@ class _DeviceRunner:
         u, v, t = (x.raw_native for x in lazy)
         tdt = [torch.from_numpy(np.empty(0, dtype=x.dtype)).dtype for x in (u, v, t)]
         ingest = [engine.needs_ingest(dt, x.packing, x.flip_lat, x.flip_lev, x.byteswap) for dt, x in zip(tdt, lazy)]
-        shape_in = (self.chunk,) + tuple(u.shape[1:])
+        chunk = max(1, min(self.chunk, n))       # never stage more snapshots than there are
+        shape_in = (chunk,) + tuple(u.shape[1:])
         pin_in = [[torch.empty(shape_in, dtype=dt).pin_memory() for dt in tdt] for _ in range(2)]
         dev_in = [[torch.empty(shape_in, dtype=dt, device="cuda") for dt in tdt] for _ in range(2)]
         ev_in = [torch.cuda.Event() for _ in range(2)]
         ev_free = [torch.cuda.Event() for _ in range(2)]
         for e in ev_free:
             e.record(main)
-        bounds = [(lo, min(n, lo + self.chunk)) for lo in range(0, n, self.chunk)]
+        bounds = [(lo, min(n, lo + chunk)) for lo in range(0, n, chunk)]
 
         def stage(c):   # host threads: pageable user arrays -> pinned slot
             lo, hi = bounds[c]
@@ -671,7 +672,7 @@ class _DeviceRunner:
                     src.record_stream(s_out)
                     buf = pin_out[slot].get(name)
                     if buf is None or buf.shape[1:] != src.shape[1:]:
-                        buf = pin_out[slot][name] = torch.empty((self.chunk,) + tuple(src.shape[1:]),
+                        buf = pin_out[slot][name] = torch.empty((chunk,) + tuple(src.shape[1:]),
                                                                 dtype=src.dtype).pin_memory()
                     buf[:hi - lo].copy_(src, non_blocking=True)
                     host[name] = buf[:hi - lo]

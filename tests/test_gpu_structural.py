@@ -66,3 +66,37 @@ def test_flux_vector_identity_and_divergence_consistency(kind):
     assert np.abs(f.flux_vector_phi_baro).sum() > 0 and np.abs(emf).sum() > 0
     np.testing.assert_allclose(d[60 + eqb:-pole], emf[60 + eqb:-pole], atol=1e-5)
     np.testing.assert_allclose(d[pole:61 - eqb], emf[pole:61 - eqb], atol=1e-5)
+
+
+@pytest.mark.parametrize("nh_only", [False, True])
+@pytest.mark.parametrize("kind", ["nh18", "nhn22"])
+def test_basic_qgdataset_calls(kind, nh_only):
+    """tests/test_xarrayinterface.py:108-143, :216-275 of the reference: a dataset without leading dimensions, every
+    compute method, datasets agree with the accessors, layer-wise and flux-vector variables with the right dims."""
+    from hn2016_falwa_b200 import xarrayinterface as xi
+    dims = ("plev", "ylat", "xlon")
+    coords = dict(plev=PLEV, ylat=YLAT, xlon=XLON)
+    ds = xi.SimpleDataset({n: xi.SimpleDataArray(a, dims, coords, name=n) for n, a in zip("uvt", (U, V, T))})
+    q = xi.QGDataset(ds, qgfield=_cls(kind), qgfield_kwargs={"northern_hemisphere_results_only": nh_only})
+    out1 = q.interpolate_fields()
+    for name in ("qgpv", "interpolated_u", "interpolated_v", "interpolated_theta"):
+        np.testing.assert_allclose(out1[name].data, getattr(q, name).data)
+    assert "static_stability" in out1 or ("static_stability_n" in out1 and "static_stability_s" in out1)
+    out2 = q.compute_reference_states()
+    for name in ("qref", "uref", "ptref"):
+        np.testing.assert_allclose(out2[name].data, getattr(q, name).data)
+    out3 = q.compute_lwa_and_barotropic_fluxes()
+    for name in ("adv_flux_f1", "adv_flux_f2", "adv_flux_f3", "convergence_zonal_advective_flux",
+                 "divergence_eddy_momentum_flux", "meridional_heat_flux", "lwa_baro", "u_baro", "lwa",
+                 "flux_vector_lambda_baro", "flux_vector_phi_baro"):
+        np.testing.assert_allclose(out3[name].data, getattr(q, name).data)
+    nrow = NLAT // 2 + 1 if nh_only else NLAT
+    assert out3["flux_vector_lambda_baro"].dims == ("ylat", "xlon") and out3["lwa_baro"].shape == (nrow, NLON)
+    layer = q.compute_layerwise_lwa_fluxes()
+    for name in ("lwa", "ua1", "ua2", "ep1", "ep2", "ep3", "stretch_term"):
+        assert name in layer and layer[name].dims == ("height", "ylat", "xlon")
+        assert layer[name].shape == (KMAX, nrow, NLON) and np.isfinite(layer[name].data).all()
+    out4 = q.compute_lwa_only()
+    for name in ("lwa_baro", "u_baro", "lwa"):
+        np.testing.assert_allclose(out4[name].data, getattr(q, name).data)
+    assert out4["lwa_baro"].shape == (nrow, NLON)
