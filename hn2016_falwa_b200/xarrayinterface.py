@@ -581,6 +581,9 @@ class _DeviceRunner:
                                                          + 40)
             free = torch.cuda.mem_get_info()[0]
             chunk = int(max(1, min(256, 0.4 * free // per)))
+            # ... and at most ~8 GB of page-locked input staging (two slots x three fields)
+            stage = 2 * 3 * 8 * self.plan.nlon * self.plan.nlat * self.plan.nlev
+            chunk = int(max(1, min(chunk, 8e9 // stage)))
         self.chunk = chunk
         self.pool = ThreadPoolExecutor(max_workers=6)
 
