@@ -391,12 +391,15 @@ lwa_scan_kernel(ScanArgs p) {
             double nbv = 0.0;
             if (HAS_NC) nbv = n_[r0];
             {   // first entering row
-                const bool cyc = ent && (e1 > t), anti = ent && (e1 < t), d = cyc || anti;
+                // class weights 1.0 / 0.0 and one fused multiply-add per sum: fma(1, x, S) == S + x and
+                // fma(0, x, S) == S exactly, at a third of the instructions of select + add on 64-bit values
+                const bool cyc = ent && (e1 > t), anti = ent && (e1 < t);
+                const double wc = cyc ? 1.0 : 0.0, wa = anti ? -1.0 : 0.0, wd = (cyc || anti) ? 1.0 : 0.0;
                 const double qc = qe * ce, qu = qe * ue;
-                S1c += cyc ? qc : 0.0; S2c += cyc ? ce : 0.0;
-                S1a -= anti ? qc : 0.0; S2a -= anti ? ce : 0.0;
-                T3 += d ? qu : 0.0; T4 += d ? ue : 0.0;
-                if (HAS_NC) T5 += d ? ne * ce : 0.0;
+                S1c = __fma_rn(wc, qc, S1c); S2c = __fma_rn(wc, ce, S2c);
+                S1a = __fma_rn(wa, qc, S1a); S2a = __fma_rn(wa, ce, S2a);
+                T3 = __fma_rn(wd, qu, T3); T4 = __fma_rn(wd, ue, T4);
+                if (HAS_NC) T5 = __fma_rn(wd, ne * ce, T5);
             }
 #pragma unroll 1
             for (int jj = jfirst + 1; jj < j; ++jj) {              // further entering rows (exception rows, t = 0)
@@ -410,11 +413,12 @@ lwa_scan_kernel(ScanArgs p) {
             }
             {   // first row leaving (cyclonic) / entering (anticyclonic) at t: E(jj) == t
                 const bool cyc = binr && (t > nb0), anti = binr && !(t > nb0);
+                const double wc = cyc ? -1.0 : 0.0, wa = anti ? 1.0 : 0.0, wd = binr ? -1.0 : 0.0;
                 const double qc = qb * cb, qu = qb * ub;
-                S1c -= cyc ? qc : 0.0; S2c -= cyc ? cb : 0.0;
-                S1a += anti ? qc : 0.0; S2a += anti ? cb : 0.0;
-                T3 -= binr ? qu : 0.0; T4 -= binr ? ub : 0.0;
-                if (HAS_NC) T5 -= binr ? nbv * cb : 0.0;
+                S1c = __fma_rn(wc, qc, S1c); S2c = __fma_rn(wc, cb, S2c);
+                S1a = __fma_rn(wa, qc, S1a); S2a = __fma_rn(wa, cb, S2a);
+                T3 = __fma_rn(wd, qu, T3); T4 = __fma_rn(wd, ub, T4);
+                if (HAS_NC) T5 = __fma_rn(wd, nbv * cb, T5);
             }
 #pragma unroll 1
             for (int x = x0 + 1; x < xe; ++x) {
