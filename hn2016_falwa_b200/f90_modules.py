@@ -18,6 +18,9 @@ import torch
 from . import _lib
 from ._lib import check, dptr, hptr, stream_ptr
 
+# LWA methods of compute_flux_dirinv_nshem / compute_lwa_only_nhn22: 0 = default, 1 = the reference's double loop
+LWA_METHODS = (0, 1)
+
 
 def _dev(x, ndim):
     """numpy (Fortran index order, any strides) or CUDA tensor -> contiguous CUDA tensor in memory order."""
