@@ -223,9 +223,25 @@ extern "C" int falwa_b200_compute_flux_dirinv_nshem(
     const int nrows = p.jend - p.jstart + 1;
     dim3 block(32, 8);
     dim3 grid(ceil_div(imax, 32), ceil_div(nrows, 8), kmax - 2);
-    const bool use_scan = (method != 1) && is_nhem && scan_supported(nd);
+    // method: 0 = automatic (windowed sums, else interval scan, else the double loop), 1 = double loop,
+    //         2 = interval scan, 3 = windowed sums
+    const bool use_window = (method == 0 || method == 3) && is_nhem && win_supported(imax, nd, pv, uu, ncforce);
+    const bool use_scan = !use_window && (method != 1) && is_nhem && scan_supported(nd);
     ScanTables tabs;
-    if (use_scan) {  // astar1, astar2, ua2, ncforce3d by the interval scan, the pointwise terms afterwards
+    if (use_window) {  // astar1, astar2, ua2, ncforce3d by exact windowed sums (lwa_window.cu), the pointwise terms afterwards
+        WinArgs w{};
+        w.imax = imax; w.nd = nd; w.kmax = kmax; w.jstart = p.jstart; w.jend = p.jend; w.nhemi = 1;
+        w.k_first = 2; w.k_count = kmax - 2;
+        w.fr[0].in_row0 = p.joff; w.fr[0].out_row0 = 0; w.fr[0].rev = 0; w.fr[0].skip_first = 0; w.fr[0].sg = 1.0;
+        w.qref = qref; w.q_batch = 0; w.q_kstride = nd; w.q_row0[0] = 0; w.q_rstep[0] = 1; w.q_sg[0] = 1.0;
+        w.uref = uref; w.u_batch = 0; w.u_kstride = jd; w.u_row0[0] = -p.uoff; w.u_rstep[0] = 1;
+        w.cosphi = p.cosphi; w.ab = p.ab;
+        w.a1 = astar1; w.a2 = astar2; w.u2 = ua2; w.ncf = ncforce3d;
+        w.out_batch = 0; w.out_plane = (size_t)nd * imax; w.out_pitch = imax;
+        w.mask_count = p.mask_count;
+        if ((rc = lwa_window_launch(w, 0, pv, uu, ncforce, jmax, 1, 1, st))) return rc;
+        { FALWA_KERNEL("flux_pointwise_kernel", st); flux_bruteforce_kernel<false><<<grid, block, 0, st>>>(p); }
+    } else if (use_scan) {  // astar1, astar2, ua2, ncforce3d by the interval scan, the pointwise terms afterwards
         if ((rc = tabs.alloc(1, nd, kmax, st))) return rc;
         ThrArgs t{};
         ScanArgs s{};
@@ -287,7 +303,19 @@ extern "C" int falwa_b200_compute_lwa_only_nhn22(const double* pv, const double*
     dim3 block(32, 8);
     dim3 grid(ceil_div(imax, 32), ceil_div(nrows, 8), kmax - 2);
     ScanTables tabs;
-    if ((method != 1) && is_nhem && scan_supported(nd)) {
+    if ((method == 0 || method == 3) && is_nhem && win_supported(imax, nd, pv, uu, nullptr)) {
+        WinArgs w{};
+        w.imax = imax; w.nd = nd; w.kmax = kmax; w.jstart = p.jstart; w.jend = p.jend; w.nhemi = 1;
+        w.k_first = 2; w.k_count = kmax - 2;
+        w.fr[0].in_row0 = p.joff; w.fr[0].out_row0 = 0; w.fr[0].rev = 0; w.fr[0].skip_first = 0; w.fr[0].sg = 1.0;
+        w.qref = qref; w.q_batch = 0; w.q_kstride = nd; w.q_row0[0] = 0; w.q_rstep[0] = 1; w.q_sg[0] = 1.0;
+        w.uref = nullptr;
+        w.cosphi = p.cosphi; w.ab = p.ab;
+        w.a1 = astar1; w.a2 = astar2; w.u2 = nullptr; w.ncf = nullptr;
+        w.out_batch = 0; w.out_plane = (size_t)nd * imax; w.out_pitch = imax;
+        w.mask_count = nullptr;
+        if ((rc = lwa_window_launch(w, 0, pv, uu, nullptr, jmax, 1, 1, st))) return rc;
+    } else if ((method != 1) && is_nhem && scan_supported(nd)) {
         if ((rc = tabs.alloc(1, nd, kmax, st))) return rc;
         ThrArgs t{};
         ScanArgs s{};

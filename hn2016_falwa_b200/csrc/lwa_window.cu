@@ -1,0 +1,480 @@
+// Local wave activity by exact windowed sums: the B200-native replacement of the reference's O(nd^2) (j, jj) double
+// loop (compute_flux_dirinv.f90:70-116, compute_lwa_only_nhn22.f90:55-90) on the hot path.
+//
+// For one column (fixed longitude and level) with PV values q_jj (jj = 1..nd, equator -> pole, hemispheric frame) and
+// thresholds Q_j, the reference accumulates for every row j
+//     cyclonic      { jj <  j : q_jj >  Q_j }      astar1 += (q_jj - Q_j) a dphi cos(phi_jj)
+//     anticyclonic  { jj >= j : q_jj <= Q_j }      astar2 -= (q_jj - Q_j) a dphi cos(phi_jj)
+// and ua2 / ncforce3d over the same two sets.  In the atmosphere a PV contour is displaced by a few rows only, so the
+// two sets of row j live in a short window around j.  The window is found EXACTLY, per threshold, from two monotone
+// bound arrays of the column: PE(x) = max q over rows < x and PP(x) = min q over rows >= x.  Going equatorward from
+// j-1, no row at or beyond x can be in the cyclonic set once PE(x+1) <= Q_j; going poleward from j, none once
+// PP(x) > Q_j.  Inside the window every (j, jj) pair is evaluated with the reference's own predicate and term
+// ((q - Q) > 0, (q - Q) * aa), so set membership is exact and no sort, search or atomic is involved; a column whose
+// contours are displaced far costs proportionally more steps (worst case the reference's full loop), never a wrong
+// answer.  The bounds are carried as the upper 32 bits of the order-preserving integer image of the doubles
+// (conservative by construction: q > Q implies key(q) >= key(Q)), so building them is integer min/max work.
+//
+// Layout: one CTA = (snapshot, hemisphere, 8 longitudes) x all nd rows, walking the levels of its range.  The
+// (rows x 8) tiles of q and u (and ncforce) of a level arrive by TMA (cp.async.bulk.tensor, one elected thread, mbarrier
+// completion) straight in the layout the math uses — a warp works on 4 rows x 8 longitudes = 256 contiguous bytes of
+// shared memory — two levels in flight, so the tile of level k+1 lands while level k is computed.  In the
+// accumulating mode (compute_lwa_and_barotropic_fluxes) the density-weighted vertical sums of astar1, astar2, ua1, ua2
+// (oopinterface.py:405-420) stay in registers across the level walk and only |astar1 + astar2| — the user-visible 3-D
+// LWA — is written per level: the a1 / a2 / ua2 intermediates of the interval-scan path never exist.
+#include "common.cuh"
+#include <cuda.h>
+#include <climits>
+
+namespace falwa {
+
+constexpr int kWinCols = 8;                                       // longitudes per tile: 64-byte row segments
+constexpr int kWinWarps = 16;
+constexpr int kWinThreads = kWinWarps * 32;
+constexpr int kWinGroupsPerWarp = 6;                              // 4-row groups a warp owns (register accumulators)
+constexpr int kWinMaxRows = 4 * kWinWarps * kWinGroupsPerWarp;    // 384 hemispheric rows (0.25 deg: 361)
+constexpr int kWinSpan = 13;                                      // rows per lane in the bound scans (odd stride)
+constexpr int kWinKeyPitch = 420;                                 // >= 32 * 13 + 2 and == 4 (mod 32): conflict-free
+
+struct WinFrame {
+    int in_row0, out_row0;   // memory row of tile row 0 in the inputs / outputs
+    int rev;                 // tile row m holds hemispheric row jj = rev ? nd - m : m + 1
+    int skip_first;          // do not write hemispheric row 1 (the other hemisphere's launch owns the equator)
+    double sg;               // sign of pv in the hemispheric frame
+};
+
+struct WinArgs {
+    int imax, nd, kmax, jstart, jend, nhemi;
+    int nbox, boxrows;                      // TMA boxes per tile, rows per box (even; nbox * boxrows >= nd)
+    int k_first, k_count, k_per_cta;        // 1-based first level, number of levels, levels per CTA (grid.y chunks)
+    WinFrame fr[2];
+    const double* qref; size_t q_batch; int q_kstride; int q_row0[2], q_rstep[2]; double q_sg[2];
+    const double* uref; size_t u_batch; int u_kstride; int u_row0[2], u_rstep[2];   // uref may be null (-> 0)
+    const double* cosphi;                   // [nd+2], index jj
+    double ab;                              // a * dphi
+    // MODE 0: the 3-D pieces per level (u2 / ncf may be null)
+    double *a1, *a2, *u2, *ncf; size_t out_batch, out_plane; int out_pitch;
+    // MODE 1: |a1 + a2| per level and the vertical sums, global frame
+    double *lwa, *out2d; const double* vw; double dc; size_t lwa_batch, lwa_plane, o2_batch, o2_plane;
+    int slot_a1, slot_a2, slot_lwa, slot_ua1, slot_ua2, slot_ncf;
+    unsigned long long* mask_count;         // optional: [0] anticyclonic pairs, [1] cyclonic pairs
+};
+
+__device__ __forceinline__ uint32_t win_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void win_mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(win_smem(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void win_mbar_expect(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(win_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void win_mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok = 0;
+    const uint32_t a = win_smem(bar);
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void win_tma_load(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(win_smem(dst)), "l"(map), "r"(win_smem(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// upper half of the order-preserving integer image of a double (NaN sorts outside the numbers; harmless, see above)
+__device__ __forceinline__ int win_key(double x) {
+    const int hi = __double2hiint(x);
+    return hi ^ ((hi >> 31) & 0x7fffffff);
+}
+
+struct WinSmem {
+    size_t tile_doubles;     // doubles of one (rows x 8) tile
+    size_t off_aa, off_keys, off_pe, off_pp, off_q, off_u, off_cs, off_bar, total;
+};
+__host__ __device__ inline WinSmem win_smem_layout(int nd, int nbox, int boxrows, int nfields) {
+    WinSmem s;
+    s.tile_doubles = (size_t)nbox * boxrows * kWinCols;
+    size_t o = (size_t)2 * nfields * s.tile_doubles * 8;
+    s.off_aa = o; o += s.tile_doubles * 8;
+    s.off_keys = o; o += (size_t)kWinCols * kWinKeyPitch * 4;
+    s.off_pe = o; o += (size_t)kWinCols * kWinKeyPitch * 4;
+    s.off_pp = o; o += (size_t)kWinCols * kWinKeyPitch * 4;
+    s.off_q = o; o += (size_t)2 * nd * 8;
+    s.off_u = o; o += (size_t)2 * nd * 8;
+    s.off_cs = o; o += (size_t)nd * 8;
+    s.off_bar = o; o += 16;
+    s.total = o;
+    return s;
+}
+
+template <int MODE, bool HAS_NC, bool COUNT>
+__global__ void __launch_bounds__(kWinThreads, 1)
+lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_u,
+                  const __grid_constant__ CUtensorMap tm_n, const WinArgs p) {
+    extern __shared__ __align__(1024) unsigned char win_raw[];
+    constexpr int NF = HAS_NC ? 3 : 2;
+    constexpr int P = kWinKeyPitch;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int nd = p.nd;
+    const WinSmem L = win_smem_layout(nd, p.nbox, p.boxrows, NF);
+    const int TD = (int)L.tile_doubles;
+    double* tiles = reinterpret_cast<double*>(win_raw);                 // [stage][field][rows][8]
+    double* aa8 = reinterpret_cast<double*>(win_raw + L.off_aa);        // [rows][8]: a dphi cos(phi) of the tile row
+    int* keys = reinterpret_cast<int*>(win_raw + L.off_keys);           // [8][P], hemispheric row index
+    int* PE = reinterpret_cast<int*>(win_raw + L.off_pe);               // [8][P]: PE[x] = max key of rows < x
+    int* PP = reinterpret_cast<int*>(win_raw + L.off_pp);               // [8][P]: PP[x] = min key of rows >= x
+    double* Qh = reinterpret_cast<double*>(win_raw + L.off_q);          // [2][nd] thresholds of a level
+    double* Ur = reinterpret_cast<double*>(win_raw + L.off_u);          // [2][nd] uref of a level
+    double* abcs = reinterpret_cast<double*>(win_raw + L.off_cs);       // [nd] a dphi cos(phi_j)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(win_raw + L.off_bar);  // [2] "tile of this stage has landed"
+
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int c = lane & 7, r = lane >> 3;
+    const int prob = blockIdx.z, b = prob / p.nhemi, h = prob % p.nhemi;
+    const WinFrame fr = p.fr[h];
+    const int i0 = blockIdx.x * kWinCols;
+    const bool colok = (i0 + c) < p.imax;
+    const int kbeg = p.k_first + blockIdx.y * p.k_per_cta;
+    const int kend = min(kbeg + p.k_per_cta, p.k_first + p.k_count);    // exclusive
+    const int nlev = kend - kbeg;
+    if (nlev <= 0) return;
+    const int G = (nd + 3) >> 2;
+    const unsigned tile_bytes = (unsigned)(TD * 8);
+
+    auto issue = [&](int li) {   // one elected thread: all boxes of level kbeg + li into stage li & 1
+        const int s = li & 1, k = kbeg + li;
+        win_mbar_expect(&bars[s], tile_bytes * NF);
+        for (int bx = 0; bx < p.nbox; ++bx) {
+            const int row = fr.in_row0 + bx * p.boxrows;
+            double* dst = tiles + (size_t)(s * NF) * TD + (size_t)bx * p.boxrows * kWinCols;
+            win_tma_load(dst, &tm_q, &bars[s], i0, row, k - 1, b);
+            win_tma_load(dst + TD, &tm_u, &bars[s], i0, row, k - 1, b);
+            if (HAS_NC) win_tma_load(dst + 2 * TD, &tm_n, &bars[s], i0, row, k - 1, b);
+        }
+    };
+    auto table_fetch = [&](int k, int j0, double& Q, double& U) {   // thresholds of hemispheric row j0 + 1 at level k
+        Q = 0.0; U = 0.0;
+        if (j0 < nd && j0 + 1 >= p.jstart && j0 + 1 <= p.jend) {
+            Q = __fma_rn(p.q_sg[h], p.qref[(size_t)b * p.q_batch + (size_t)(k - 1) * p.q_kstride + p.q_row0[h] + p.q_rstep[h] * j0], 0.0);
+            if (p.uref) U = p.uref[(size_t)b * p.u_batch + (size_t)(k - 1) * p.u_kstride + p.u_row0[h] + p.u_rstep[h] * j0];
+        }
+    };
+
+    if (tid == 0) {
+        win_mbar_init(&bars[0], 1);
+        win_mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        issue(0);
+        if (nlev > 1) issue(1);
+    }
+    for (int m = tid; m < p.nbox * p.boxrows; m += kWinThreads) {
+        const int jj = fr.rev ? nd - m : m + 1;
+        const double v = (m < nd) ? p.ab * p.cosphi[jj] : 0.0;
+#pragma unroll
+        for (int cc = 0; cc < kWinCols; ++cc) aa8[m * kWinCols + cc] = v;
+    }
+    for (int j0 = tid; j0 < nd; j0 += kWinThreads) {
+        abcs[j0] = p.ab * p.cosphi[j0 + 1];
+        table_fetch(kbeg, j0, Qh[j0], Ur[j0]);
+    }
+    if (MODE == 1) {   // levels 1 and kmax of the 3-D LWA are zero (compute_flux_dirinv.f90 touches k = 2 .. kmax-1)
+        for (int t = tid; t < nd * kWinCols; t += kWinThreads) {
+            const int m = t >> 3, cc = t & 7;
+            const int j0 = fr.rev ? nd - 1 - m : m;
+            if (i0 + cc < p.imax && !(fr.skip_first && j0 == 0)) {
+                const size_t o = (size_t)b * p.lwa_batch + (size_t)(fr.out_row0 + m) * p.out_pitch + i0 + cc;
+                p.lwa[o] = 0.0;
+                p.lwa[o + (size_t)(p.kmax - 1) * p.lwa_plane] = 0.0;
+            }
+        }
+    }
+
+    double acc[kWinGroupsPerWarp][HAS_NC ? 5 : 4];
+#pragma unroll
+    for (int gi = 0; gi < kWinGroupsPerWarp; ++gi)
+#pragma unroll
+        for (int x = 0; x < (HAS_NC ? 5 : 4); ++x) acc[gi][x] = 0.0;
+    unsigned cnt_c = 0, cnt_a = 0;
+    const int step = fr.rev ? kWinCols : -kWinCols;   // doubles per row step toward the equator
+
+    for (int li = 0; li < nlev; ++li) {
+        const int s = li & 1, k = kbeg + li;
+        double* tq = tiles + (size_t)(s * NF) * TD;
+        const double* Qc = Qh + s * nd;   // table buffers alternate with the level like the tile stages
+        const double* Uc = Ur + s * nd;
+        // thresholds of the next level travel while this one is computed
+        double Qn = 0.0, Un = 0.0;
+        if (li + 1 < nlev) table_fetch(k + 1, tid, Qn, Un);
+        win_mbar_wait(&bars[s], (unsigned)((li >> 1) & 1));
+
+        // ---- phase 1: hemispheric-frame PV (sign, -0 -> +0) and its keys ---------------------------
+        for (int hg = w; hg < G; hg += kWinWarps) {
+            const int j0 = 4 * hg + r;
+            if (j0 < nd) {
+                const int m = fr.rev ? nd - 1 - j0 : j0;
+                const double q = __fma_rn(fr.sg, tq[m * kWinCols + c], 0.0);
+                if (fr.sg != 1.0) tq[m * kWinCols + c] = q;
+                keys[c * P + j0] = win_key(q);
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: the two monotone bound arrays of every column, one warp per (column, direction) -
+        {
+            const int cc = w & 7;
+            int incl[kWinSpan];
+            if (w < 8) {   // PE[x] = max key over rows < x  (PE[0] = -inf)
+                int run = INT_MIN;
+#pragma unroll
+                for (int t = 0; t < kWinSpan; ++t) {
+                    const int row = kWinSpan * lane + t;
+                    const int v = (row < nd) ? keys[cc * P + row] : INT_MIN;
+                    run = max(run, v);
+                    incl[t] = run;
+                }
+                int ex = run;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int n = __shfl_up_sync(FULL, ex, d);
+                    if (lane >= d) ex = max(ex, n);
+                }
+                int off = __shfl_up_sync(FULL, ex, 1);
+                if (lane == 0) { off = INT_MIN; PE[cc * P] = INT_MIN; }
+#pragma unroll
+                for (int t = 0; t < kWinSpan; ++t) {
+                    const int row = kWinSpan * lane + t;
+                    if (row < nd) PE[cc * P + row + 1] = max(off, incl[t]);
+                }
+            } else {       // PP[x] = min key over rows >= x  (PP[nd] = +inf)
+                int run = INT_MAX;
+#pragma unroll
+                for (int t = kWinSpan - 1; t >= 0; --t) {
+                    const int row = kWinSpan * lane + t;
+                    const int v = (row < nd) ? keys[cc * P + row] : INT_MAX;
+                    run = min(run, v);
+                    incl[t] = run;
+                }
+                int ex = run;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int n = __shfl_down_sync(FULL, ex, d);
+                    if (lane + d < 32) ex = min(ex, n);
+                }
+                int off = __shfl_down_sync(FULL, ex, 1);
+                if (lane == 31) off = INT_MAX;
+                if (lane == 0) PP[cc * P + nd] = INT_MAX;
+#pragma unroll
+                for (int t = 0; t < kWinSpan; ++t) {
+                    const int row = kWinSpan * lane + t;
+                    if (row < nd) PP[cc * P + row] = min(off, incl[t]);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- main: the two windowed sums of every threshold row ----------------------------------------
+        const double wd = (MODE == 1) ? p.vw[k - 1] * p.dc : 0.0;
+#pragma unroll
+        for (int gi = 0; gi < kWinGroupsPerWarp; ++gi) {
+            const int hg = w + kWinWarps * gi;
+            if (hg < G) {
+                const int j0 = 4 * hg + r;
+                const bool valid = j0 < nd;
+                const int m = fr.rev ? nd - 1 - j0 : j0;
+                const bool act = valid && colok && (j0 + 1 >= p.jstart) && (j0 + 1 <= p.jend);
+                const double Qj = valid ? Qc[j0] : 0.0;
+                const int kq = win_key(Qj);
+                const int kqc = act ? max(kq, INT_MIN + 1) : INT_MAX;   // "may exceed Q_j":      key >= kqc
+                const int kqa = act ? min(kq, INT_MAX - 1) : INT_MIN;   // "may not exceed Q_j":  key <= kqa
+                double A1 = 0.0, A2 = 0.0, B = 0.0, N = 0.0;
+                const double* tp = tq + m * kWinCols + c;
+                {   // cyclonic side: rows j0-1, j0-2, ... while some row at or beyond may exceed Q_j
+                    const int* pe_p = PE + c * P + j0;
+                    int pe = valid ? *pe_p : INT_MIN;
+                    const double* t = tp;
+                    while (__any_sync(FULL, pe >= kqc)) {
+                        t += step; --pe_p;
+                        if (pe >= kqc) {
+                            const double qv = t[0], uv = t[TD], av = t[aa8 - tq];
+                            double nv = 0.0;
+                            if (HAS_NC) nv = t[2 * TD];
+                            pe = *pe_p;
+                            const double diff = qv - Qj;
+                            if (diff > 0.0) {
+                                A1 = __fma_rn(diff, av, A1);
+                                B = __fma_rn(diff, uv, B);
+                                if (HAS_NC) N = __fma_rn(nv, av, N);
+                                if (COUNT) ++cnt_c;
+                            }
+                        }
+                    }
+                }
+                {   // anticyclonic side: rows j0, j0+1, ... while some row at or beyond may not exceed Q_j
+                    const int* pp_p = PP + c * P + j0;
+                    int pp = valid ? *pp_p : INT_MAX;
+                    const double* t = tp;
+                    while (__any_sync(FULL, pp <= kqa)) {
+                        if (pp <= kqa) {
+                            const double qv = t[0], uv = t[TD], av = t[aa8 - tq];
+                            double nv = 0.0;
+                            if (HAS_NC) nv = t[2 * TD];
+                            pp = pp_p[1];
+                            const double diff = qv - Qj;
+                            if (diff <= 0.0) {
+                                A2 = __fma_rn(-diff, av, A2);
+                                B = __fma_rn(-diff, uv, B);
+                                if (HAS_NC) N = __fma_rn(-nv, av, N);
+                                if (COUNT) ++cnt_a;
+                            }
+                        }
+                        t -= step; ++pp_p;
+                    }
+                }
+                if (valid) {
+                    // a1 = A1, a2 = A2;  ua2 = a dphi cos(phi_j) B - uref_j (a1 + a2)   (compute_flux_dirinv.f90:96-113)
+                    const double lw = A1 + A2;
+                    double x1 = 0.0, u2 = 0.0;
+                    if (act) {
+                        x1 = Uc[j0] * lw;
+                        u2 = __fma_rn(abcs[j0], B, -x1);
+                    }
+                    const bool store = colok && !(fr.skip_first && j0 == 0);
+                    if (MODE == 1) {
+                        acc[gi][0] = acc[gi][0] + A1 * wd;
+                        acc[gi][1] = acc[gi][1] + A2 * wd;
+                        acc[gi][2] = acc[gi][2] + x1 * wd;
+                        acc[gi][3] = acc[gi][3] + u2 * wd;
+                        if (HAS_NC) acc[gi][HAS_NC ? 4 : 0] = acc[gi][HAS_NC ? 4 : 0] + N * wd;
+                        if (store)
+                            st_stream(&p.lwa[(size_t)b * p.lwa_batch + (size_t)(k - 1) * p.lwa_plane +
+                                             (size_t)(fr.out_row0 + m) * p.out_pitch + i0 + c], fabs(lw));
+                    } else if (store) {
+                        const size_t o = (size_t)b * p.out_batch + (size_t)(k - 1) * p.out_plane +
+                                         (size_t)(fr.out_row0 + m) * p.out_pitch + i0 + c;
+                        p.a1[o] = A1;
+                        p.a2[o] = A2;
+                        if (p.u2) p.u2[o] = u2;
+                        if (HAS_NC && p.ncf) p.ncf[o] = N;
+                    }
+                }
+            }
+        }
+        // next level's thresholds into the other table buffer (its last readers finished a level ago)
+        if (li + 1 < nlev && tid < nd) {
+            Qh[(s ^ 1) * nd + tid] = Qn;
+            Ur[(s ^ 1) * nd + tid] = Un;
+        }
+        // the tile of this stage is rewritten by the async proxy next: order the generic accesses before it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0 && li + 2 < nlev) issue(li + 2);
+    }
+
+    if (MODE == 1) {
+#pragma unroll
+        for (int gi = 0; gi < kWinGroupsPerWarp; ++gi) {
+            const int hg = w + kWinWarps * gi;
+            const int j0 = 4 * hg + r;
+            if (hg < G && j0 < nd && colok && !(fr.skip_first && j0 == 0)) {
+                const int m = fr.rev ? nd - 1 - j0 : j0;
+                double* o = p.out2d + (size_t)b * p.o2_batch + (size_t)(fr.out_row0 + m) * p.out_pitch + i0 + c;
+                o[(size_t)p.slot_a1 * p.o2_plane] = acc[gi][0];
+                o[(size_t)p.slot_a2 * p.o2_plane] = acc[gi][1];
+                o[(size_t)p.slot_lwa * p.o2_plane] = acc[gi][0] + acc[gi][1];
+                o[(size_t)p.slot_ua1 * p.o2_plane] = acc[gi][2];
+                o[(size_t)p.slot_ua2 * p.o2_plane] = acc[gi][3];
+                if (HAS_NC) o[(size_t)p.slot_ncf * p.o2_plane] = (fr.sg < 0.0) ? -acc[gi][HAS_NC ? 4 : 0] : acc[gi][HAS_NC ? 4 : 0];
+            }
+        }
+    }
+    if (COUNT && p.mask_count) {
+        cnt_c = __reduce_add_sync(FULL, cnt_c);
+        cnt_a = __reduce_add_sync(FULL, cnt_a);
+        if (lane == 0 && (cnt_c | cnt_a)) {
+            atomicAdd(&p.mask_count[0], (unsigned long long)cnt_a);
+            atomicAdd(&p.mask_count[1], (unsigned long long)cnt_c);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*WinEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static WinEncodeFn win_encoder() {
+    static WinEncodeFn fn = []() -> WinEncodeFn {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        return (WinEncodeFn)f;
+    }();
+    return fn;
+}
+
+// fields [batch][levels][rows][imax] (longitude fastest) as a 4-D tensor with (8 x boxrows) boxes
+static int win_tensor_map(CUtensorMap* tm, const double* base, int imax, int rows, int levels, int batch, int boxrows) {
+    WinEncodeFn enc = win_encoder();
+    if (!enc) return FALWA_ERR_ARG;
+    cuuint64_t dims[4] = {(cuuint64_t)imax, (cuuint64_t)rows, (cuuint64_t)levels, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {(cuuint64_t)imax * 8, (cuuint64_t)imax * rows * 8, (cuuint64_t)imax * rows * levels * 8};
+    cuuint32_t box[4] = {(cuuint32_t)kWinCols, (cuuint32_t)boxrows, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : FALWA_ERR_ARG;
+}
+
+// the window kernel needs TMA-compatible fields (16-byte aligned base and row pitch) and at most 384 hemispheric rows
+static bool win_supported(int imax, int nd, const void* pv, const void* uu, const void* nc) {
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    return nd >= 4 && nd <= kWinMaxRows && (imax % 2 == 0) && al(pv) && al(uu) && (!nc || al(nc)) && win_encoder() != nullptr;
+}
+
+template <int MODE>
+static int win_launch_mode(const CUtensorMap& tq, const CUtensorMap& tu, const CUtensorMap& tn, const WinArgs& a, bool has_nc,
+                           dim3 grid, size_t smem, cudaStream_t st) {
+    auto go = [&](auto kern) -> int {
+        FALWA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kWinThreads, smem, st>>>(tq, tu, tn, a);
+        return 0;
+    };
+    const bool count = a.mask_count != nullptr;
+    if (has_nc) return count ? go(lwa_window_kernel<MODE, true, true>) : go(lwa_window_kernel<MODE, true, false>);
+    return count ? go(lwa_window_kernel<MODE, false, true>) : go(lwa_window_kernel<MODE, false, false>);
+}
+
+// pv / uu / nc: [batch][kmax][in_rows][imax]; a.k_first / k_count / frames / thresholds / outputs filled by the caller
+static int lwa_window_launch(WinArgs a, int mode, const double* pv, const double* uu, const double* nc, int in_rows,
+                             int batch, int nprob, cudaStream_t st) {
+    const int nbox = (a.nd + 255) / 256;
+    int boxrows = (a.nd + nbox - 1) / nbox;
+    boxrows += boxrows & 1;
+    a.nbox = nbox; a.boxrows = boxrows;
+    CUtensorMap tq, tu, tn;
+    int rc;
+    if ((rc = win_tensor_map(&tq, pv, a.imax, in_rows, a.kmax, batch, boxrows))) return rc;
+    if ((rc = win_tensor_map(&tu, uu, a.imax, in_rows, a.kmax, batch, boxrows))) return rc;
+    if ((rc = win_tensor_map(&tn, nc ? nc : pv, a.imax, in_rows, a.kmax, batch, boxrows))) return rc;
+    const int tiles = ceil_div(a.imax, kWinCols);
+    if (mode == 1) a.k_per_cta = a.k_count;
+    else a.k_per_cta = std::max(1, std::min(a.k_count, ceil_div((long long)a.k_count * tiles * nprob, 148 * 8)));
+    const int chunks = ceil_div(a.k_count, a.k_per_cta);
+    const size_t smem = win_smem_layout(a.nd, nbox, boxrows, nc ? 3 : 2).total;
+    dim3 grid(tiles, chunks, nprob);
+    FALWA_KERNEL("lwa_window_kernel", st);
+    rc = mode == 1 ? win_launch_mode<1>(tq, tu, tn, a, nc != nullptr, grid, smem, st)
+                   : win_launch_mode<0>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
+    if (rc) return rc;
+    FALWA_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace falwa

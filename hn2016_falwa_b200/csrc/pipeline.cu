@@ -396,7 +396,9 @@ struct ColumnLevelPlain : ColumnLevelBase {
 // SPECIAL = false walks every ordinary row (launch: 32 x 8 tiles over all rows; the two special rows return at once);
 // SPECIAL = true walks only the first row and the boundary row (launch: grid.y = 2), which need extra neighbour
 // loads — keeping those out of the ordinary instantiation saves 36 registers there (3 CTAs per SM instead of 2).
-template <bool SPECIAL>
+// EXT = true: the LWA pieces never exist as 3-D intermediates — lwa_window_kernel has already written the 3-D LWA and
+// the vertical sums of astar1 / astar2 / ua1 / ua2 (/ ncforce) — and this kernel only walks u, v and theta.
+template <bool SPECIAL, bool EXT>
 __global__ void __launch_bounds__(256, SPECIAL ? 2 : 3)
 flux_column_kernel(FusedFluxArgs p, double* __restrict__ hs /* [b][nhemi][nd][imax] */) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -417,8 +419,8 @@ flux_column_kernel(FusedFluxArgs p, double* __restrict__ hs /* [b][nhemi][nd][im
     const size_t plane = (size_t)nlat * imax;
     const size_t f3 = (size_t)b * plane * kmax;
     const double *uu = p.uu + f3, *vv = p.vv + f3, *pt = p.pt + f3;
-    const double *sa1 = p.sa1 + f3, *sa2 = p.sa2 + f3, *su2 = p.su2 + f3;
-    const double* snc = p.has_ncforce ? p.snc + f3 : nullptr;
+    const double *sa1 = EXT ? nullptr : p.sa1 + f3, *sa2 = EXT ? nullptr : p.sa2 + f3, *su2 = EXT ? nullptr : p.su2 + f3;
+    const double* snc = (!EXT && p.has_ncforce) ? p.snc + f3 : nullptr;
     const double* uref = p.uref_st + (size_t)b * kmax * nlat;
     const double* tref = p.tref_st + (size_t)b * kmax * nlat;
     const double* tg = p.prof + (size_t)b * 4 * kmax + (south ? 0 : kmax);  // tn0 north / ts0 south
@@ -453,8 +455,10 @@ flux_column_kernel(FusedFluxArgs p, double* __restrict__ hs /* [b][nhemi][nd][im
         if (k < kmax) {
             if (in_range) {
                 L.t0 = pt[lev + o2]; L.tr = tref[(size_t)(k - 1) * nlat + g];
-                L.a1 = sa1[lev + o2]; L.a2 = sa2[lev + o2]; L.u2 = su2[lev + o2];
-                if (snc) L.nc = snc[lev + o2];
+                if (!EXT) {
+                    L.a1 = sa1[lev + o2]; L.a2 = sa2[lev + o2]; L.u2 = su2[lev + o2];
+                    if (snc) L.nc = snc[lev + o2];
+                }
             }
             if constexpr (SPECIAL) {
                 if (first) {
@@ -472,7 +476,7 @@ flux_column_kernel(FusedFluxArgs p, double* __restrict__ hs /* [b][nhemi][nd][im
 
     double s_a1 = 0, s_a2 = 0, s_ua1 = 0, s_ua2 = 0, s_ep1 = 0, s_nc = 0, s_u = 0, s_fphi = 0, s_g = 0;
     double s_e2 = 0, s_e3 = 0, ep4 = 0;   // directly evaluated ep2 / ep3 of the two special rows
-    if (!skip_out) {
+    if (!EXT && !skip_out) {
         lwa[o2] = 0.0;
         lwa[(size_t)(kmax - 1) * plane + o2] = 0.0;
     }
@@ -503,13 +507,15 @@ flux_column_kernel(FusedFluxArgs p, double* __restrict__ hs /* [b][nhemi][nd][im
                 e1 = e1 - 0.5 * ((cur.t0 - cur.tr) * (cur.t0 - cur.tr)) * f11[k - 1];
                 e1 = e1 * c0;
             }
-            if (!skip_out) lwa[lev + o2] = fabs(cur.a1 + cur.a2);
-            s_a1 = s_a1 + cur.a1 * wd;
-            s_a2 = s_a2 + cur.a2 * wd;
-            s_ua1 = s_ua1 + x_ua1 * wd;
-            s_ua2 = s_ua2 + cur.u2 * wd;
+            if (!EXT) {
+                if (!skip_out) lwa[lev + o2] = fabs(cur.a1 + cur.a2);
+                s_a1 = s_a1 + cur.a1 * wd;
+                s_a2 = s_a2 + cur.a2 * wd;
+                s_ua1 = s_ua1 + x_ua1 * wd;
+                s_ua2 = s_ua2 + cur.u2 * wd;
+                s_nc = s_nc + cur.nc * wd;
+            }
             s_ep1 = s_ep1 + e1 * wd;
-            s_nc = s_nc + cur.nc * wd;
             if (first) s_e3 = s_e3 + ((cur.um - cur.urm) * cm * cm * (sg * cur.vm)) * wd;
             if (brow) {  // compute_flux_dirinv.f90:173-178
                 double wk = wd;
@@ -522,18 +528,20 @@ flux_column_kernel(FusedFluxArgs p, double* __restrict__ hs /* [b][nhemi][nd][im
     }
     hs[(((size_t)b * p.nhemi + hidx) * nd + (j - 1)) * imax + i] = s_g;
     if (skip_out) return;
-    out[(size_t)O_ASTAR1 * plane + o2] = s_a1;
-    out[(size_t)O_ASTAR2 * plane + o2] = s_a2;
-    out[(size_t)O_LWA * plane + o2] = s_a1 + s_a2;
-    out[(size_t)O_UA1 * plane + o2] = s_ua1;
-    out[(size_t)O_UA2 * plane + o2] = s_ua2;
+    if (!EXT) {
+        out[(size_t)O_ASTAR1 * plane + o2] = s_a1;
+        out[(size_t)O_ASTAR2 * plane + o2] = s_a2;
+        out[(size_t)O_LWA * plane + o2] = s_a1 + s_a2;
+        out[(size_t)O_UA1 * plane + o2] = s_ua1;
+        out[(size_t)O_UA2 * plane + o2] = s_ua2;
+    }
     out[(size_t)O_EP1 * plane + o2] = s_ep1;
     // hemispheric-frame ep2 / ep3 of the special rows; baro_post_kernel fills the others from hs and applies the
     // southern swap + sign (oopinterface.py:790-792)
     out[(size_t)O_EP2 * plane + o2] = s_e2;
     out[(size_t)O_EP3 * plane + o2] = s_e3;
     out[(size_t)O_EP4 * plane + o2] = ep4;
-    out[(size_t)O_NCF * plane + o2] = south ? -s_nc : s_nc;
+    if (!EXT || !p.has_ncforce) out[(size_t)O_NCF * plane + o2] = south ? -s_nc : s_nc;
     out[(size_t)O_UBARO * plane + o2] = s_u;
     out[(size_t)O_FPHI * plane + o2] = s_fphi;
 }
@@ -1240,9 +1248,36 @@ static int lwa_fluxes_impl(const falwa_plan* P, int batch, const double* qgpv, c
         FALWA_CUDA_TRY(cudaMemsetAsync(lwa, 0, sizeof(double) * (size_t)batch * f3, st));
         FALWA_CUDA_TRY(cudaMemsetAsync(out2d, 0, sizeof(double) * (size_t)batch * O_COUNT * nlat * nlon, st));
     }
-    const bool use_scan = (method != 1) && scan_supported(nd);
+    // method: 0 = automatic (windowed sums, else interval scan, else the double loop), 1 = double loop,
+    //         2 = interval scan, 3 = windowed sums
+    const bool use_window = (method == 0 || method == 3) && !l3d && win_supported(nlon, nd, qgpv, u, ncforce);
+    const bool use_scan = !use_window && (method != 1) && scan_supported(nd);
     ScanTables tabs;
-    if (use_scan) {
+    if (use_window) {
+        // 3-D LWA and the vertical sums of astar1, astar2, ua1, ua2 (, ncforce) in one walk over the levels
+        WinArgs w{};
+        w.imax = nlon; w.nd = nd; w.kmax = kmax; w.jstart = jb + 1; w.jend = nd - 1; w.nhemi = nhemi;
+        w.k_first = 2; w.k_count = kmax - 2;
+        for (int h = 0; h < 2; ++h) {  // hemispheric row jj -> global row nd-2+jj (north) / nd-jj (south)
+            w.fr[h].in_row0 = w.fr[h].out_row0 = h ? 0 : nd - 1;
+            w.fr[h].rev = h;
+            w.fr[h].skip_first = (nhemi == 2 && h == 0) ? 1 : 0;
+            w.fr[h].sg = h ? -1.0 : 1.0;
+            w.q_row0[h] = w.u_row0[h] = nd - 1;
+            w.q_rstep[h] = w.u_rstep[h] = h ? -1 : 1;
+            w.q_sg[h] = h ? -1.0 : 1.0;
+        }
+        w.qref = qref_cu; w.q_batch = (size_t)kmax * nlat; w.q_kstride = nlat;
+        w.uref = uref_st; w.u_batch = (size_t)kmax * nlat; w.u_kstride = nlat;
+        w.cosphi = d + P->o_cosphi; w.ab = p.ab;
+        w.lwa = lwa; w.out2d = out2d; w.vw = d + P->o_vw; w.dc = p.dc;
+        w.lwa_batch = f3; w.lwa_plane = (size_t)nlat * nlon; w.out_pitch = nlon;
+        w.o2_batch = (size_t)O_COUNT * nlat * nlon; w.o2_plane = (size_t)nlat * nlon;
+        w.slot_a1 = O_ASTAR1; w.slot_a2 = O_ASTAR2; w.slot_lwa = O_LWA; w.slot_ua1 = O_UA1; w.slot_ua2 = O_UA2;
+        w.slot_ncf = O_NCF;
+        w.mask_count = nullptr;
+        if ((rc = lwa_window_launch(w, 1, qgpv, u, ncforce, nlat, batch, batch * nhemi, st))) return rc;
+    } else if (use_scan) {
         // LWA pieces a1, a2, ua2 (, ncforce3d) of every level by the interval scan, in the global frame
         const int narr = ncforce ? 4 : 3, nprob = batch * nhemi;
         if ((rc = tmp.alloc((size_t)narr * batch * f3, st))) return rc;
@@ -1278,11 +1313,16 @@ static int lwa_fluxes_impl(const falwa_plan* P, int batch, const double* qgpv, c
             FALWA_KERNEL("fused_flux_layerwise_kernel", st);
             if (use_scan) fused_flux_kernel<false><<<grid, block, 0, st>>>(p);
             else fused_flux_kernel<true><<<grid, block, 0, st>>>(p);
+        } else if (use_window) {
+            if ((rc = hsum.alloc((size_t)batch * nhemi * nd * nlon, st))) return rc;
+            FALWA_KERNEL("flux_column_kernel", st);
+            flux_column_kernel<false, true><<<grid, block, 0, st>>>(p, hsum.d);
+            flux_column_kernel<true, true><<<dim3(ceil_div(nlon, 256), 2, batch * nhemi), 256, 0, st>>>(p, hsum.d);
         } else if (use_scan) {
             if ((rc = hsum.alloc((size_t)batch * nhemi * nd * nlon, st))) return rc;
             FALWA_KERNEL("flux_column_kernel", st);
-            flux_column_kernel<false><<<grid, block, 0, st>>>(p, hsum.d);
-            flux_column_kernel<true><<<dim3(ceil_div(nlon, 256), 2, batch * nhemi), 256, 0, st>>>(p, hsum.d);
+            flux_column_kernel<false, false><<<grid, block, 0, st>>>(p, hsum.d);
+            flux_column_kernel<true, false><<<dim3(ceil_div(nlon, 256), 2, batch * nhemi), 256, 0, st>>>(p, hsum.d);
         } else {
             FALWA_KERNEL("fused_flux_bruteforce_kernel", st);
             fused_flux_kernel<true><<<grid, block, 0, st>>>(p);
@@ -1290,7 +1330,7 @@ static int lwa_fluxes_impl(const falwa_plan* P, int batch, const double* qgpv, c
         FALWA_LAUNCH_CHECK();
     }
     { FALWA_KERNEL("baro_post_kernel", st); baro_post_kernel<<<dim3(ceil_div(P->nlon, 256), P->nlat, batch), 256, 0, st>>>(
-        P->nlon, P->nlat, P->a, P->dphi, P->dlambda, d + P->o_clat, out2d, (use_scan && !l3d) ? hsum.d : nullptr, nhemi, nd, jb); }
+        P->nlon, P->nlat, P->a, P->dphi, P->dlambda, d + P->o_clat, out2d, ((use_scan || use_window) && !l3d) ? hsum.d : nullptr, nhemi, nd, jb); }
     FALWA_LAUNCH_CHECK();
     return 0;
 }

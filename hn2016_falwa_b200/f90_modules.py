@@ -18,8 +18,9 @@ import torch
 from . import _lib
 from ._lib import check, dptr, hptr, stream_ptr
 
-# LWA methods of compute_flux_dirinv_nshem / compute_lwa_only_nhn22: 0 = default, 1 = the reference's double loop
-LWA_METHODS = (0, 1)
+# LWA methods of compute_flux_dirinv_nshem / compute_lwa_only_nhn22: 0 = default (exact windowed sums, lwa_window.cu),
+# 1 = the reference's double loop, 2 = interval scan (flux_scan.cu)
+LWA_METHODS = (0, 1, 2)
 
 
 def _dev(x, ndim):

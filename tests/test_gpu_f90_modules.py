@@ -158,7 +158,7 @@ def test_compute_reference_states_nh18(gpu, staged, hemisphere):
     compare(tag + "tref", g[2], w[2], rtol=1e-9)
 
 
-@pytest.mark.parametrize("method", [0, 1], ids=["scan", "bruteforce"])
+@pytest.mark.parametrize("method", [0, 1, 2], ids=["window", "bruteforce", "scan"])
 @pytest.mark.parametrize("kind", ["nh18", "nhn22"])
 @pytest.mark.parametrize("hemisphere", ["north", "south"])
 def test_compute_flux_dirinv_nshem(gpu, staged, kind, hemisphere, method):
@@ -190,7 +190,7 @@ def test_compute_flux_dirinv_nshem(gpu, staged, kind, hemisphere, method):
         compare(f"{name}/{kind}/{hemisphere}/flux{method}/{nm}", a_, b_, rtol=rtol, atol=ascale * np.abs(b_).max())
 
 
-@pytest.mark.parametrize("method", [0, 1], ids=["scan", "bruteforce"])
+@pytest.mark.parametrize("method", [0, 1, 2], ids=["window", "bruteforce", "scan"])
 def test_compute_lwa_only_nhn22(gpu, staged, method):
     name, inputs, o18, _ = staged
     c = o18["config"]

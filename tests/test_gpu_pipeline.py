@@ -36,7 +36,7 @@ def _check_all(tag, f, want):
         compare(f"{tag}/{name}", getattr(f, name), want[name], rtol=rtol, atol=atol)
 
 
-@pytest.mark.parametrize("method", [0, 1], ids=["scan", "bruteforce"])
+@pytest.mark.parametrize("method", [0, 1, 2], ids=["window", "bruteforce", "scan"])
 @pytest.mark.parametrize("kind", ["nh18", "nhn22"])
 def test_qgfield_pipeline_matches_oracle(case, kind, method):
     name, inputs = case
