@@ -139,6 +139,8 @@ def algorithmic_bytes(nlon, nlat, nd, kmax, nlev, has_avort=True):
         "fused_flux_bruteforce_kernel": 2 * (4 * hemi3 + hemi3 + 11 * hemi2),
         "lwa_scan_kernel": 2 * (2 * hemi3 + 3 * hemi3),                        # read pv, u; write a1, a2, ua2
         "flux_column_kernel": 2 * (6 * hemi3 + hemi3 + 12 * hemi2),            # read a1,a2,ua2,u,v,theta; write lwa + 2-D
+        "lwa_window_kernel": 2 * (2 * hemi3 + hemi3 + 5 * hemi2),              # read pv, u; write lwa + 5 vertical sums
+        "flux_uvt_column_kernel": 2 * (3 * hemi3 + 8 * hemi2),                 # read u, v, theta; write 2-D sums
         "baro_post_kernel": 2 * f3 + 8 * f2,
         "pipeline": 3 * f3in + 4 * f3 + f3 + 12 * f2,                         # 3056.6 MB at 0.25°
     }
@@ -408,7 +410,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=1, help="snapshots per H2D/D2H chunk of the end-to-end run")
     ap.add_argument("--grid", default="0.25", choices=sorted(GRIDS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--method", type=int, default=0, help="LWA algorithm: 0 automatic, 1 brute force")
+    ap.add_argument("--method", type=int, default=0, help="LWA algorithm: 0 automatic (windowed sums), 1 double loop, 2 interval scan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

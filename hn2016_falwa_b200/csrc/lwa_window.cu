@@ -86,15 +86,16 @@ __device__ __forceinline__ int win_key(double x) {
     return hi ^ ((hi >> 31) & 0x7fffffff);
 }
 
+// Shared-memory plan.  The tile stride is a compile-time constant so that, from the address of q(row, col), the
+// operands u(row, col) and aa(row) sit at immediate offsets (one address register per window step).
+constexpr int kWinTile = kWinMaxRows * kWinCols;     // doubles of one (rows x 8) tile slot
+// Without ncforce: [q0 | u0 | aa | q1 | u1 | aa];  with: [q0 | u0 | n0 | aa | q1 | u1 | n1] (one aa8 between the stages).
 struct WinSmem {
-    size_t tile_doubles;     // doubles of one (rows x 8) tile
-    size_t off_aa, off_keys, off_pe, off_pp, off_q, off_u, off_cs, off_bar, total;
+    size_t off_keys, off_pe, off_pp, off_q, off_u, off_cs, off_bar, total;
 };
-__host__ __device__ inline WinSmem win_smem_layout(int nd, int nbox, int boxrows, int nfields) {
+__host__ __device__ inline WinSmem win_smem_layout(int nd, int nfields) {
     WinSmem s;
-    s.tile_doubles = (size_t)nbox * boxrows * kWinCols;
-    size_t o = (size_t)2 * nfields * s.tile_doubles * 8;
-    s.off_aa = o; o += s.tile_doubles * 8;
+    size_t o = (size_t)(nfields == 3 ? 7 : 6) * kWinTile * 8;
     s.off_keys = o; o += (size_t)kWinCols * kWinKeyPitch * 4;
     s.off_pe = o; o += (size_t)kWinCols * kWinKeyPitch * 4;
     s.off_pp = o; o += (size_t)kWinCols * kWinKeyPitch * 4;
@@ -113,12 +114,12 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     extern __shared__ __align__(1024) unsigned char win_raw[];
     constexpr int NF = HAS_NC ? 3 : 2;
     constexpr int P = kWinKeyPitch;
+    constexpr int TU = kWinTile, TN = 2 * kWinTile;                      // u, nc relative to q (doubles)
+    constexpr int SD = (HAS_NC ? 4 : 3) * kWinTile;                      // doubles between the two stages
     constexpr unsigned FULL = 0xffffffffu;
     const int nd = p.nd;
-    const WinSmem L = win_smem_layout(nd, p.nbox, p.boxrows, NF);
-    const int TD = (int)L.tile_doubles;
-    double* tiles = reinterpret_cast<double*>(win_raw);                 // [stage][field][rows][8]
-    double* aa8 = reinterpret_cast<double*>(win_raw + L.off_aa);        // [rows][8]: a dphi cos(phi) of the tile row
+    const WinSmem L = win_smem_layout(nd, NF);
+    double* tiles = reinterpret_cast<double*>(win_raw);                 // [stage][q | u | aa8 | nc][rows][8]
     int* keys = reinterpret_cast<int*>(win_raw + L.off_keys);           // [8][P], hemispheric row index
     int* PE = reinterpret_cast<int*>(win_raw + L.off_pe);               // [8][P]: PE[x] = max key of rows < x
     int* PP = reinterpret_cast<int*>(win_raw + L.off_pp);               // [8][P]: PP[x] = min key of rows >= x
@@ -138,25 +139,28 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     const int nlev = kend - kbeg;
     if (nlev <= 0) return;
     const int G = (nd + 3) >> 2;
-    const unsigned tile_bytes = (unsigned)(TD * 8);
+    const unsigned box_bytes = (unsigned)(p.boxrows * kWinCols * 8);
 
     auto issue = [&](int li) {   // one elected thread: all boxes of level kbeg + li into stage li & 1
         const int s = li & 1, k = kbeg + li;
-        win_mbar_expect(&bars[s], tile_bytes * NF);
+        win_mbar_expect(&bars[s], box_bytes * p.nbox * NF);
         for (int bx = 0; bx < p.nbox; ++bx) {
             const int row = fr.in_row0 + bx * p.boxrows;
-            double* dst = tiles + (size_t)(s * NF) * TD + (size_t)bx * p.boxrows * kWinCols;
+            double* dst = tiles + (size_t)s * SD + (size_t)bx * p.boxrows * kWinCols;
             win_tma_load(dst, &tm_q, &bars[s], i0, row, k - 1, b);
-            win_tma_load(dst + TD, &tm_u, &bars[s], i0, row, k - 1, b);
-            if (HAS_NC) win_tma_load(dst + 2 * TD, &tm_n, &bars[s], i0, row, k - 1, b);
+            win_tma_load(dst + TU, &tm_u, &bars[s], i0, row, k - 1, b);
+            if (HAS_NC) win_tma_load(dst + TN, &tm_n, &bars[s], i0, row, k - 1, b);
         }
     };
-    auto table_fetch = [&](int k, int j0, double& Q, double& U) {   // thresholds of hemispheric row j0 + 1 at level k
+    // thresholds of hemispheric row tid + 1: per-thread base pointers, one level stride
+    const bool trow = tid < nd && tid + 1 >= p.jstart && tid + 1 <= p.jend;
+    const double* qsrc = trow ? p.qref + (size_t)b * p.q_batch + p.q_row0[h] + p.q_rstep[h] * tid : nullptr;
+    const double* usrc = (trow && p.uref) ? p.uref + (size_t)b * p.u_batch + p.u_row0[h] + p.u_rstep[h] * tid : nullptr;
+    const double qsg = p.q_sg[h];
+    auto table_fetch = [&](int k, double& Q, double& U) {
         Q = 0.0; U = 0.0;
-        if (j0 < nd && j0 + 1 >= p.jstart && j0 + 1 <= p.jend) {
-            Q = __fma_rn(p.q_sg[h], p.qref[(size_t)b * p.q_batch + (size_t)(k - 1) * p.q_kstride + p.q_row0[h] + p.q_rstep[h] * j0], 0.0);
-            if (p.uref) U = p.uref[(size_t)b * p.u_batch + (size_t)(k - 1) * p.u_kstride + p.u_row0[h] + p.u_rstep[h] * j0];
-        }
+        if (qsrc) Q = __fma_rn(qsg, qsrc[(size_t)(k - 1) * p.q_kstride], 0.0);
+        if (usrc) U = usrc[(size_t)(k - 1) * p.u_kstride];
     };
 
     if (tid == 0) {
@@ -169,16 +173,20 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         issue(0);
         if (nlev > 1) issue(1);
     }
-    for (int m = tid; m < p.nbox * p.boxrows; m += kWinThreads) {
-        const int jj = fr.rev ? nd - m : m + 1;
-        const double v = (m < nd) ? p.ab * p.cosphi[jj] : 0.0;
+    for (int t = tid; t < nd * kWinCols; t += kWinThreads) {   // a dphi cos(phi) of every tile row, both stages
+        const int m = t >> 3;
+        const double v = p.ab * p.cosphi[fr.rev ? nd - m : m + 1];
+        tiles[(HAS_NC ? 3 : 2) * kWinTile + t] = v;
+        if (!HAS_NC) tiles[5 * kWinTile + t] = v;
+    }
+    for (int t = nd + tid; t < kWinSpan * 32; t += kWinThreads)   // rows beyond the column: neutral for the minima
 #pragma unroll
-        for (int cc = 0; cc < kWinCols; ++cc) aa8[m * kWinCols + cc] = v;
+        for (int cc = 0; cc < kWinCols; ++cc) keys[cc * P + t] = INT_MAX;
+    if (tid < nd) {
+        abcs[tid] = p.ab * p.cosphi[tid + 1];
+        table_fetch(kbeg, Qh[tid], Ur[tid]);
     }
-    for (int j0 = tid; j0 < nd; j0 += kWinThreads) {
-        abcs[j0] = p.ab * p.cosphi[j0 + 1];
-        table_fetch(kbeg, j0, Qh[j0], Ur[j0]);
-    }
+    if (tid < kWinCols) { PE[tid * P] = INT_MIN; PP[tid * P + nd] = INT_MAX; }
     if (MODE == 1) {   // levels 1 and kmax of the 3-D LWA are zero (compute_flux_dirinv.f90 touches k = 2 .. kmax-1)
         for (int t = tid; t < nd * kWinCols; t += kWinThreads) {
             const int m = t >> 3, cc = t & 7;
@@ -191,48 +199,55 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         }
     }
 
-    double acc[kWinGroupsPerWarp][HAS_NC ? 5 : 4];
+    constexpr int NACC = HAS_NC ? 5 : 4;
+    double acc[kWinGroupsPerWarp][NACC];
 #pragma unroll
     for (int gi = 0; gi < kWinGroupsPerWarp; ++gi)
 #pragma unroll
-        for (int x = 0; x < (HAS_NC ? 5 : 4); ++x) acc[gi][x] = 0.0;
+        for (int x = 0; x < NACC; ++x) acc[gi][x] = 0.0;
     unsigned cnt_c = 0, cnt_a = 0;
     const int step = fr.rev ? kWinCols : -kWinCols;   // doubles per row step toward the equator
+    const int jstart = p.jstart, jend = p.jend;
+    // this lane's element of group 0 of its warp; groups of a warp are 16 groups = 64 rows apart
+    const int j00 = 4 * w + r;
+    const int m00 = fr.rev ? nd - 1 - j00 : j00;
+    const int mstep = fr.rev ? -4 * kWinWarps : 4 * kWinWarps;          // tile rows between consecutive groups of a warp
+    double* const out_base = (MODE == 1 ? p.lwa + (size_t)b * p.lwa_batch : p.a1 + (size_t)b * p.out_batch) +
+                             (size_t)(fr.out_row0 + m00) * p.out_pitch + i0 + c;
+    const size_t out_lev = (MODE == 1) ? p.lwa_plane : p.out_plane;
+    const long long out_gstep = (long long)mstep * p.out_pitch;
+    const bool skip00 = fr.skip_first && j00 == 0;
 
     for (int li = 0; li < nlev; ++li) {
         const int s = li & 1, k = kbeg + li;
-        double* tq = tiles + (size_t)(s * NF) * TD;
-        const double* Qc = Qh + s * nd;   // table buffers alternate with the level like the tile stages
-        const double* Uc = Ur + s * nd;
+        double* const tq = tiles + (size_t)s * SD;
+        const int TA = HAS_NC ? (s ? -kWinTile : 3 * kWinTile) : 2 * kWinTile;   // aa8 relative to q of this stage
+        const double* const Qc = Qh + s * nd;   // table buffers alternate with the level like the tile stages
+        const double* const Uc = Ur + s * nd;
         // thresholds of the next level travel while this one is computed
         double Qn = 0.0, Un = 0.0;
-        if (li + 1 < nlev) table_fetch(k + 1, tid, Qn, Un);
+        if (li + 1 < nlev) table_fetch(k + 1, Qn, Un);
         win_mbar_wait(&bars[s], (unsigned)((li >> 1) & 1));
 
         // ---- phase 1: hemispheric-frame PV (sign, -0 -> +0) and its keys ---------------------------
-        for (int hg = w; hg < G; hg += kWinWarps) {
-            const int j0 = 4 * hg + r;
-            if (j0 < nd) {
-                const int m = fr.rev ? nd - 1 - j0 : j0;
-                const double q = __fma_rn(fr.sg, tq[m * kWinCols + c], 0.0);
-                if (fr.sg != 1.0) tq[m * kWinCols + c] = q;
-                keys[c * P + j0] = win_key(q);
+        {
+            double* tp = tq + m00 * kWinCols + c;
+            int* kp = keys + c * P + j00;
+            for (int j0 = j00; j0 < nd; j0 += 4 * kWinWarps, tp += mstep * kWinCols, kp += 4 * kWinWarps) {
+                const double q = __fma_rn(fr.sg, *tp, 0.0);
+                if (fr.sg != 1.0) *tp = q;
+                *kp = win_key(q);
             }
         }
         __syncthreads();
         // ---- phase 2: the two monotone bound arrays of every column, one warp per (column, direction) -
         {
-            const int cc = w & 7;
             int incl[kWinSpan];
-            if (w < 8) {   // PE[x] = max key over rows < x  (PE[0] = -inf)
+            if (w < 8) {   // PE[x] = max key over rows < x  (PE[0] = -inf); rows beyond nd do not reach entries <= nd
+                const int* kp = keys + w * P + kWinSpan * lane;
                 int run = INT_MIN;
 #pragma unroll
-                for (int t = 0; t < kWinSpan; ++t) {
-                    const int row = kWinSpan * lane + t;
-                    const int v = (row < nd) ? keys[cc * P + row] : INT_MIN;
-                    run = max(run, v);
-                    incl[t] = run;
-                }
+                for (int t = 0; t < kWinSpan; ++t) { run = max(run, kp[t]); incl[t] = run; }
                 int ex = run;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -240,21 +255,15 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     if (lane >= d) ex = max(ex, n);
                 }
                 int off = __shfl_up_sync(FULL, ex, 1);
-                if (lane == 0) { off = INT_MIN; PE[cc * P] = INT_MIN; }
+                if (lane == 0) off = INT_MIN;
+                int* op = PE + w * P + kWinSpan * lane + 1;
 #pragma unroll
-                for (int t = 0; t < kWinSpan; ++t) {
-                    const int row = kWinSpan * lane + t;
-                    if (row < nd) PE[cc * P + row + 1] = max(off, incl[t]);
-                }
-            } else {       // PP[x] = min key over rows >= x  (PP[nd] = +inf)
+                for (int t = 0; t < kWinSpan; ++t) op[t] = max(off, incl[t]);
+            } else if (w < 16) {       // PP[x] = min key over rows >= x  (PP[nd] = +inf; rows beyond nd hold +inf keys)
+                const int* kp = keys + (w - 8) * P + kWinSpan * lane;
                 int run = INT_MAX;
 #pragma unroll
-                for (int t = kWinSpan - 1; t >= 0; --t) {
-                    const int row = kWinSpan * lane + t;
-                    const int v = (row < nd) ? keys[cc * P + row] : INT_MAX;
-                    run = min(run, v);
-                    incl[t] = run;
-                }
+                for (int t = kWinSpan - 1; t >= 0; --t) { run = min(run, kp[t]); incl[t] = run; }
                 int ex = run;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -263,98 +272,86 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                 }
                 int off = __shfl_down_sync(FULL, ex, 1);
                 if (lane == 31) off = INT_MAX;
-                if (lane == 0) PP[cc * P + nd] = INT_MAX;
+                int* op = PP + (w - 8) * P + kWinSpan * lane;
 #pragma unroll
-                for (int t = 0; t < kWinSpan; ++t) {
-                    const int row = kWinSpan * lane + t;
-                    if (row < nd) PP[cc * P + row] = min(off, incl[t]);
-                }
+                for (int t = 0; t < kWinSpan; ++t) op[t] = min(off, incl[t]);
             }
         }
         __syncthreads();
         // ---- main: the two windowed sums of every threshold row ----------------------------------------
         const double wd = (MODE == 1) ? p.vw[k - 1] * p.dc : 0.0;
+        double* out_k = out_base + (size_t)(k - 1) * out_lev;
 #pragma unroll
         for (int gi = 0; gi < kWinGroupsPerWarp; ++gi) {
-            const int hg = w + kWinWarps * gi;
-            if (hg < G) {
-                const int j0 = 4 * hg + r;
+            const int j0 = j00 + 4 * kWinWarps * gi;
+            if (4 * (w + kWinWarps * gi) < nd) {   // warp-uniform: the group exists
                 const bool valid = j0 < nd;
-                const int m = fr.rev ? nd - 1 - j0 : j0;
-                const bool act = valid && colok && (j0 + 1 >= p.jstart) && (j0 + 1 <= p.jend);
+                const bool act = valid && colok && (j0 + 1 >= jstart) && (j0 + 1 <= jend);
                 const double Qj = valid ? Qc[j0] : 0.0;
                 const int kq = win_key(Qj);
-                const int kqc = act ? max(kq, INT_MIN + 1) : INT_MAX;   // "may exceed Q_j":      key >= kqc
-                const int kqa = act ? min(kq, INT_MAX - 1) : INT_MIN;   // "may not exceed Q_j":  key <= kqa
+                const int kqc = max(kq, INT_MIN + 1);   // "may exceed Q_j":      key >= kqc  (never true at PE[0])
+                const int kqa = min(kq, INT_MAX - 1);   // "may not exceed Q_j":  key <= kqa  (never true at PP[nd])
                 double A1 = 0.0, A2 = 0.0, B = 0.0, N = 0.0;
-                const double* tp = tq + m * kWinCols + c;
+                const double* const tp = tq + (valid ? m00 + mstep * gi : 0) * kWinCols + c;
+                const int* const kbase = PE + c * P + (valid ? j0 : 0);   // PP sits at a fixed offset behind PE
                 {   // cyclonic side: rows j0-1, j0-2, ... while some row at or beyond may exceed Q_j
-                    const int* pe_p = PE + c * P + j0;
-                    int pe = valid ? *pe_p : INT_MIN;
+                    const int* pk = kbase;
                     const double* t = tp;
-                    while (__any_sync(FULL, pe >= kqc)) {
-                        t += step; --pe_p;
-                        if (pe >= kqc) {
-                            const double qv = t[0], uv = t[TD], av = t[aa8 - tq];
-                            double nv = 0.0;
-                            if (HAS_NC) nv = t[2 * TD];
-                            pe = *pe_p;
-                            const double diff = qv - Qj;
-                            if (diff > 0.0) {
-                                A1 = __fma_rn(diff, av, A1);
-                                B = __fma_rn(diff, uv, B);
-                                if (HAS_NC) N = __fma_rn(nv, av, N);
-                                if (COUNT) ++cnt_c;
-                            }
+                    bool mine = act && (*pk >= kqc);
+                    while (__any_sync(FULL, mine)) {
+                        if (mine) { t += step; --pk; }     // finished lanes keep re-reading their last row
+                        double qv = t[0], uv = t[TU], av = t[TA], nv = HAS_NC ? t[TN] : 0.0;
+                        const int pe = *pk;
+                        asm volatile("" : "+d"(uv), "+d"(av), "+d"(nv));   // keep the loads ahead of the compare
+                        const double diff = qv - Qj;
+                        if (mine && diff > 0.0) {
+                            A1 = __fma_rn(diff, av, A1);
+                            B = __fma_rn(diff, uv, B);
+                            if (HAS_NC) N = __fma_rn(nv, av, N);
+                            if (COUNT) ++cnt_c;
                         }
+                        mine = mine && (pe >= kqc);
                     }
                 }
                 {   // anticyclonic side: rows j0, j0+1, ... while some row at or beyond may not exceed Q_j
-                    const int* pp_p = PP + c * P + j0;
-                    int pp = valid ? *pp_p : INT_MAX;
+                    const int* pk = kbase + kWinCols * P;
                     const double* t = tp;
-                    while (__any_sync(FULL, pp <= kqa)) {
-                        if (pp <= kqa) {
-                            const double qv = t[0], uv = t[TD], av = t[aa8 - tq];
-                            double nv = 0.0;
-                            if (HAS_NC) nv = t[2 * TD];
-                            pp = pp_p[1];
-                            const double diff = qv - Qj;
-                            if (diff <= 0.0) {
-                                A2 = __fma_rn(-diff, av, A2);
-                                B = __fma_rn(-diff, uv, B);
-                                if (HAS_NC) N = __fma_rn(-nv, av, N);
-                                if (COUNT) ++cnt_a;
-                            }
+                    bool mine = act && (*pk <= kqa);
+                    while (__any_sync(FULL, mine)) {
+                        double qv = t[0], uv = t[TU], av = t[TA], nv = HAS_NC ? t[TN] : 0.0;
+                        const int pp = pk[1];
+                        asm volatile("" : "+d"(uv), "+d"(av), "+d"(nv));
+                        const double diff = qv - Qj;
+                        if (mine && diff <= 0.0) {
+                            A2 = __fma_rn(-diff, av, A2);
+                            B = __fma_rn(-diff, uv, B);
+                            if (HAS_NC) N = __fma_rn(-nv, av, N);
+                            if (COUNT) ++cnt_a;
                         }
-                        t -= step; ++pp_p;
+                        mine = mine && (pp <= kqa);
+                        if (mine) { t -= step; ++pk; }
                     }
                 }
                 if (valid) {
                     // a1 = A1, a2 = A2;  ua2 = a dphi cos(phi_j) B - uref_j (a1 + a2)   (compute_flux_dirinv.f90:96-113)
                     const double lw = A1 + A2;
-                    double x1 = 0.0, u2 = 0.0;
-                    if (act) {
-                        x1 = Uc[j0] * lw;
-                        u2 = __fma_rn(abcs[j0], B, -x1);
-                    }
-                    const bool store = colok && !(fr.skip_first && j0 == 0);
+                    const double x1 = Uc[j0] * lw;                  // inactive rows: lw = B = 0
+                    const double u2 = __fma_rn(abcs[j0], B, -x1);
+                    const bool store = colok && !(gi == 0 && skip00);
+                    double* o = out_k + (long long)gi * out_gstep;
                     if (MODE == 1) {
-                        acc[gi][0] = acc[gi][0] + A1 * wd;
-                        acc[gi][1] = acc[gi][1] + A2 * wd;
-                        acc[gi][2] = acc[gi][2] + x1 * wd;
-                        acc[gi][3] = acc[gi][3] + u2 * wd;
-                        if (HAS_NC) acc[gi][HAS_NC ? 4 : 0] = acc[gi][HAS_NC ? 4 : 0] + N * wd;
-                        if (store)
-                            st_stream(&p.lwa[(size_t)b * p.lwa_batch + (size_t)(k - 1) * p.lwa_plane +
-                                             (size_t)(fr.out_row0 + m) * p.out_pitch + i0 + c], fabs(lw));
+                        acc[gi][0] = __fma_rn(A1, wd, acc[gi][0]);
+                        acc[gi][1] = __fma_rn(A2, wd, acc[gi][1]);
+                        acc[gi][2] = __fma_rn(x1, wd, acc[gi][2]);
+                        acc[gi][3] = __fma_rn(u2, wd, acc[gi][3]);
+                        if (HAS_NC) acc[gi][NACC - 1] = __fma_rn(N, wd, acc[gi][NACC - 1]);
+                        if (store) st_stream(o, fabs(lw));
                     } else if (store) {
-                        const size_t o = (size_t)b * p.out_batch + (size_t)(k - 1) * p.out_plane +
-                                         (size_t)(fr.out_row0 + m) * p.out_pitch + i0 + c;
-                        p.a1[o] = A1;
-                        p.a2[o] = A2;
-                        if (p.u2) p.u2[o] = u2;
-                        if (HAS_NC && p.ncf) p.ncf[o] = N;
+                        const long long d12 = p.a2 - p.a1;
+                        o[0] = A1;
+                        o[d12] = A2;
+                        if (p.u2) o[p.u2 - p.a1] = u2;
+                        if (HAS_NC && p.ncf) o[p.ncf - p.a1] = N;
                     }
                 }
             }
@@ -371,19 +368,18 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     }
 
     if (MODE == 1) {
+        double* o2 = p.out2d + (size_t)b * p.o2_batch + (size_t)(fr.out_row0 + m00) * p.out_pitch + i0 + c;
 #pragma unroll
         for (int gi = 0; gi < kWinGroupsPerWarp; ++gi) {
-            const int hg = w + kWinWarps * gi;
-            const int j0 = 4 * hg + r;
-            if (hg < G && j0 < nd && colok && !(fr.skip_first && j0 == 0)) {
-                const int m = fr.rev ? nd - 1 - j0 : j0;
-                double* o = p.out2d + (size_t)b * p.o2_batch + (size_t)(fr.out_row0 + m) * p.out_pitch + i0 + c;
+            const int j0 = j00 + 4 * kWinWarps * gi;
+            if (j0 < nd && colok && !(gi == 0 && skip00)) {
+                double* o = o2 + (long long)gi * out_gstep;
                 o[(size_t)p.slot_a1 * p.o2_plane] = acc[gi][0];
                 o[(size_t)p.slot_a2 * p.o2_plane] = acc[gi][1];
                 o[(size_t)p.slot_lwa * p.o2_plane] = acc[gi][0] + acc[gi][1];
                 o[(size_t)p.slot_ua1 * p.o2_plane] = acc[gi][2];
                 o[(size_t)p.slot_ua2 * p.o2_plane] = acc[gi][3];
-                if (HAS_NC) o[(size_t)p.slot_ncf * p.o2_plane] = (fr.sg < 0.0) ? -acc[gi][HAS_NC ? 4 : 0] : acc[gi][HAS_NC ? 4 : 0];
+                if (HAS_NC) o[(size_t)p.slot_ncf * p.o2_plane] = (fr.sg < 0.0) ? -acc[gi][NACC - 1] : acc[gi][NACC - 1];
             }
         }
     }
@@ -467,7 +463,7 @@ static int lwa_window_launch(WinArgs a, int mode, const double* pv, const double
     if (mode == 1) a.k_per_cta = a.k_count;
     else a.k_per_cta = std::max(1, std::min(a.k_count, ceil_div((long long)a.k_count * tiles * nprob, 148 * 8)));
     const int chunks = ceil_div(a.k_count, a.k_per_cta);
-    const size_t smem = win_smem_layout(a.nd, nbox, boxrows, nc ? 3 : 2).total;
+    const size_t smem = win_smem_layout(a.nd, nc ? 3 : 2).total;
     dim3 grid(tiles, chunks, nprob);
     FALWA_KERNEL("lwa_window_kernel", st);
     rc = mode == 1 ? win_launch_mode<1>(tq, tu, tn, a, nc != nullptr, grid, smem, st)

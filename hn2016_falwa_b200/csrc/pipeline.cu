@@ -1315,7 +1315,7 @@ static int lwa_fluxes_impl(const falwa_plan* P, int batch, const double* qgpv, c
             else fused_flux_kernel<true><<<grid, block, 0, st>>>(p);
         } else if (use_window) {
             if ((rc = hsum.alloc((size_t)batch * nhemi * nd * nlon, st))) return rc;
-            FALWA_KERNEL("flux_column_kernel", st);
+            FALWA_KERNEL("flux_uvt_column_kernel", st);
             flux_column_kernel<false, true><<<grid, block, 0, st>>>(p, hsum.d);
             flux_column_kernel<true, true><<<dim3(ceil_div(nlon, 256), 2, batch * nhemi), 256, 0, st>>>(p, hsum.d);
         } else if (use_scan) {
