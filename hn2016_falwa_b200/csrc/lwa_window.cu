@@ -29,10 +29,7 @@
 namespace falwa {
 
 constexpr int kWinCols = 8;                                       // longitudes per tile: 64-byte row segments
-constexpr int kWinWarps = 16;
-constexpr int kWinThreads = kWinWarps * 32;
-constexpr int kWinGroupsPerWarp = 6;                              // 4-row groups a warp owns (register accumulators)
-constexpr int kWinMaxRows = 4 * kWinWarps * kWinGroupsPerWarp;    // 384 hemispheric rows (0.25 deg: 361)
+constexpr int kWinMaxRows = 384;                                  // hemispheric rows (0.25 deg: 361): 96 four-row groups
 constexpr int kWinSpan = 13;                                      // rows per lane in the bound scans (odd stride)
 constexpr int kWinKeyPitch = 420;                                 // >= 32 * 13 + 2 and == 4 (mod 32): conflict-free
 
@@ -107,11 +104,35 @@ __host__ __device__ inline WinSmem win_smem_layout(int nd, int nfields) {
     return s;
 }
 
-template <int MODE, bool HAS_NC, bool COUNT>
-__global__ void __launch_bounds__(kWinThreads, 1)
+// One window step of a threshold row: diff = q - Q; in the set (and still inside this lane's window) the pair adds
+// diff * aa to the LWA piece and diff * u to the flux sum.  Written with predicated FMAs (no select chains): a pair
+// outside the set leaves every sum bit-for-bit untouched, whatever its operands are (NaN-safe like the reference's IF).
+template <bool ANTI, bool HAS_NC, bool COUNT>
+__device__ __forceinline__ void win_pair(double qv, double Qj, double av, double uv, double nv, bool mine,
+                                         double& A, double& B, double& N, unsigned& cnt) {
+    unsigned m = mine, c = cnt;
+    if (!ANTI) {
+        asm("{\n\t.reg .pred p, pm;\n\t.reg .f64 d;\n\t"
+            "setp.ne.u32 pm, %6, 0;\n\tsub.rn.f64 d, %4, %5;\n\tsetp.gt.and.f64 p, d, 0d0000000000000000, pm;\n\t"
+            "@p fma.rn.f64 %0, d, %7, %0;\n\t@p fma.rn.f64 %1, d, %8, %1;\n\t@p fma.rn.f64 %2, %9, %7, %2;\n\t@p add.u32 %3, %3, 1;\n\t}"
+            : "+d"(A), "+d"(B), "+d"(N), "+r"(c) : "d"(qv), "d"(Qj), "r"(m), "d"(av), "d"(uv), "d"(nv));
+    } else {
+        asm("{\n\t.reg .pred p, pm;\n\t.reg .f64 d;\n\t"
+            "setp.ne.u32 pm, %6, 0;\n\tsub.rn.f64 d, %5, %4;\n\tsetp.ge.and.f64 p, d, 0d0000000000000000, pm;\n\t"
+            "@p fma.rn.f64 %0, d, %7, %0;\n\t@p fma.rn.f64 %1, d, %8, %1;\n\t@p fma.rn.f64 %2, %9, %7, %2;\n\t@p add.u32 %3, %3, 1;\n\t}"
+            : "+d"(A), "+d"(B), "+d"(N), "+r"(c) : "d"(qv), "d"(Qj), "r"(m), "d"(av), "d"(uv), "d"(-nv));
+    }
+    if (COUNT) cnt = c;
+    (void)HAS_NC;
+}
+
+template <int MODE, bool HAS_NC, bool COUNT, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_u,
                   const __grid_constant__ CUtensorMap tm_n, const WinArgs p) {
     extern __shared__ __align__(1024) unsigned char win_raw[];
+    constexpr int NT = NW * 32;
+    constexpr int GPW = kWinMaxRows / (4 * NW);                          // 4-row groups a warp owns
     constexpr int NF = HAS_NC ? 3 : 2;
     constexpr int P = kWinKeyPitch;
     constexpr int TU = kWinTile, TN = 2 * kWinTile;                      // u, nc relative to q (doubles)
@@ -138,7 +159,6 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     const int kend = min(kbeg + p.k_per_cta, p.k_first + p.k_count);    // exclusive
     const int nlev = kend - kbeg;
     if (nlev <= 0) return;
-    const int G = (nd + 3) >> 2;
     const unsigned box_bytes = (unsigned)(p.boxrows * kWinCols * 8);
 
     auto issue = [&](int li) {   // one elected thread: all boxes of level kbeg + li into stage li & 1
@@ -152,16 +172,11 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             if (HAS_NC) win_tma_load(dst + TN, &tm_n, &bars[s], i0, row, k - 1, b);
         }
     };
-    // thresholds of hemispheric row tid + 1: per-thread base pointers, one level stride
+    // thresholds of hemispheric row tid + 1: per-thread source pointers, one level stride
     const bool trow = tid < nd && tid + 1 >= p.jstart && tid + 1 <= p.jend;
     const double* qsrc = trow ? p.qref + (size_t)b * p.q_batch + p.q_row0[h] + p.q_rstep[h] * tid : nullptr;
     const double* usrc = (trow && p.uref) ? p.uref + (size_t)b * p.u_batch + p.u_row0[h] + p.u_rstep[h] * tid : nullptr;
     const double qsg = p.q_sg[h];
-    auto table_fetch = [&](int k, double& Q, double& U) {
-        Q = 0.0; U = 0.0;
-        if (qsrc) Q = __fma_rn(qsg, qsrc[(size_t)(k - 1) * p.q_kstride], 0.0);
-        if (usrc) U = usrc[(size_t)(k - 1) * p.u_kstride];
-    };
 
     if (tid == 0) {
         win_mbar_init(&bars[0], 1);
@@ -173,22 +188,23 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         issue(0);
         if (nlev > 1) issue(1);
     }
-    for (int t = tid; t < nd * kWinCols; t += kWinThreads) {   // a dphi cos(phi) of every tile row, both stages
+    for (int t = tid; t < nd * kWinCols; t += NT) {   // a dphi cos(phi) of every tile row
         const int m = t >> 3;
         const double v = p.ab * p.cosphi[fr.rev ? nd - m : m + 1];
         tiles[(HAS_NC ? 3 : 2) * kWinTile + t] = v;
         if (!HAS_NC) tiles[5 * kWinTile + t] = v;
     }
-    for (int t = nd + tid; t < kWinSpan * 32; t += kWinThreads)   // rows beyond the column: neutral for the minima
+    for (int t = nd + tid; t < kWinSpan * 32; t += NT)   // rows beyond the column: neutral for the minima
 #pragma unroll
         for (int cc = 0; cc < kWinCols; ++cc) keys[cc * P + t] = INT_MAX;
     if (tid < nd) {
         abcs[tid] = p.ab * p.cosphi[tid + 1];
-        table_fetch(kbeg, Qh[tid], Ur[tid]);
+        Qh[tid] = qsrc ? __fma_rn(qsg, qsrc[(size_t)(kbeg - 1) * p.q_kstride], 0.0) : 0.0;
+        Ur[tid] = usrc ? usrc[(size_t)(kbeg - 1) * p.u_kstride] : 0.0;
     }
     if (tid < kWinCols) { PE[tid * P] = INT_MIN; PP[tid * P + nd] = INT_MAX; }
     if (MODE == 1) {   // levels 1 and kmax of the 3-D LWA are zero (compute_flux_dirinv.f90 touches k = 2 .. kmax-1)
-        for (int t = tid; t < nd * kWinCols; t += kWinThreads) {
+        for (int t = tid; t < nd * kWinCols; t += NT) {
             const int m = t >> 3, cc = t & 7;
             const int j0 = fr.rev ? nd - 1 - m : m;
             if (i0 + cc < p.imax && !(fr.skip_first && j0 == 0)) {
@@ -200,46 +216,68 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     }
 
     constexpr int NACC = HAS_NC ? 5 : 4;
-    double acc[kWinGroupsPerWarp][NACC];
+    double acc[GPW][NACC];
 #pragma unroll
-    for (int gi = 0; gi < kWinGroupsPerWarp; ++gi)
+    for (int gi = 0; gi < GPW; ++gi)
 #pragma unroll
         for (int x = 0; x < NACC; ++x) acc[gi][x] = 0.0;
     unsigned cnt_c = 0, cnt_a = 0;
-    const int step = fr.rev ? kWinCols : -kWinCols;   // doubles per row step toward the equator
-    const int jstart = p.jstart, jend = p.jend;
-    // this lane's element of group 0 of its warp; groups of a warp are 16 groups = 64 rows apart
+    // this lane's element of group 0 of its warp; groups of a warp are NW groups = 4 NW rows apart.  What a lane does
+    // for a group does not depend on the level: one bit per group.
     const int j00 = 4 * w + r;
     const int m00 = fr.rev ? nd - 1 - j00 : j00;
-    const int mstep = fr.rev ? -4 * kWinWarps : 4 * kWinWarps;          // tile rows between consecutive groups of a warp
+    const int mstep = fr.rev ? -4 * NW : 4 * NW;                      // tile rows between consecutive groups of a warp
+    unsigned validm = 0, actm = 0, storem = 0;
+#pragma unroll
+    for (int gi = 0; gi < GPW; ++gi) {
+        const int j0 = j00 + 4 * NW * gi;
+        const bool valid = j0 < nd;
+        if (valid) validm |= 1u << gi;
+        if (valid && colok && j0 + 1 >= p.jstart && j0 + 1 <= p.jend) actm |= 1u << gi;
+        if (valid && colok && !(fr.skip_first && j0 == 0)) storem |= 1u << gi;
+    }
+    const int ngroups = (nd - 4 * w + 4 * NW - 1) / (4 * NW);            // groups of this warp that exist (warp-uniform)
+    const int step = fr.rev ? kWinCols : -kWinCols;                      // doubles per row step toward the equator
     double* const out_base = (MODE == 1 ? p.lwa + (size_t)b * p.lwa_batch : p.a1 + (size_t)b * p.out_batch) +
                              (size_t)(fr.out_row0 + m00) * p.out_pitch + i0 + c;
     const size_t out_lev = (MODE == 1) ? p.lwa_plane : p.out_plane;
     const long long out_gstep = (long long)mstep * p.out_pitch;
-    const bool skip00 = fr.skip_first && j00 == 0;
+    const int toff0 = m00 * kWinCols + c;                                // this lane's element of group 0 in a tile
+    const int koff0 = c * P + j00;                                       // ... and its key
 
+    double wd = (MODE == 1) ? p.vw[kbeg - 1] * p.dc : 0.0;
     for (int li = 0; li < nlev; ++li) {
         const int s = li & 1, k = kbeg + li;
         double* const tq = tiles + (size_t)s * SD;
         const int TA = HAS_NC ? (s ? -kWinTile : 3 * kWinTile) : 2 * kWinTile;   // aa8 relative to q of this stage
         const double* const Qc = Qh + s * nd;   // table buffers alternate with the level like the tile stages
         const double* const Uc = Ur + s * nd;
-        // thresholds of the next level travel while this one is computed
-        double Qn = 0.0, Un = 0.0;
-        if (li + 1 < nlev) table_fetch(k + 1, Qn, Un);
+        // thresholds and weight of the next level travel while this one is computed
+        const bool more = li + 1 < nlev;
+        double Qn = 0.0, Un = 0.0, wdn = 0.0;
+        if (more && qsrc) Qn = qsrc[(size_t)k * p.q_kstride];
+        if (more && usrc) Un = usrc[(size_t)k * p.u_kstride];
+        if (MODE == 1 && more) wdn = p.vw[k];
         win_mbar_wait(&bars[s], (unsigned)((li >> 1) & 1));
 
         // ---- phase 1: hemispheric-frame PV (sign, -0 -> +0) and its keys ---------------------------
         {
-            double* tp = tq + m00 * kWinCols + c;
-            int* kp = keys + c * P + j00;
-            for (int j0 = j00; j0 < nd; j0 += 4 * kWinWarps, tp += mstep * kWinCols, kp += 4 * kWinWarps) {
-                const double q = __fma_rn(fr.sg, *tp, 0.0);
-                if (fr.sg != 1.0) *tp = q;
-                *kp = win_key(q);
+            double* tp = tq + toff0;
+            int* kp = keys + koff0;
+#pragma unroll
+            for (int gi = 0; gi < GPW; ++gi) {
+                if ((validm >> gi) & 1) {
+                    const double q = __fma_rn(fr.sg, tp[gi * mstep * kWinCols], 0.0);
+                    if (fr.sg != 1.0) tp[gi * mstep * kWinCols] = q;
+                    kp[gi * 4 * NW] = win_key(q);
+                }
             }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // see the TMA issue below
         __syncthreads();
+        // Every warp has finished the previous level: its stage is free.  The load of level li + 1 has the rest of
+        // this level to land.
+        if (tid == 0 && li >= 1 && more) issue(li + 1);
         // ---- phase 2: the two monotone bound arrays of every column, one warp per (column, direction) -
         {
             int incl[kWinSpan];
@@ -279,37 +317,28 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         }
         __syncthreads();
         // ---- main: the two windowed sums of every threshold row ----------------------------------------
-        const double wd = (MODE == 1) ? p.vw[k - 1] * p.dc : 0.0;
-        double* out_k = out_base + (size_t)(k - 1) * out_lev;
+        double* const out_k = out_base + (size_t)(k - 1) * out_lev;
 #pragma unroll
-        for (int gi = 0; gi < kWinGroupsPerWarp; ++gi) {
-            const int j0 = j00 + 4 * kWinWarps * gi;
-            if (4 * (w + kWinWarps * gi) < nd) {   // warp-uniform: the group exists
-                const bool valid = j0 < nd;
-                const bool act = valid && colok && (j0 + 1 >= jstart) && (j0 + 1 <= jend);
-                const double Qj = valid ? Qc[j0] : 0.0;
+        for (int gi = 0; gi < GPW; ++gi) {
+            if (gi < ngroups) {   // warp-uniform
+                const bool valid = (validm >> gi) & 1, act = (actm >> gi) & 1;
+                const int j0 = valid ? j00 + 4 * NW * gi : 0;              // lanes past the last row idle on row 0
+                const double Qj = Qc[j0];
                 const int kq = win_key(Qj);
                 const int kqc = max(kq, INT_MIN + 1);   // "may exceed Q_j":      key >= kqc  (never true at PE[0])
                 const int kqa = min(kq, INT_MAX - 1);   // "may not exceed Q_j":  key <= kqa  (never true at PP[nd])
                 double A1 = 0.0, A2 = 0.0, B = 0.0, N = 0.0;
-                const double* const tp = tq + (valid ? m00 + mstep * gi : 0) * kWinCols + c;
-                const int* const kbase = PE + c * P + (valid ? j0 : 0);   // PP sits at a fixed offset behind PE
+                const double* const tp = tq + (valid ? toff0 + gi * mstep * kWinCols : c);
+                const int* const kbase = PE + c * P + j0;   // PP sits at a fixed offset behind PE
                 {   // cyclonic side: rows j0-1, j0-2, ... while some row at or beyond may exceed Q_j
                     const int* pk = kbase;
                     const double* t = tp;
                     bool mine = act && (*pk >= kqc);
                     while (__any_sync(FULL, mine)) {
                         if (mine) { t += step; --pk; }     // finished lanes keep re-reading their last row
-                        double qv = t[0], uv = t[TU], av = t[TA], nv = HAS_NC ? t[TN] : 0.0;
+                        const double qv = t[0], uv = t[TU], av = t[TA], nv = HAS_NC ? t[TN] : 0.0;
                         const int pe = *pk;
-                        asm volatile("" : "+d"(uv), "+d"(av), "+d"(nv));   // keep the loads ahead of the compare
-                        const double diff = qv - Qj;
-                        if (mine && diff > 0.0) {
-                            A1 = __fma_rn(diff, av, A1);
-                            B = __fma_rn(diff, uv, B);
-                            if (HAS_NC) N = __fma_rn(nv, av, N);
-                            if (COUNT) ++cnt_c;
-                        }
+                        win_pair<false, HAS_NC, COUNT>(qv, Qj, av, uv, nv, mine, A1, B, N, cnt_c);
                         mine = mine && (pe >= kqc);
                     }
                 }
@@ -318,16 +347,9 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     const double* t = tp;
                     bool mine = act && (*pk <= kqa);
                     while (__any_sync(FULL, mine)) {
-                        double qv = t[0], uv = t[TU], av = t[TA], nv = HAS_NC ? t[TN] : 0.0;
+                        const double qv = t[0], uv = t[TU], av = t[TA], nv = HAS_NC ? t[TN] : 0.0;
                         const int pp = pk[1];
-                        asm volatile("" : "+d"(uv), "+d"(av), "+d"(nv));
-                        const double diff = qv - Qj;
-                        if (mine && diff <= 0.0) {
-                            A2 = __fma_rn(-diff, av, A2);
-                            B = __fma_rn(-diff, uv, B);
-                            if (HAS_NC) N = __fma_rn(-nv, av, N);
-                            if (COUNT) ++cnt_a;
-                        }
+                        win_pair<true, HAS_NC, COUNT>(qv, Qj, av, uv, nv, mine, A2, B, N, cnt_a);
                         mine = mine && (pp <= kqa);
                         if (mine) { t -= step; ++pk; }
                     }
@@ -337,7 +359,7 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     const double lw = A1 + A2;
                     const double x1 = Uc[j0] * lw;                  // inactive rows: lw = B = 0
                     const double u2 = __fma_rn(abcs[j0], B, -x1);
-                    const bool store = colok && !(gi == 0 && skip00);
+                    const bool store = (storem >> gi) & 1;
                     double* o = out_k + (long long)gi * out_gstep;
                     if (MODE == 1) {
                         acc[gi][0] = __fma_rn(A1, wd, acc[gi][0]);
@@ -347,9 +369,8 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                         if (HAS_NC) acc[gi][NACC - 1] = __fma_rn(N, wd, acc[gi][NACC - 1]);
                         if (store) st_stream(o, fabs(lw));
                     } else if (store) {
-                        const long long d12 = p.a2 - p.a1;
                         o[0] = A1;
-                        o[d12] = A2;
+                        o[p.a2 - p.a1] = A2;
                         if (p.u2) o[p.u2 - p.a1] = u2;
                         if (HAS_NC && p.ncf) o[p.ncf - p.a1] = N;
                     }
@@ -357,22 +378,18 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             }
         }
         // next level's thresholds into the other table buffer (its last readers finished a level ago)
-        if (li + 1 < nlev && tid < nd) {
-            Qh[(s ^ 1) * nd + tid] = Qn;
+        if (more && tid < nd) {
+            Qh[(s ^ 1) * nd + tid] = __fma_rn(qsg, Qn, 0.0);
             Ur[(s ^ 1) * nd + tid] = Un;
         }
-        // the tile of this stage is rewritten by the async proxy next: order the generic accesses before it
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (tid == 0 && li + 2 < nlev) issue(li + 2);
+        wd = wdn * p.dc;
     }
 
     if (MODE == 1) {
         double* o2 = p.out2d + (size_t)b * p.o2_batch + (size_t)(fr.out_row0 + m00) * p.out_pitch + i0 + c;
 #pragma unroll
-        for (int gi = 0; gi < kWinGroupsPerWarp; ++gi) {
-            const int j0 = j00 + 4 * kWinWarps * gi;
-            if (j0 < nd && colok && !(gi == 0 && skip00)) {
+        for (int gi = 0; gi < GPW; ++gi) {
+            if ((storem >> gi) & 1) {
                 double* o = o2 + (long long)gi * out_gstep;
                 o[(size_t)p.slot_a1 * p.o2_plane] = acc[gi][0];
                 o[(size_t)p.slot_a2 * p.o2_plane] = acc[gi][1];
@@ -434,17 +451,17 @@ static bool win_supported(int imax, int nd, const void* pv, const void* uu, cons
     return nd >= 4 && nd <= kWinMaxRows && (imax % 2 == 0) && al(pv) && al(uu) && (!nc || al(nc)) && win_encoder() != nullptr;
 }
 
-template <int MODE>
+template <int MODE, int NW>
 static int win_launch_mode(const CUtensorMap& tq, const CUtensorMap& tu, const CUtensorMap& tn, const WinArgs& a, bool has_nc,
                            dim3 grid, size_t smem, cudaStream_t st) {
     auto go = [&](auto kern) -> int {
         FALWA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kWinThreads, smem, st>>>(tq, tu, tn, a);
+        kern<<<grid, NW * 32, smem, st>>>(tq, tu, tn, a);
         return 0;
     };
     const bool count = a.mask_count != nullptr;
-    if (has_nc) return count ? go(lwa_window_kernel<MODE, true, true>) : go(lwa_window_kernel<MODE, true, false>);
-    return count ? go(lwa_window_kernel<MODE, false, true>) : go(lwa_window_kernel<MODE, false, false>);
+    if (has_nc) return count ? go(lwa_window_kernel<MODE, true, true, NW>) : go(lwa_window_kernel<MODE, true, false, NW>);
+    return count ? go(lwa_window_kernel<MODE, false, true, NW>) : go(lwa_window_kernel<MODE, false, false, NW>);
 }
 
 // pv / uu / nc: [batch][kmax][in_rows][imax]; a.k_first / k_count / frames / thresholds / outputs filled by the caller
@@ -466,8 +483,10 @@ static int lwa_window_launch(WinArgs a, int mode, const double* pv, const double
     const size_t smem = win_smem_layout(a.nd, nc ? 3 : 2).total;
     dim3 grid(tiles, chunks, nprob);
     FALWA_KERNEL("lwa_window_kernel", st);
-    rc = mode == 1 ? win_launch_mode<1>(tq, tu, tn, a, nc != nullptr, grid, smem, st)
-                   : win_launch_mode<0>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
+    static const int nw = tune_int("FALWA_WIN_WARPS", 16);
+    if (mode == 1 && nw == 24) rc = win_launch_mode<1, 24>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
+    else rc = mode == 1 ? win_launch_mode<1, 16>(tq, tu, tn, a, nc != nullptr, grid, smem, st)
+                        : win_launch_mode<0, 16>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
     if (rc) return rc;
     FALWA_LAUNCH_CHECK();
     return 0;
