@@ -99,10 +99,50 @@ __host__ __device__ inline WinSmem win_smem_layout(int nd, int nfields) {
     s.off_q = o; o += (size_t)2 * nd * 8;
     s.off_u = o; o += (size_t)2 * nd * 8;
     s.off_cs = o; o += (size_t)nd * 8;
-    s.off_bar = o; o += 16;
+    s.off_bar = o; o += 32;
     s.total = o;
     return s;
 }
+
+// ---- tensor memory as the accumulator file -----------------------------------------------------------------------
+// The vertical sums of a CTA (4 per grid point of its tile: 92 KB at 0.25 deg) do not fit beside the tiles in shared
+// memory, and kept in registers they push the kernel to its register limit (the compiler re-derives addresses instead
+// of holding them).  Nothing here uses the tensor cores, so their 256 KB of tensor memory per SM is free: every thread
+// owns 8 (10 with ncforce) 32-bit columns of its own TMEM lane per group and updates them once per level with
+// tcgen05.ld / tcgen05.st.  A warp reaches lanes 32 (warp % 4) .. + 31 only; warps that share a lane quarter use
+// different columns.
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, unsigned ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(win_smem(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, unsigned ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, double& a) {
+    uint32_t v0, v1;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    a = __hiloint2double((int)v1, (int)v0);
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, double a) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};"
+                 ::"r"(taddr), "r"(__double2loint(a)), "r"(__double2hiint(a)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, double (&a)[4]) {
+    uint32_t v[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int x = 0; x < 4; ++x) a[x] = __hiloint2double((int)v[2 * x + 1], (int)v[2 * x]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const double (&a)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(__double2loint(a[0])), "r"(__double2hiint(a[0])), "r"(__double2loint(a[1])),
+                 "r"(__double2hiint(a[1])), "r"(__double2loint(a[2])), "r"(__double2hiint(a[2])),
+                 "r"(__double2loint(a[3])), "r"(__double2hiint(a[3])) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // One window step of a threshold row: diff = q - Q; in the set (and still inside this lane's window) the pair adds
 // diff * aa to the LWA piece and diff * u to the flux sum.  Written with predicated FMAs (no select chains): a pair
@@ -215,12 +255,25 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         }
     }
 
-    constexpr int NACC = HAS_NC ? 5 : 4;
-    double acc[GPW][NACC];
+    // accumulator file in tensor memory (MODE 1): this thread's columns of group gi start at tacc + gi * TCOL
+    constexpr int TCOL = HAS_NC ? 10 : 8;
+    constexpr unsigned TMEM_COLS = (NW / 4) * GPW * TCOL <= 256 ? 256 : 512;
+    uint32_t tacc = 0;
+    if (MODE == 1) {
+        uint32_t* tbase = reinterpret_cast<uint32_t*>(bars + 2);
+        if (w == 0) tmem_alloc(tbase, TMEM_COLS);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tacc = *tbase + ((uint32_t)((w & 3) * 32) << 16) + (uint32_t)((w >> 2) * GPW * TCOL);
+        const double zero[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int gi = 0; gi < GPW; ++gi)
-#pragma unroll
-        for (int x = 0; x < NACC; ++x) acc[gi][x] = 0.0;
+        for (int gi = 0; gi < GPW; ++gi) {
+            tmem_st8(tacc + gi * TCOL, zero);
+            if (HAS_NC) tmem_st2(tacc + gi * TCOL + 8, 0.0);
+        }
+        tmem_wait_st();
+    }
     unsigned cnt_c = 0, cnt_a = 0;
     // this lane's element of group 0 of its warp; groups of a warp are NW groups = 4 NW rows apart.  What a lane does
     // for a group does not depend on the level: one bit per group.
@@ -236,6 +289,7 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         if (valid && colok && j0 + 1 >= p.jstart && j0 + 1 <= p.jend) actm |= 1u << gi;
         if (valid && colok && !(fr.skip_first && j0 == 0)) storem |= 1u << gi;
     }
+    asm volatile("" : "+r"(validm), "+r"(actm), "+r"(storem));          // keep the bits; do not re-derive them per level
     const int ngroups = (nd - 4 * w + 4 * NW - 1) / (4 * NW);            // groups of this warp that exist (warp-uniform)
     const int step = fr.rev ? kWinCols : -kWinCols;                      // doubles per row step toward the equator
     double* const out_base = (MODE == 1 ? p.lwa + (size_t)b * p.lwa_batch : p.a1 + (size_t)b * p.out_batch) +
@@ -354,19 +408,27 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                         if (mine) { t -= step; ++pk; }
                     }
                 }
-                if (valid) {
+                {
                     // a1 = A1, a2 = A2;  ua2 = a dphi cos(phi_j) B - uref_j (a1 + a2)   (compute_flux_dirinv.f90:96-113)
+                    // (lanes past the last row and inactive rows carry A1 = A2 = B = N = 0 and add nothing)
                     const double lw = A1 + A2;
-                    const double x1 = Uc[j0] * lw;                  // inactive rows: lw = B = 0
+                    const double x1 = Uc[j0] * lw;
                     const double u2 = __fma_rn(abcs[j0], B, -x1);
                     const bool store = (storem >> gi) & 1;
                     double* o = out_k + (long long)gi * out_gstep;
                     if (MODE == 1) {
-                        acc[gi][0] = __fma_rn(A1, wd, acc[gi][0]);
-                        acc[gi][1] = __fma_rn(A2, wd, acc[gi][1]);
-                        acc[gi][2] = __fma_rn(x1, wd, acc[gi][2]);
-                        acc[gi][3] = __fma_rn(u2, wd, acc[gi][3]);
-                        if (HAS_NC) acc[gi][NACC - 1] = __fma_rn(N, wd, acc[gi][NACC - 1]);
+                        double a[4];
+                        tmem_ld8(tacc + gi * TCOL, a);
+                        a[0] = __fma_rn(A1, wd, a[0]);
+                        a[1] = __fma_rn(A2, wd, a[1]);
+                        a[2] = __fma_rn(x1, wd, a[2]);
+                        a[3] = __fma_rn(u2, wd, a[3]);
+                        tmem_st8(tacc + gi * TCOL, a);
+                        if (HAS_NC) {
+                            double an;
+                            tmem_ld2(tacc + gi * TCOL + 8, an);
+                            tmem_st2(tacc + gi * TCOL + 8, __fma_rn(N, wd, an));
+                        }
                         if (store) st_stream(o, fabs(lw));
                     } else if (store) {
                         o[0] = A1;
@@ -383,22 +445,29 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             Ur[(s ^ 1) * nd + tid] = Un;
         }
         wd = wdn * p.dc;
+        if (MODE == 1) tmem_wait_st();
     }
 
     if (MODE == 1) {
         double* o2 = p.out2d + (size_t)b * p.o2_batch + (size_t)(fr.out_row0 + m00) * p.out_pitch + i0 + c;
 #pragma unroll
         for (int gi = 0; gi < GPW; ++gi) {
+            double a[4], an = 0.0;
+            tmem_ld8(tacc + gi * TCOL, a);
+            if (HAS_NC) tmem_ld2(tacc + gi * TCOL + 8, an);
             if ((storem >> gi) & 1) {
                 double* o = o2 + (long long)gi * out_gstep;
-                o[(size_t)p.slot_a1 * p.o2_plane] = acc[gi][0];
-                o[(size_t)p.slot_a2 * p.o2_plane] = acc[gi][1];
-                o[(size_t)p.slot_lwa * p.o2_plane] = acc[gi][0] + acc[gi][1];
-                o[(size_t)p.slot_ua1 * p.o2_plane] = acc[gi][2];
-                o[(size_t)p.slot_ua2 * p.o2_plane] = acc[gi][3];
-                if (HAS_NC) o[(size_t)p.slot_ncf * p.o2_plane] = (fr.sg < 0.0) ? -acc[gi][NACC - 1] : acc[gi][NACC - 1];
+                o[(size_t)p.slot_a1 * p.o2_plane] = a[0];
+                o[(size_t)p.slot_a2 * p.o2_plane] = a[1];
+                o[(size_t)p.slot_lwa * p.o2_plane] = a[0] + a[1];
+                o[(size_t)p.slot_ua1 * p.o2_plane] = a[2];
+                o[(size_t)p.slot_ua2 * p.o2_plane] = a[3];
+                if (HAS_NC) o[(size_t)p.slot_ncf * p.o2_plane] = (fr.sg < 0.0) ? -an : an;
             }
         }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (w == 0) tmem_dealloc(*reinterpret_cast<uint32_t*>(bars + 2), TMEM_COLS);
     }
     if (COUNT && p.mask_count) {
         cnt_c = __reduce_add_sync(FULL, cnt_c);
@@ -485,6 +554,7 @@ static int lwa_window_launch(WinArgs a, int mode, const double* pv, const double
     FALWA_KERNEL("lwa_window_kernel", st);
     static const int nw = tune_int("FALWA_WIN_WARPS", 16);
     if (mode == 1 && nw == 24) rc = win_launch_mode<1, 24>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
+    else if (mode == 1 && nw == 32) rc = win_launch_mode<1, 32>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
     else rc = mode == 1 ? win_launch_mode<1, 16>(tq, tu, tn, a, nc != nullptr, grid, smem, st)
                         : win_launch_mode<0, 16>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
     if (rc) return rc;
