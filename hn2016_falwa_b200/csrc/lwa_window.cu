@@ -86,23 +86,38 @@ __device__ __forceinline__ int win_key(double x) {
 // Shared-memory plan.  The tile stride is a compile-time constant so that, from the address of q(row, col), the
 // operands u(row, col) and aa(row) sit at immediate offsets (one address register per window step).
 constexpr int kWinTile = kWinMaxRows * kWinCols;     // doubles of one (rows x 8) tile slot
-// Without ncforce: [q0 | u0 | aa | q1 | u1 | aa];  with: [q0 | u0 | n0 | aa | q1 | u1 | n1] (one aa8 between the stages).
+// Bound arrays first, then the tiles — without ncforce [q0 | u0 | aa | q1 | u1 | aa], with it [q0 | u0 | n0 | aa | q1 | u1 | n1]
+// (one aa8 between the stages) — then the per-level tables.  Lanes of the last group that lie past the last row compute
+// on whatever sits at their (in-bounds, thanks to this order and the tail pad) addresses and never store.
 struct WinSmem {
-    size_t off_keys, off_pe, off_pp, off_q, off_u, off_cs, off_bar, total;
+    size_t off_keys, off_pe, off_pp, off_tiles, off_q, off_u, off_cs, off_bar, total;
 };
 __host__ __device__ inline WinSmem win_smem_layout(int nd, int nfields) {
     WinSmem s;
-    size_t o = (size_t)(nfields == 3 ? 7 : 6) * kWinTile * 8;
+    size_t o = 0;
     s.off_keys = o; o += (size_t)kWinCols * kWinKeyPitch * 4;
     s.off_pe = o; o += (size_t)kWinCols * kWinKeyPitch * 4;
     s.off_pp = o; o += (size_t)kWinCols * kWinKeyPitch * 4;
+    s.off_tiles = o; o += (size_t)(nfields == 3 ? 7 : 6) * kWinTile * 8;
     s.off_q = o; o += (size_t)2 * nd * 8;
     s.off_u = o; o += (size_t)2 * nd * 8;
     s.off_cs = o; o += (size_t)nd * 8;
     s.off_bar = o; o += 32;
-    s.total = o;
+    s.total = o + 256;
     return s;
 }
+
+// shared-memory accesses with explicit 32-bit addresses (the hot loops carry one address register per operand stream)
+__device__ __forceinline__ double lds64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+template <int OFF> __device__ __forceinline__ double lds64o(uint32_t a) {
+    double v; asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF)); return v;
+}
+__device__ __forceinline__ int lds32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+template <int OFF> __device__ __forceinline__ int lds32o(uint32_t a) {
+    int v; asm volatile("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF)); return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 // ---- tensor memory as the accumulator file -----------------------------------------------------------------------
 // The vertical sums of a CTA (4 per grid point of its tile: 92 KB at 0.25 deg) do not fit beside the tiles in shared
@@ -180,7 +195,7 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     constexpr unsigned FULL = 0xffffffffu;
     const int nd = p.nd;
     const WinSmem L = win_smem_layout(nd, NF);
-    double* tiles = reinterpret_cast<double*>(win_raw);                 // [stage][q | u | aa8 | nc][rows][8]
+    double* tiles = reinterpret_cast<double*>(win_raw + L.off_tiles);   // [stage][q | u | aa8 | nc][rows][8]
     int* keys = reinterpret_cast<int*>(win_raw + L.off_keys);           // [8][P], hemispheric row index
     int* PE = reinterpret_cast<int*>(win_raw + L.off_pe);               // [8][P]: PE[x] = max key of rows < x
     int* PP = reinterpret_cast<int*>(win_raw + L.off_pp);               // [8][P]: PP[x] = min key of rows >= x
@@ -291,21 +306,31 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     }
     asm volatile("" : "+r"(validm), "+r"(actm), "+r"(storem));          // keep the bits; do not re-derive them per level
     const int ngroups = (nd - 4 * w + 4 * NW - 1) / (4 * NW);            // groups of this warp that exist (warp-uniform)
-    const int step = fr.rev ? kWinCols : -kWinCols;                      // doubles per row step toward the equator
-    double* const out_base = (MODE == 1 ? p.lwa + (size_t)b * p.lwa_batch : p.a1 + (size_t)b * p.out_batch) +
-                             (size_t)(fr.out_row0 + m00) * p.out_pitch + i0 + c;
-    const size_t out_lev = (MODE == 1) ? p.lwa_plane : p.out_plane;
-    const long long out_gstep = (long long)mstep * p.out_pitch;
-    const int toff0 = m00 * kWinCols + c;                                // this lane's element of group 0 in a tile
-    const int koff0 = c * P + j00;                                       // ... and its key
+    // Everything the level walk needs is held as 32-bit shared addresses / 64-bit global pointers that the compiler
+    // must treat as opaque values (it otherwise re-derives them from the kernel parameters in every group).
+    uint32_t stepb = fr.rev ? 64u : 0xffffffc0u;                         // bytes per row step toward the equator
+    uint32_t gbytes = (uint32_t)(mstep * kWinCols * 8);                  // bytes between consecutive groups of a warp
+    uint32_t a_t0 = win_smem(tiles) + (uint32_t)((m00 * kWinCols + c) * 8);   // this lane's element of group 0, stage 0
+    uint32_t a_key = win_smem(keys) + (uint32_t)((c * P + j00) * 4);     // ... its key; PE / PP follow at fixed offsets
+    uint32_t a_tab = win_smem(Qh) + (uint32_t)(j00 * 8);                 // ... its threshold; Ur / abcs at fixed offsets
+    const uint32_t o_ur = (uint32_t)((Ur - Qh) * 8), o_cs = (uint32_t)((abcs - Qh) * 8);
+    double* out_k = (MODE == 1 ? p.lwa + (size_t)b * p.lwa_batch + (size_t)(kbeg - 1) * p.lwa_plane
+                               : p.a1 + (size_t)b * p.out_batch + (size_t)(kbeg - 1) * p.out_plane) +
+                    (size_t)(fr.out_row0 + m00) * p.out_pitch + i0 + c;
+    long long out_lev = (long long)((MODE == 1) ? p.lwa_plane : p.out_plane);
+    long long out_gstep = (long long)mstep * p.out_pitch;
+    asm volatile("" : "+r"(stepb), "+r"(gbytes), "+r"(a_t0), "+r"(a_key), "+r"(a_tab), "+l"(out_k), "+l"(out_lev), "+l"(out_gstep));
+    constexpr int KPE = kWinCols * P * 4, KPP = 2 * kWinCols * P * 4;    // PE, PP relative to keys (bytes)
+    constexpr int GK = 4 * NW * 4, GT = 4 * NW * 8;                      // key / table bytes between groups of a warp
+    const double sgn = fr.sg;
 
     double wd = (MODE == 1) ? p.vw[kbeg - 1] * p.dc : 0.0;
     for (int li = 0; li < nlev; ++li) {
         const int s = li & 1, k = kbeg + li;
-        double* const tq = tiles + (size_t)s * SD;
-        const int TA = HAS_NC ? (s ? -kWinTile : 3 * kWinTile) : 2 * kWinTile;   // aa8 relative to q of this stage
-        const double* const Qc = Qh + s * nd;   // table buffers alternate with the level like the tile stages
-        const double* const Uc = Ur + s * nd;
+        uint32_t a_t = a_t0 + (uint32_t)(s * SD * 8);                     // this lane's element of group 0 in this stage
+        uint32_t a_q = a_tab + (uint32_t)(s * nd * 8);                    // table buffers alternate like the tile stages
+        asm volatile("" : "+r"(a_t), "+r"(a_q));
+        const uint32_t TAb = (uint32_t)((HAS_NC ? (s ? -kWinTile : 3 * kWinTile) : 2 * kWinTile) * 8);   // aa8 from q
         // thresholds and weight of the next level travel while this one is computed
         const bool more = li + 1 < nlev;
         double Qn = 0.0, Un = 0.0, wdn = 0.0;
@@ -316,16 +341,16 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 
         // ---- phase 1: hemispheric-frame PV (sign, -0 -> +0) and its keys ---------------------------
         {
-            double* tp = tq + toff0;
-            int* kp = keys + koff0;
+            double q[GPW];
 #pragma unroll
-            for (int gi = 0; gi < GPW; ++gi) {
+            for (int gi = 0; gi < GPW; ++gi) q[gi] = ((validm >> gi) & 1) ? lds64(a_t + gi * gbytes) : 0.0;
+#pragma unroll
+            for (int gi = 0; gi < GPW; ++gi)
                 if ((validm >> gi) & 1) {
-                    const double q = __fma_rn(fr.sg, tp[gi * mstep * kWinCols], 0.0);
-                    if (fr.sg != 1.0) tp[gi * mstep * kWinCols] = q;
-                    kp[gi * 4 * NW] = win_key(q);
+                    const double qh = __fma_rn(sgn, q[gi], 0.0);
+                    if (sgn != 1.0) sts64(a_t + gi * gbytes, qh);
+                    sts32(a_key + gi * GK, win_key(qh));
                 }
-            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // see the TMA issue below
         __syncthreads();
@@ -371,51 +396,48 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         }
         __syncthreads();
         // ---- main: the two windowed sums of every threshold row ----------------------------------------
-        double* const out_k = out_base + (size_t)(k - 1) * out_lev;
+        double* o = out_k;
 #pragma unroll
         for (int gi = 0; gi < GPW; ++gi) {
             if (gi < ngroups) {   // warp-uniform
-                const bool valid = (validm >> gi) & 1, act = (actm >> gi) & 1;
-                const int j0 = valid ? j00 + 4 * NW * gi : 0;              // lanes past the last row idle on row 0
-                const double Qj = Qc[j0];
+                const bool act = (actm >> gi) & 1;
+                const uint32_t at = a_t + gi * gbytes, ak = a_key + gi * GK, aq = a_q + gi * GT;
+                const double Qj = lds64(aq);
                 const int kq = win_key(Qj);
                 const int kqc = max(kq, INT_MIN + 1);   // "may exceed Q_j":      key >= kqc  (never true at PE[0])
                 const int kqa = min(kq, INT_MAX - 1);   // "may not exceed Q_j":  key <= kqa  (never true at PP[nd])
                 double A1 = 0.0, A2 = 0.0, B = 0.0, N = 0.0;
-                const double* const tp = tq + (valid ? toff0 + gi * mstep * kWinCols : c);
-                const int* const kbase = PE + c * P + j0;   // PP sits at a fixed offset behind PE
                 {   // cyclonic side: rows j0-1, j0-2, ... while some row at or beyond may exceed Q_j
-                    const int* pk = kbase;
-                    const double* t = tp;
-                    bool mine = act && (*pk >= kqc);
+                    uint32_t t = at, pk = ak;
+                    bool mine = act && (lds32o<KPE>(pk) >= kqc);
                     while (__any_sync(FULL, mine)) {
-                        if (mine) { t += step; --pk; }     // finished lanes keep re-reading their last row
-                        const double qv = t[0], uv = t[TU], av = t[TA], nv = HAS_NC ? t[TN] : 0.0;
-                        const int pe = *pk;
+                        if (mine) { t += stepb; pk -= 4; }     // finished lanes keep re-reading their last row
+                        const double qv = lds64(t), uv = lds64o<TU * 8>(t), av = lds64(t + TAb);
+                        const double nv = HAS_NC ? lds64o<TN * 8>(t) : 0.0;
+                        const int pe = lds32o<KPE>(pk);
                         win_pair<false, HAS_NC, COUNT>(qv, Qj, av, uv, nv, mine, A1, B, N, cnt_c);
                         mine = mine && (pe >= kqc);
                     }
                 }
                 {   // anticyclonic side: rows j0, j0+1, ... while some row at or beyond may not exceed Q_j
-                    const int* pk = kbase + kWinCols * P;
-                    const double* t = tp;
-                    bool mine = act && (*pk <= kqa);
+                    uint32_t t = at, pk = ak;
+                    bool mine = act && (lds32o<KPP>(pk) <= kqa);
                     while (__any_sync(FULL, mine)) {
-                        const double qv = t[0], uv = t[TU], av = t[TA], nv = HAS_NC ? t[TN] : 0.0;
-                        const int pp = pk[1];
+                        const double qv = lds64(t), uv = lds64o<TU * 8>(t), av = lds64(t + TAb);
+                        const double nv = HAS_NC ? lds64o<TN * 8>(t) : 0.0;
+                        const int pp = lds32o<KPP + 4>(pk);
                         win_pair<true, HAS_NC, COUNT>(qv, Qj, av, uv, nv, mine, A2, B, N, cnt_a);
                         mine = mine && (pp <= kqa);
-                        if (mine) { t -= step; ++pk; }
+                        if (mine) { t -= stepb; pk += 4; }
                     }
                 }
                 {
                     // a1 = A1, a2 = A2;  ua2 = a dphi cos(phi_j) B - uref_j (a1 + a2)   (compute_flux_dirinv.f90:96-113)
-                    // (lanes past the last row and inactive rows carry A1 = A2 = B = N = 0 and add nothing)
+                    // (lanes past the last row and inactive rows carry A1 = A2 = B = N = 0; they store nothing)
                     const double lw = A1 + A2;
-                    const double x1 = Uc[j0] * lw;
-                    const double u2 = __fma_rn(abcs[j0], B, -x1);
+                    const double x1 = lds64(aq + o_ur) * lw;
+                    const double u2 = __fma_rn(lds64(a_tab + o_cs + gi * GT), B, -x1);
                     const bool store = (storem >> gi) & 1;
-                    double* o = out_k + (long long)gi * out_gstep;
                     if (MODE == 1) {
                         double a[4];
                         tmem_ld8(tacc + gi * TCOL, a);
@@ -436,9 +458,11 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                         if (p.u2) o[p.u2 - p.a1] = u2;
                         if (HAS_NC && p.ncf) o[p.ncf - p.a1] = N;
                     }
+                    o += out_gstep;
                 }
             }
         }
+        out_k += out_lev;
         // next level's thresholds into the other table buffer (its last readers finished a level ago)
         if (more && tid < nd) {
             Qh[(s ^ 1) * nd + tid] = __fma_rn(qsg, Qn, 0.0);
@@ -552,7 +576,7 @@ static int lwa_window_launch(WinArgs a, int mode, const double* pv, const double
     const size_t smem = win_smem_layout(a.nd, nc ? 3 : 2).total;
     dim3 grid(tiles, chunks, nprob);
     FALWA_KERNEL("lwa_window_kernel", st);
-    static const int nw = tune_int("FALWA_WIN_WARPS", 16);
+    static const int nw = tune_int("FALWA_WIN_WARPS", 24);
     if (mode == 1 && nw == 24) rc = win_launch_mode<1, 24>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
     else if (mode == 1 && nw == 32) rc = win_launch_mode<1, 32>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
     else rc = mode == 1 ? win_launch_mode<1, 16>(tq, tu, tn, a, nc != nullptr, grid, smem, st)
