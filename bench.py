@@ -133,6 +133,7 @@ def algorithmic_bytes(nlon, nlat, nd, kmax, nlev, has_avort=True):
     return {
         "theta_rowmean_kernel": f3in,
         "interp_kernel": 3 * f3in + 3 * f3,
+        "interp_qgpv_kernel": 3 * f3in + 5 * f3,                                # read u, v, T; write u, v, theta, avort, qgpv
         "avort_pv_kernel": 3 * f3 + 2 * f3,
         "zonal_stats_kernel": 4 * f3,
         "area_hist3_kernel": 2 * f3,
