@@ -23,6 +23,7 @@ enum Out2D {
 struct falwa_plan {
     int kind, nlon, nlat, nlev, kmax, jb, nd, jd, npart, maxit;
     double a, omega, dz, h, rr, cp, tol, rjac, prefactor, dphi, dlambda;
+    double hist_area_scale, hist_cbound;  // fixed-point scales of the area histograms (area_hist3_kernel)
     std::vector<double> height, sinlat;   // host copies (tables built per call)
     double* d_tab = nullptr;
     int* d_lo = nullptr;
@@ -46,72 +47,109 @@ namespace falwa {
 // not accumulated at all: refstate_level_kernel forms  S[m] = (N - N_edge)[nb - m] (sign-flipped circulation)
 // + S_edge[m],  where the edge points (exactly classified with the reference's divisions) go to slots 1 and 3.
 // NEED_QN: the circulation sums of the pv histogram are only needed by the NH18 boundary condition.
+//
+// Reproducible sums: the bins are accumulated as 64-bit fixed-point integers — every term is rounded once
+// to a multiple of 2^-e and integer addition is associative, so the histogram (hence Qref) is bit-identical from run
+// to run whatever order the atomics land in — and integer shared-memory / L2 atomics are single instructions, where
+// an fp64 shared-memory atomicAdd is a compare-and-swap loop.  Areas use one scale for the whole grid (the sphere's
+// area must fit 2^62); circulations use a power-of-two scale per level derived from that level's extrema.  The
+// quantisation (relative 2^-40 or better per term against the largest term) is far below the rtol the sums are
+// compared with, and is the same for every run.
 // ---------------------------------------------------------------------------------------------
+__host__ __device__ inline double hist_pow2_scale(double bound) {   // 2^e with bound * 2^e in [2^60, 2^61)
+    if (!(bound > 0.0) || !(bound < 1e300)) return 1.0;
+    int ex;
+    frexp(bound, &ex);          // bound = m * 2^ex, m in [0.5, 1)
+    return ldexp(1.0, 61 - ex);
+}
+__device__ __forceinline__ double hist_circ_scale(double vmax, double vmin, double cbound) {
+    return hist_pow2_scale(fmax(fabs(vmax), fabs(vmin)) * cbound);
+}
+
+// 64-bit fixed-point add into shared memory with native 32-bit atomics (a 64-bit shared-memory atomicAdd, integer or
+// floating point, is a compare-and-swap loop): the low word is added first and its carry rides with the high word.
+// The pair (lo, hi) is the little-endian image of the 64-bit sum modulo 2^64, whatever the order of the adds.
+__device__ __forceinline__ void fx_add(unsigned long long* slot, long long v) {
+    unsigned* w = reinterpret_cast<unsigned*>(slot);
+    const unsigned lo = (unsigned)v, hi = (unsigned)((unsigned long long)v >> 32);
+    const unsigned old = atomicAdd(w, lo);
+    const unsigned carry = (old + lo) < old ? 1u : 0u;
+    if (hi + carry) atomicAdd(w + 1, hi + carry);
+}
+
+// A lane's run of points in one bin: `cnt` points of a row with cell area dai (fixed point) and the run's circulation
+// sum (accumulated in the lane's fixed order in fp64, rounded once to fixed point here).
 template <bool NEED_QN>
-__device__ __forceinline__ void hist_flush(double* sh, int nb, int cur, double sa, double sc) {
+__device__ __forceinline__ void hist_flush(unsigned long long* sh, int nb, int cur, int cnt, long long dai, double sc, double scale) {
     if (cur > 0) {
-        atomicAdd(&sh[cur - 1], sa);
-        if (NEED_QN) atomicAdd(&sh[nb + cur - 1], sc);
+        fx_add(&sh[cur - 1], (long long)cnt * dai);
+        if (NEED_QN) fx_add(&sh[nb + cur - 1], __double2ll_rn(sc * scale));
     }
 }
 
 template <bool NEED_QN, bool WITH_V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 area_hist3_kernel(int nlon, int nlat, int kmax, int nb, const double* __restrict__ pv,
                   const double* __restrict__ avort, const unsigned long long* __restrict__ ext,
-                  const double* __restrict__ da, int rows_per_block, double* __restrict__ hist, int run) {
-    extern __shared__ double sh[];  // [4][2][nb]
+                  const double* __restrict__ da, int rows_per_block, unsigned long long* __restrict__ hist, int run,
+                  double area_scale, double cbound) {
+    extern __shared__ unsigned long long shi[];  // [4][2][nb]
     const int k = blockIdx.y + 1, b = blockIdx.z;
     pv += (size_t)b * nlon * nlat * kmax;
     if (WITH_V) avort += (size_t)b * nlon * nlat * kmax;
     ext += (size_t)b * 2 * kmax * 2;
     hist += (size_t)b * 4 * kmax * 2 * nb;
-    for (int t = threadIdx.x; t < 4 * 2 * nb; t += blockDim.x) sh[t] = 0.0;
+    for (int t = threadIdx.x; t < 4 * 2 * nb; t += blockDim.x) shi[t] = 0ull;
     __syncthreads();
     const double pmax = ordered_to_f64(ext[k * 2 + 0]), pmin = ordered_to_f64(ext[k * 2 + 1]);
     const double dqp = (pmax - pmin) / (double)(nb - 1);
     const double smax = -pmin;                      // southern frame: q' = -pv, max' = -min
     const double dqs = (smax - (-pmax)) / (double)(nb - 1);
     const double rdqp = 1. / dqp;
-    double vmax = 0., dqv = 1.;
+    const double scp = hist_circ_scale(pmax, pmin, cbound);
+    double vmax = 0., dqv = 1., scv = 1.;
     if (WITH_V) {
         vmax = ordered_to_f64(ext[(kmax + k) * 2 + 0]);
         const double vmin = ordered_to_f64(ext[(kmax + k) * 2 + 1]);
         dqv = (vmax - vmin) / (double)(nb - 1);
+        scv = hist_circ_scale(vmax, vmin, cbound);
     }
     const double rdqv = 1. / dqv;
     const int j0 = blockIdx.x * rows_per_block, j1 = min(nlat, j0 + rows_per_block);
     const int runs_per_row = (nlon + run - 1) / run;
     const int total = (j1 - j0) * runs_per_row;
     const size_t lev = (size_t)k * nlat * nlon;
-    double* hN = sh;
-    double* hSx = sh + 2 * nb;
-    double* hV = sh + 4 * nb;
-    double* hNx = sh + 6 * nb;
+    unsigned long long* hN = shi;
+    unsigned long long* hSx = shi + 2 * nb;
+    unsigned long long* hV = shi + 4 * nb;
+    unsigned long long* hNx = shi + 6 * nb;
     const int nrows = j1 - j0;
     for (int t = threadIdx.x; t < total; t += blockDim.x) {
         // consecutive lanes take the same longitude run of consecutive ROWS: PV differs from row to row, so the
-        // lanes of a warp hit different bins and the shared-memory CAS loops rarely collide
+        // lanes of a warp hit different bins and their shared-memory atomics rarely meet
         const int j = j0 + t % nrows;
         const int i0 = (t / nrows) * run, i1 = min(nlon, i0 + run);
         const double daj = da[j];
-        int cn = -1, cv = -1;
-        double an = 0, qn = 0, av = 0, qv = 0;
+        const long long dai = __double2ll_rn(daj * area_scale);
+        int cn = -1, cv = -1, an = 0, av = 0;
+        double qn = 0., qv = 0.;
         auto point = [&](double q, double w) {
             bool edge;
             int ind = area_bin(pmax, q, dqp, rdqp, nb, &edge);
-            if (ind != cn) { hist_flush<NEED_QN>(hN, nb, cn, an, qn); cn = ind; an = 0; qn = 0; }
-            an += daj; qn += daj * q;
+            if (ind != cn) { hist_flush<NEED_QN>(hN, nb, cn, an, dai, qn, scp); cn = ind; an = 0; qn = 0.; }
+            ++an;
+            if (NEED_QN) qn += daj * q;
             if (__builtin_expect(edge, 0)) {  // rare: classify the southern bin with the reference's own division
                 const double qq = -q;
                 const int is = max(1, min(nb, 1 + (int)area_bin_exact(smax - qq, dqs)));
-                atomicAdd(&hSx[is - 1], daj); atomicAdd(&hSx[nb + is - 1], daj * qq);
-                atomicAdd(&hNx[ind - 1], daj); atomicAdd(&hNx[nb + ind - 1], daj * q);
+                const long long tq = __double2ll_rn((daj * q) * scp);
+                fx_add(&hSx[is - 1], dai); fx_add(&hSx[nb + is - 1], -tq);
+                fx_add(&hNx[ind - 1], dai); fx_add(&hNx[nb + ind - 1], tq);
             }
             if (WITH_V) {
                 ind = area_bin(vmax, w, dqv, rdqv, nb);
-                if (ind != cv) { hist_flush<true>(hV, nb, cv, av, qv); cv = ind; av = 0; qv = 0; }
-                av += daj; qv += daj * w;
+                if (ind != cv) { hist_flush<true>(hV, nb, cv, av, dai, qv, scv); cv = ind; av = 0; qv = 0.; }
+                ++av; qv += daj * w;
             }
         };
         const size_t row = lev + (size_t)j * nlon;
@@ -143,13 +181,13 @@ area_hist3_kernel(int nlon, int nlat, int kmax, int nb, const double* __restrict
             }
         }
         for (; i < i1; ++i) point(pv[row + i], WITH_V ? avort[row + i] : 0.0);
-        hist_flush<NEED_QN>(hN, nb, cn, an, qn);
-        if (WITH_V) hist_flush<true>(hV, nb, cv, av, qv);
+        hist_flush<NEED_QN>(hN, nb, cn, an, dai, qn, scp);
+        if (WITH_V) hist_flush<true>(hV, nb, cv, av, dai, qv, scv);
     }
     __syncthreads();
     for (int t = threadIdx.x; t < 4 * 2 * nb; t += blockDim.x) {
-        const double x = sh[t];
-        if (x != 0.0) {
+        const unsigned long long x = shi[t];
+        if (x != 0ull) {
             const int hsel = t / (2 * nb), r = t % (2 * nb);
             atomicAdd(&hist[((size_t)hsel * kmax + k) * 2 * nb + r], x);
         }
@@ -599,8 +637,9 @@ baro_post_kernel(int nlon, int nlat, double a, double dphi, double dlambda, cons
 // ---------------------------------------------------------------------------------------------
 struct LevelArgs {
     int kind, kmax, nlat, nd, nb;
-    double a, dphi, pi;
-    const double *zm, *hist, *alat, *cosmid, *norm, *cosw;
+    double a, dphi, pi, area_scale, cbound;
+    const double *zm, *alat, *cosmid, *norm, *cosw;
+    const long long* hist;   // fixed-point bins of area_hist3_kernel
     const unsigned long long* ext;
     double *work, *ckref;
     size_t per, njk, njd;
@@ -640,7 +679,7 @@ refstate_level_kernel(LevelArgs p) {
     }
     if (!interior) return;
     const unsigned long long* extb = p.ext + (size_t)b * 2 * kmax * 2;
-    const double* histb = p.hist + (size_t)b * 4 * kmax * 2 * nb;
+    const long long* histb = p.hist + (size_t)b * 4 * kmax * 2 * nb;
     double qmax = ordered_to_f64(extb[k * 2 + 0]), qmin = ordered_to_f64(extb[k * 2 + 1]);
     if (sgn < 0) { const double t = qmax; qmax = -qmin; qmin = -t; }
     const double dq = (qmax - qmin) / (double)(nb - 1);
@@ -651,20 +690,25 @@ refstate_level_kernel(LevelArgs p) {
         dqv = (vmax - vmin) / (double)(nb - 1);
     }
     {   // cumulative sums in the reference's order (bin 1 is never added)
-        const double* an = histb + ((size_t)0 * kmax + k) * 2 * nb;     // +pv, all points
-        const double* sx = histb + ((size_t)1 * kmax + k) * 2 * nb;     // southern bins of the edge points
-        const double* av = histb + ((size_t)2 * kmax + k) * 2 * nb;     // avort
-        const double* nx = histb + ((size_t)3 * kmax + k) * 2 * nb;     // northern bins of the edge points
+        const long long* an = histb + ((size_t)0 * kmax + k) * 2 * nb;     // +pv, all points
+        const long long* sx = histb + ((size_t)1 * kmax + k) * 2 * nb;     // southern bins of the edge points
+        const long long* av = histb + ((size_t)2 * kmax + k) * 2 * nb;     // avort
+        const long long* nx = histb + ((size_t)3 * kmax + k) * 2 * nb;     // northern bins of the edge points
+        // fixed point -> double (the scales of area_hist3_kernel; the southern frame has the same |extrema|)
+        const double ia = 1.0 / p.area_scale;
+        const double icp = 1.0 / hist_circ_scale(ordered_to_f64(extb[k * 2 + 0]), ordered_to_f64(extb[k * 2 + 1]), p.cbound);
+        const double icv = do_vort ? 1.0 / hist_circ_scale(ordered_to_f64(extb[(kmax + k) * 2 + 0]),
+                                                           ordered_to_f64(extb[(kmax + k) * 2 + 1]), p.cbound) : 1.0;
         for (int t = tid; t < nb; t += blockDim.x) {
             if (hs == 0) {
-                aan[t] = an[t]; ccn[t] = an[nb + t];
+                aan[t] = (double)an[t] * ia; ccn[t] = (double)an[nb + t] * icp;
             } else {   // mirror: southern bin t <- northern bin nb-2-t (circulation changes sign), plus the edge points
                 const int tn = nb - 2 - t;
-                double a = sx[t], c = sx[nb + t];
+                long long a = sx[t], c = sx[nb + t];
                 if (tn >= 0) { a += an[tn] - nx[tn]; c += -(an[nb + tn] - nx[nb + tn]); }
-                aan[t] = a; ccn[t] = c;
+                aan[t] = (double)a * ia; ccn[t] = (double)c * icp;
             }
-            if (do_vort) { aav[t] = av[t]; ccv[t] = av[nb + t]; }
+            if (do_vort) { aav[t] = (double)av[t] * ia; ccv[t] = (double)av[nb + t] * icv; }
         }
         __syncthreads();
         if (tid == 0) {
@@ -793,6 +837,12 @@ extern "C" int falwa_b200_plan_create(falwa_plan** out, int kind, int nlon, int 
     host_alat_da(nd, nlat, a, dphi, P->dlambda, alat, da);
     P->o_alat = push_tab(tab, alat);
     P->o_da = push_tab(tab, da);
+    {   // fixed-point scales: the area of all cells, and (per unit of |field|) of all circulation terms, fits 2^61
+        double total = 0.0, damax = 0.0;
+        for (double x : da) { total += std::fabs(x) * (double)nlon; damax = std::max(damax, std::fabs(x)); }
+        P->hist_area_scale = hist_pow2_scale(total);
+        P->hist_cbound = damax * (double)nlon * (double)nlat;
+    }
     std::vector<double> cosmid(nd, 0.), norm(nd, 1.), vw(kmax);
     for (int j = 1; j <= nd; ++j) {
         cosmid[j - 1] = std::cos(dphi * ((double)j - 0.5));
@@ -988,6 +1038,7 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
     DeviceScratch<unsigned long long> ext;
     DeviceScratch<int> nit;
     const bool have_stats = zm_in && ext_in;
+    const double area_scale = P->hist_area_scale, cbound = P->hist_cbound;
     if (!have_stats) {
         if ((rc = zm.alloc((size_t)batch * 3 * kmax * nlat, st))) return rc;
         if ((rc = ext.alloc((size_t)batch * 2 * kmax * 2, st))) return rc;
@@ -1010,16 +1061,17 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
         int slabs = std::max(1, std::min(nlat, (148 * tune_int("FALWA_HIST_CTAS", 12) + (kmax - 3)) / (kmax - 2) / std::max(1, std::min(batch, 4))));
         const int rows = ceil_div(nlat, slabs);
         slabs = ceil_div(nlat, rows);
-        const size_t smem = sizeof(double) * 4 * 2 * nb;
+        const size_t smem = sizeof(unsigned long long) * 4 * 2 * nb;
         const int hrun = tune_int("FALWA_HIST_RUN", 64);
+        unsigned long long* histi = reinterpret_cast<unsigned long long*>(hist.d);
         dim3 hgrid(slabs, kmax - 2, batch);
         FALWA_KERNEL("area_hist3_kernel", st);
         if (P->kind == 0) {  // NH18: pv histogram with circulation sums (SOR boundary condition), no vorticity histogram
             FALWA_CUDA_TRY(cudaFuncSetAttribute(area_hist3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            area_hist3_kernel<true, false><<<hgrid, 256, smem, st>>>(nlon, nlat, kmax, nb, qgpv, avort, extd, d + P->o_da, rows, hist.d, hrun);
+            area_hist3_kernel<true, false><<<hgrid, 256, smem, st>>>(nlon, nlat, kmax, nb, qgpv, avort, extd, d + P->o_da, rows, histi, hrun, area_scale, cbound);
         } else {             // NHN22: areas of the pv histogram, areas + circulation of the vorticity histogram
             FALWA_CUDA_TRY(cudaFuncSetAttribute(area_hist3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            area_hist3_kernel<false, true><<<hgrid, 256, smem, st>>>(nlon, nlat, kmax, nb, qgpv, avort, extd, d + P->o_da, rows, hist.d, hrun);
+            area_hist3_kernel<false, true><<<hgrid, 256, smem, st>>>(nlon, nlat, kmax, nb, qgpv, avort, extd, d + P->o_da, rows, histi, hrun, area_scale, cbound);
         }
         FALWA_LAUNCH_CHECK();
     }
@@ -1080,8 +1132,8 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
     {
         LevelArgs la;
         la.kind = P->kind; la.kmax = kmax; la.nlat = nlat; la.nd = nd; la.nb = nb;
-        la.a = P->a; la.dphi = P->dphi; la.pi = pi;
-        la.zm = zmd; la.hist = hist.d; la.alat = d + P->o_alat; la.cosmid = d + P->o_cosmid; la.norm = d + P->o_norm;
+        la.a = P->a; la.dphi = P->dphi; la.pi = pi; la.area_scale = area_scale; la.cbound = cbound;
+        la.zm = zmd; la.hist = reinterpret_cast<const long long*>(hist.d); la.alat = d + P->o_alat; la.cosmid = d + P->o_cosmid; la.norm = d + P->o_norm;
         la.cosw = (P->kind == 0) ? d + P->o_cosw : nullptr;
         la.ext = extd; la.work = work.d; la.ckref = work.d + ckoff; la.per = per; la.njk = njk; la.njd = njd;
         const size_t smem = sizeof(double) * ((size_t)4 * nb + 3 * nd);

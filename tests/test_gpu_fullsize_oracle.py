@@ -142,3 +142,18 @@ def test_equivalent_latitude_bins_are_exact(case, hemisphere):
         _note(what="bin_mismatch", kind=kind, hemisphere=hemisphere, which=nm, mismatch=mism,
               points=int(a_[:, :, 1:-1].size))
         assert mism == 0
+
+
+def test_results_are_bit_reproducible(snap):
+    """the area histograms accumulate 64-bit fixed-point integers, the LWA kernels use no floating-point
+    atomics — two runs of the pipeline on the same inputs give bit-identical reference states and fluxes."""
+    runs = []
+    for _ in range(2):
+        f = _cls("nhn22")(*snap)
+        f.interpolate_fields(return_named_tuple=False)
+        f.compute_reference_states(return_named_tuple=False)
+        f.compute_lwa_and_barotropic_fluxes(return_named_tuple=False)
+        runs.append({n: np.array(getattr(f, n)) for n in ("qref", "uref", "ptref", "lwa", "lwa_baro", "adv_flux_f2")})
+    diff = {n: int((runs[0][n] != runs[1][n]).sum()) for n in runs[0]}
+    _note(what="run_to_run_differences", kind="nhn22", **diff)
+    assert not any(diff.values()), diff
