@@ -40,7 +40,7 @@ struct ProfileRecord {
 };
 struct ProfileState {
     bool enabled = false;
-    long long launches = 0;
+    std::atomic<long long> launches{0};   // kernels launched by this library (any host thread)
     std::vector<ProfileRecord> recs;
 };
 inline ProfileState& profile_state() {
@@ -174,15 +174,25 @@ struct PinnedRing {
     // the ring bytes [off, off + bytes) are in use until everything queued on `st` so far has run
     void fence(size_t off, size_t bytes, cudaStream_t st) {
         cudaEvent_t ev;
+        bool ok = true;
         if (!pool.empty()) { ev = pool.back(); pool.pop_back(); }
-        else if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return;
-        cudaEventRecord(ev, st);
+        else ok = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+        if (ok && cudaEventRecord(ev, st) != cudaSuccess) { pool.push_back(ev); ok = false; }
+        if (!ok) {   // no usable event: the bytes are free once the stream has drained
+            (void)cudaGetLastError();
+            cudaStreamSynchronize(st);
+            return;
+        }
         fences.push_back({off, off + ((bytes + 255) & ~(size_t)255), ev});
     }
 };
+// One ring (and one event pool) per device: an event belongs to the device it was created on, and a process may
+// drive several GPUs through the C ABI.
 inline PinnedRing& pinned_ring() {
-    static PinnedRing r;
-    return r;
+    static PinnedRing rings[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = 0; }
+    return rings[dev & 15];
 }
 
 __global__ void __launch_bounds__(256)

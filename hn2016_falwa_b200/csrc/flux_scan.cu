@@ -296,7 +296,8 @@ lwa_scan_kernel(ScanArgs p) {
         for (int c = 0; c < 4; ++c) {
             const int r = r0 + 32 * c + lane;
             if (r < nd) {
-                const int nx = s_nxt[r + 1], e = e4[c];
+                // a NaN PV value belongs to neither set of any row (the reference's comparisons are false): not displaced
+                const int nx = s_nxt[r + 1], e = (q4[c] == q4[c]) ? e4[c] : nx;
                 E_[r] = (short)e;
                 if (e > nx) ccyc += (unsigned)(e - nx); else canti += (unsigned)(nx - e);
                 // slot inside the bin: native 32-bit shared-memory atomic (arrival order is arbitrary; step 4 sorts
@@ -392,14 +393,15 @@ lwa_scan_kernel(ScanArgs p) {
             if (HAS_NC) nbv = n_[r0];
             {   // first entering row
                 // class weights 1.0 / 0.0 and one fused multiply-add per sum: fma(1, x, S) == S + x and
-                // fma(0, x, S) == S exactly, at a third of the instructions of select + add on 64-bit values
-                const bool cyc = ent && (e1 > t), anti = ent && (e1 < t);
-                const double wc = cyc ? 1.0 : 0.0, wa = anti ? -1.0 : 0.0, wd = (cyc || anti) ? 1.0 : 0.0;
-                const double qc = qe * ce, qu = qe * ue;
+                // fma(0, x, S) == S exactly for finite x, at a third of the instructions of select + add on 64-bit
+                // values; the operands of a row outside both sets are zeroed so that a NaN / Inf there cannot leak
+                const bool cyc = ent && (e1 > t), anti = ent && (e1 < t), on = cyc || anti;
+                const double wc = cyc ? 1.0 : 0.0, wa = anti ? -1.0 : 0.0, wd = on ? 1.0 : 0.0;
+                const double qc = on ? qe * ce : 0.0, qu = on ? qe * ue : 0.0, uz = on ? ue : 0.0;
                 S1c = __fma_rn(wc, qc, S1c); S2c = __fma_rn(wc, ce, S2c);
                 S1a = __fma_rn(wa, qc, S1a); S2a = __fma_rn(wa, ce, S2a);
-                T3 = __fma_rn(wd, qu, T3); T4 = __fma_rn(wd, ue, T4);
-                if (HAS_NC) T5 = __fma_rn(wd, ne * ce, T5);
+                T3 = __fma_rn(wd, qu, T3); T4 = __fma_rn(wd, uz, T4);
+                if (HAS_NC) T5 = __fma_rn(wd, on ? ne * ce : 0.0, T5);
             }
 #pragma unroll 1
             for (int jj = jfirst + 1; jj < j; ++jj) {              // further entering rows (exception rows, t = 0)
@@ -414,11 +416,11 @@ lwa_scan_kernel(ScanArgs p) {
             {   // first row leaving (cyclonic) / entering (anticyclonic) at t: E(jj) == t
                 const bool cyc = binr && (t > nb0), anti = binr && !(t > nb0);
                 const double wc = cyc ? -1.0 : 0.0, wa = anti ? 1.0 : 0.0, wd = binr ? -1.0 : 0.0;
-                const double qc = qb * cb, qu = qb * ub;
+                const double qc = binr ? qb * cb : 0.0, qu = binr ? qb * ub : 0.0, uz = binr ? ub : 0.0;
                 S1c = __fma_rn(wc, qc, S1c); S2c = __fma_rn(wc, cb, S2c);
                 S1a = __fma_rn(wa, qc, S1a); S2a = __fma_rn(wa, cb, S2a);
-                T3 = __fma_rn(wd, qu, T3); T4 = __fma_rn(wd, ub, T4);
-                if (HAS_NC) T5 = __fma_rn(wd, nbv * cb, T5);
+                T3 = __fma_rn(wd, qu, T3); T4 = __fma_rn(wd, uz, T4);
+                if (HAS_NC) T5 = __fma_rn(wd, binr ? nbv * cb : 0.0, T5);
             }
 #pragma unroll 1
             for (int x = x0 + 1; x < xe; ++x) {

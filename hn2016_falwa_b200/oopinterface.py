@@ -250,6 +250,12 @@ class QGFieldBase(ABC):
             lwa[:, :eq, :] = np.abs(a1 + a2)[:, ::-1, :]
             lwa_baro[:, :eq], u_baro[:, :eq] = ab[:, ::-1], ub[:, ::-1]
         self._lwa_only = dict(lwa=np.swapaxes(lwa, 0, 2), lwa_baro=lwa_baro.T, u_baro=u_baro.T)
+        # like the reference, whose storages are overwritten (oopinterface.py:676-690): results of an earlier flux
+        # stage on this object no longer stand in front of these
+        b.lwa = b.out2d = None
+        for k in list(self._cache):
+            if k == "lwa" or k.startswith("out:"):
+                self._cache.pop(k)
 
     # ---- layer-wise (un-averaged) flux terms: the next step of the path (oopinterface.py:985-1156) ------------
     def compute_ncforce_from_heating_rate(self, heating_rate):

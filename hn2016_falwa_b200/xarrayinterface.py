@@ -15,6 +15,9 @@ from collections import OrderedDict
 
 import numpy as np
 
+_trapezoid = getattr(np, "trapezoid", None) or np.trapz   # NumPy >= 2.0 / 1.x
+
+
 try:  # pragma: no cover - not available in the build image
     import xarray as xr
 except Exception:  # noqa: BLE001
@@ -236,7 +239,7 @@ class QGDataset:
         self._template = None
         self._store = {}      # name -> host array [n_local, ...]
         self._done = set()
-        self._gathered = False
+        self._global = {}     # name -> gathered array [n, ...] (every rank's shard, in order); see gather()
         if self._hi > self._lo or runner is None:
             self._make_template()
 
@@ -347,12 +350,15 @@ class QGDataset:
 
     def gather(self):
         """Concatenate every rank's shard of the stored outputs on all ranks (one all_gather per variable; the only
-        communication of the whole job).  No-op for a single process."""
-        if self._world == 1 or self._gathered:
+        communication of the whole job).  No-op for a single process.  The local shard stays what the compute methods
+        work on: a stage run after a gather() computes this rank's rows as before, and the next gather() collects the
+        variables that are new since (all ranks must call it, like any collective)."""
+        if self._world == 1:
             return
         import torch.distributed as dist
         # agree on the variable list first (a rank with an empty shard has stored nothing)
-        meta = {k: (str(a.dtype), tuple(a.shape[1:])) for k, a in self._store.items()}
+        meta = {k: (str(a.dtype), tuple(a.shape[1:])) for k, a in self._store.items()
+                if self._global.get(k) is None or self._global[k][0] is not a}
         metas = [None] * self._world
         dist.all_gather_object(metas, meta)
         union = {}
@@ -361,6 +367,7 @@ class QGDataset:
         for name in sorted(union):
             dtype, tail = union[name]
             loc = self._store.get(name)
+            src = loc
             if loc is None:
                 loc = np.empty((0,) + tuple(tail), dtype=dtype)
             parts = [None] * self._world
@@ -369,9 +376,8 @@ class QGDataset:
             else:
                 self._gather_big(parts, loc)
             parts = sorted((p for p in parts if p[1].shape[0] > 0), key=lambda p: p[0])
-            self._store[name] = np.concatenate([p[1] for p in parts], axis=0)
-        self._lo, self._hi = 0, self._n
-        self._gathered = True
+            # remember which local array the gathered copy was made from: a recomputed variable is gathered again
+            self._global[name] = (src, np.concatenate([p[1] for p in parts], axis=0))
 
     def _gather_big(self, parts, loc):
         """Tensor all_gather (NCCL on GPUs, gloo on CPU) of equally padded shards."""
@@ -399,9 +405,11 @@ class QGDataset:
         return self._other_dims + core, coords
 
     def _as_dataarray(self, var):
-        if var not in self._store:
+        if var not in self._store and var not in self._global:
             raise ValueError(f"{var} is not computed yet.")
-        arr = self._store[var]
+        g = self._global.get(var)
+        # the gathered copy, unless the variable has been recomputed locally since
+        arr = g[1] if g is not None and (var not in self._store or g[0] is self._store[var]) else self._store[var]
         dims, coords = self._coords_for(var)
         if arr.shape[0] == self._n:          # full (single process or gathered): restore the leading dims
             arr = arr.reshape(self._other_shape + arr.shape[1:])
@@ -414,7 +422,8 @@ class QGDataset:
         return SimpleDataArray(arr, dims, coords, name=var)
 
     def _dataset(self, names):
-        data_vars = OrderedDict((n, self._as_dataarray(n)) for n in names if n in self._store or self._keep_3d)
+        data_vars = OrderedDict((n, self._as_dataarray(n)) for n in names
+                                if n in self._store or n in self._global or self._keep_3d)
         if xr is not None:  # pragma: no cover
             return xr.Dataset(data_vars, attrs=self.attrs)
         return SimpleDataset(data_vars, attrs=self.attrs)
@@ -429,6 +438,9 @@ class QGDataset:
         """Global definition (NH18): one DataArray; hemispheric (NHN22): the (north, south) pair like the reference
         (xarrayinterface.py:476-497, whose suffixes follow the order of QGFieldNHN22.static_stability)."""
         st = self._store.get("static_stability")
+        g = self._global.get("static_stability")
+        if g is not None and (st is None or g[0] is st):
+            st = g[1]            # every rank's rows (after gather())
         if st is None:
             raise ValueError("static_stability is not computed yet.")
         if st.ndim == 2:
@@ -812,7 +824,7 @@ def integrate_budget(ds, var_names=None):
     coords = OrderedDict((k, v) for k, v in lwa.coords.items() if k != tname)
 
     def integ(name):
-        return np.trapezoid(np.asarray(ds[_find([name], ds, var_names, name)].data), x=tsec, axis=axis)
+        return _trapezoid(np.asarray(ds[_find([name], ds, var_names, name)].data), x=tsec, axis=axis)
     dl = np.take(lwa.data, -1, axis=axis) - np.take(lwa.data, 0, axis=axis)
     czaf, demf, mhf = (integ(n) for n in ("convergence_zonal_advective_flux", "divergence_eddy_momentum_flux",
                                           "meridional_heat_flux"))
@@ -852,6 +864,9 @@ def hemisphere_to_globe(ds, var_names=None):
         vname = None
     out = SimpleDataset(attrs=ds.attrs)
     for name, da in ds.items():
+        if yname not in da.dims:     # e.g. static_stability: carried through unchanged, as xarray does
+            out[name] = da
+            continue
         ax = da.dims.index(yname)
         idx = [slice(None)] * da.data.ndim
         idx[ax] = sel

@@ -92,11 +92,19 @@ def _worker(rank, world, port, tmp):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     ds, (xlon, ylat, plev), _ = _dataset(nt=5, flip=True)
     q = xi.QGDataset(ds, qgfield=_Template, runner=OracleRunner(xlon, ylat, plev))   # shard from the process group
+    # the usual multi-rank sequence: a stage, gather, the next stage, gather — the second stage must still work on
+    # this rank's own rows and the second gather must pick up the new variables (and leave the old ones intact)
+    q.compute_reference_states(return_dataset=False)
+    q.gather()
+    qref_first = q.qref.data.copy()
+    assert q.shard == xi.shard_bounds(5, rank, world)
     q.compute_lwa_and_barotropic_fluxes(return_dataset=False)
     lo, hi = q.shard
+    assert q.lwa_baro.data.shape[0] == hi - lo          # not gathered yet: this rank's rows only
     q.gather()
+    q.gather()                                           # nothing new: no-op
     np.savez(os.path.join(tmp, f"rank{rank}.npz"), lo=lo, hi=hi, lwa_baro=q.lwa_baro.data, uref=q.uref.data,
-             lwa=q.lwa.data)
+             lwa=q.lwa.data, qref=q.qref.data, qref_first=qref_first)
     dist.destroy_process_group()
 
 
@@ -115,3 +123,5 @@ def test_two_rank_gloo_shards_and_gather(tmp_path):
         np.testing.assert_array_equal(r["lwa_baro"], single.lwa_baro.data)
         np.testing.assert_array_equal(r["uref"], single.uref.data)
         np.testing.assert_array_equal(r["lwa"], single.lwa.data)
+        np.testing.assert_array_equal(r["qref"], single.qref.data)
+        np.testing.assert_array_equal(r["qref_first"], single.qref.data)

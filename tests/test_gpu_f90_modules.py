@@ -219,3 +219,30 @@ def test_drop_in_pipeline_through_f2py_boundary(gpu, staged, kind):
     for f in pipeline.USER_FIELDS:
         rtol, atol = tol.get(f, (1e-8, 1e-9 * float(np.abs(want[f]).max())))
         compare(f"{name}/{kind}/dropin/{f}", got[f], want[f], rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("method", [0, 2], ids=["window", "scan"])
+def test_lwa_with_nan_points_matches_the_double_loop(gpu, method):
+    """A NaN PV value makes both of the reference's comparisons false (compute_flux_dirinv.f90:90, :101): the point
+    belongs to no set of any row.  The fast LWA methods must treat it the same way as the double loop (method 1), and
+    a NaN in u may only reach the rows whose sets contain that point."""
+    inputs = testdata.synthetic_snapshot(nlon=96, nlat=49, seed=3)
+    o = pipeline.run_qgfield("nhn22", *inputs, stages=("interp", "ref"))
+    c = o["config"]
+    eq, jd = c["equator_idx"], c["jd"]
+    pv, uu, vv, pt = (np.array(_f(o[k])) for k in ("qgpv", "interpolated_u", "interpolated_v", "interpolated_theta"))
+    rng = np.random.default_rng(11)
+    for _ in range(40):
+        pv[rng.integers(0, 96), rng.integers(24, 49), rng.integers(2, 47)] = np.nan
+    for _ in range(10):
+        uu[rng.integers(0, 96), rng.integers(24, 49), rng.integers(2, 47)] = np.nan
+    kw = dict(pv=pv, uu=uu, vv=vv, pt=pt, ncforce=np.zeros(pv.shape), tn0=o["tn0"], qref=o["qref"].T[-eq:],
+              uref=o["uref"].T[-jd:], tref=o["ptref"].T[-jd:], jb=c["jb"], is_nhem=True, a=A, om=OM, dz=DZ, h=H,
+              rr=RR, cp=CP, prefac=c["prefactor"], return_mask_count=True)
+    want = gpu.compute_flux_dirinv_nshem(method=1, **kw)
+    got = gpu.compute_flux_dirinv_nshem(method=method, **kw)
+    assert got[9] == want[9]
+    for nm, a_, b_ in zip(("astar1", "astar2", "ncforce3d", "ua1", "ua2"), got[:5], want[:5]):
+        assert np.array_equal(np.isnan(a_), np.isnan(b_)), nm
+        ok = ~np.isnan(b_)
+        compare(f"nan/method{method}/{nm}", a_[ok], b_[ok], rtol=1e-8, atol=1e-11 * np.abs(b_[ok]).max())
