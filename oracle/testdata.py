@@ -67,3 +67,37 @@ def load_era_packed():
 
 
 from hn2016_falwa_b200.synthetic import ERA_PLEV, synthetic_snapshot  # noqa: E402,F401  (shared input generator)
+
+
+BARO_NPZ = os.path.join(GOLDEN_DIR, "barotropic_vorticity_256x512.npz")
+
+
+def convert_reference_barotropic(ref_data_dir="/root/reference/tests/data", out=BARO_NPZ):
+    """Run once in the build container (needs /root/reference): the reference's sampled absolute vorticity
+    (tests/data/barotropic_vorticity.nc, float32 (256, 512) at byte offset 10101) together with
+    what the reference's own BarotropicField (pure NumPy) makes of it, the inputs and the answer key of the GPU mirror
+    of tests/test_integration.py:107-125."""
+    import sys
+    raw = open(os.path.join(ref_data_dir, "barotropic_vorticity.nc"), "rb").read()
+    av = np.frombuffer(raw, dtype="<f4", count=256 * 512, offset=10101).reshape(256, 512).copy()
+    sys.path.insert(0, "/root/reference/src")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_barotropic_field", "/root/reference/src/falwa/barotropic_field.py",
+                                                  submodule_search_locations=None)
+    import types
+    pkg = types.ModuleType("falwa")
+    pkg.__path__ = ["/root/reference/src/falwa"]
+    sys.modules.setdefault("falwa", pkg)
+    from falwa.barotropic_field import BarotropicField      # the reference's unmodified module
+    xlon = np.linspace(0, 360., 512, endpoint=False)
+    ylat = np.linspace(-90, 90., 256, endpoint=True)
+    c1 = BarotropicField(xlon, ylat, pv_field=av)
+    c2 = BarotropicField(xlon, ylat, pv_field=av, return_partitioned_lwa=True)
+    assert np.isclose(c1.lwa, c2.lwa.sum(axis=0)).all()     # the reference's own assertion
+    np.savez_compressed(out, absolute_vorticity=av, equivalent_latitudes=c1.equivalent_latitudes, lwa=c1.lwa)
+    return out
+
+
+def load_reference_barotropic():
+    z = np.load(BARO_NPZ)
+    return {k: z[k] for k in z.files}

@@ -50,3 +50,23 @@ def test_batch_partitioned_and_zonally_symmetric():
     _, want = basis2d.barotropic_eqvlat_lwa(xlon, ylat, sym)
     compare("baro2d/symmetric/lwa", z, want, rtol=1e-8, atol=1e-9 * np.abs(want).max())
     assert np.array_equal(z, np.broadcast_to(z[:, :1], z.shape))
+
+
+def test_reference_barotropic_vorticity_file():
+    """GPU mirror of the reference's tests/test_integration.py:107-125 on its own sampled field
+    (tests/data/barotropic_vorticity.nc, 256 x 512): total == sum of the cyclonic / anticyclonic parts, equal
+    equivalent latitudes — and both against what the reference's unmodified BarotropicField returns for that file
+    (tests/golden/barotropic_vorticity_256x512.npz, written by oracle.testdata.convert_reference_barotropic)."""
+    from hn2016_falwa_b200.barotropic_field import BarotropicField
+    g = testdata.load_reference_barotropic()
+    av = g["absolute_vorticity"]
+    xlon = np.linspace(0, 360., 512, endpoint=False)
+    ylat = np.linspace(-90, 90., 256, endpoint=True)
+    cc1 = BarotropicField(xlon, ylat, pv_field=av)
+    cc2 = BarotropicField(xlon, ylat, pv_field=av, return_partitioned_lwa=True)
+    assert np.isclose(cc1.equivalent_latitudes, cc2.equivalent_latitudes).all()
+    assert np.isclose(cc1.lwa, cc2.lwa.sum(axis=0)).all()
+    assert cc2.lwa.shape == (2, 256, 512) and (cc2.lwa >= 0).all()
+    compare("baro2d/reference_file/eqvlat", cc1.equivalent_latitudes, g["equivalent_latitudes"], rtol=1e-8,
+            atol=1e-9 * np.abs(g["equivalent_latitudes"]).max())
+    compare("baro2d/reference_file/lwa", cc1.lwa, g["lwa"], rtol=1e-8, atol=1e-9 * np.abs(g["lwa"]).max())
