@@ -972,6 +972,18 @@ extern "C" int falwa_b200_theta_hemispheric_means(const falwa_plan* P, int batch
                               rowmean.d, means, st);
 }
 
+namespace falwa {
+// data_on_evenly_spaced_pseudoheight_grid: theta = T * exp(kappa z / H) level by level (oopinterface.py:120-122)
+__global__ void __launch_bounds__(256)
+theta_from_t_kernel(size_t plane, int nlev, const double* __restrict__ t_in, const double* __restrict__ fac,
+                    double* __restrict__ theta) {
+    const size_t n = plane * nlev;
+    const size_t base = (size_t)blockIdx.y * n;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x)
+        st_stream(&theta[base + t], ld_stream(&t_in[base + t]) * fac[t / plane]);
+}
+}  // namespace falwa
+
 // vertical interpolation + QGPV.  profiles_host [batch][4][kmax] = t0_s, t0_n, stat_s, stat_n at `height`.
 // zm [batch][3][kmax][nlat] / ext (uint64 [batch][2][kmax][2]), both optional: zonal means of qgpv, u, theta and the
 // per-level extrema of qgpv and avort, produced on the fly for falwa_b200_reference_states.
@@ -1001,6 +1013,11 @@ extern "C" int falwa_b200_interpolate_fields(const falwa_plan* P, int batch, con
         return interp_qgpv_launch(P->kind == 0 ? 0 : 1, P->nlon, P->nlat, P->nlev, kmax, jdsplit, batch, u_in, v_in, t_in,
                                   P->d_lo, d + P->o_whi, d + P->o_wlo, d + P->o_fac, d + P->o_qg, prof.d, u, v, theta, qgpv,
                                   avort, st);
+    }
+    if (already_on_height_grid && theta != t_in) {   // u, v are used as they are; T -> theta on the device
+        FALWA_KERNEL("theta_from_t_kernel", st);
+        theta_from_t_kernel<<<dim3(148 * 8, batch), 256, 0, st>>>((size_t)P->nlat * P->nlon, P->nlev, t_in, d + P->o_fac, theta);
+        FALWA_LAUNCH_CHECK();
     }
     if (!already_on_height_grid) {
         if ((rc = interp_launch(P->nlon, P->nlat, P->nlev, kmax, batch, u_in, v_in, t_in, P->d_lo, d + P->o_whi,

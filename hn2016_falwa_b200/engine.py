@@ -264,9 +264,9 @@ class QGBatch:
         self.compute_profiles()
         shape = (self.B, p.kmax, p.nlat, p.nlon)
         if self.on_height_grid:
-            self.u, self.v = self.u_in, self.v_in
-            fac = torch.from_numpy(p.theta_factor).to(self.t_in.device)
-            self.theta = (self.t_in * fac[None, :, None, None]).contiguous()
+            # the inputs already sit on the height grid (nlev == kmax): theta = T * factor(level) is formed by the
+            # library (theta_from_t_kernel) inside falwa_b200_interpolate_fields
+            self.u, self.v, self.theta = self.u_in, self.v_in, self._new(*shape)
         else:
             self.u, self.v, self.theta = self._new(*shape), self._new(*shape), self._new(*shape)
         self.avort, self.qgpv = self._new(*shape), self._new(*shape)
@@ -297,6 +297,11 @@ class QGBatch:
     # ---- stage 3 -------------------------------------------------------------------------------
     def compute_lwa_and_barotropic_fluxes(self, ncforce=None, method=0):
         p = self.plan
+        if p.nd > 416 and method != 1:   # lwa_window.cu holds 384 hemispheric rows, flux_scan.cu 416
+            import warnings
+            warnings.warn(f"{p.nd} latitudes per hemisphere exceed what the fast LWA kernels hold on chip (384 / 416): "
+                          "falling back to the reference's O(nd^2) double loop on the device (about 100x slower)",
+                          RuntimeWarning, stacklevel=2)
         if self.qref_cu is None:
             raise ValueError("Reference states have not been computed yet.")
         nc = None

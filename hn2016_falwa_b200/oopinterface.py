@@ -243,13 +243,18 @@ class QGFieldBase(ABC):
         ab, ub, a1, a2 = f90_modules.compute_lwa_only_nhn22(pv=pv.contiguous(), uu=uu.contiguous(),
                                                            qref=qcu[:, -eq:].contiguous(), **kw)
         lwa[:, -eq:, :], lwa_baro[:, -eq:], u_baro[:, -eq:] = np.abs(a1 + a2), ab, ub
+        # oopinterface.py:666-667 stores |astar1|, |astar2| of the northern hemisphere in the layer-wise storage; the
+        # southern assignments (:689-690) go to attributes nothing reads, so those rows stay zero there as well
+        p1, p2 = (np.zeros((self.nlon, nlat, self.kmax), order="F") for _ in range(2))
+        p1[:, -eq:, :], p2[:, -eq:, :] = np.abs(a1), np.abs(a2)
         if not self.northern_hemisphere_results_only:
             ab, ub, a1, a2 = f90_modules.compute_lwa_only_nhn22(
                 pv=(-pv.flip(1)).contiguous(), uu=uu.flip(1).contiguous(),
                 qref=(-qcu[:, :eq].flip(1)).contiguous(), **kw)
             lwa[:, :eq, :] = np.abs(a1 + a2)[:, ::-1, :]
             lwa_baro[:, :eq], u_baro[:, :eq] = ab[:, ::-1], ub[:, ::-1]
-        self._lwa_only = dict(lwa=np.swapaxes(lwa, 0, 2), lwa_baro=lwa_baro.T, u_baro=u_baro.T)
+        self._lwa_only = dict(lwa=np.swapaxes(lwa, 0, 2), lwa_baro=lwa_baro.T, u_baro=u_baro.T,
+                              astar1=np.swapaxes(p1, 0, 2), astar2=np.swapaxes(p2, 0, 2))
         # like the reference, whose storages are overwritten (oopinterface.py:676-690): results of an earlier flux
         # stage on this object no longer stand in front of these
         b.lwa = b.out2d = None
@@ -276,10 +281,12 @@ class QGFieldBase(ABC):
             raise ValueError("Reference states have not been computed yet.")
         nc = None if ncforce is None else np.ascontiguousarray(ncforce, dtype=np.float64)[None]
         out = engine.to_host(b.compute_layerwise_lwa_fluxes(ncforce=nc, method=method)[0])
-        self._layerwise = {n: out[i] for n, i in engine.LAYER3D.items() if n not in ("astar1", "astar2")}
+        self._layerwise = {n: out[i] for n, i in engine.LAYER3D.items()}
         self._layerwise_fluxes_computed = True
 
     def _layer(self, name):
+        if name in ("astar1", "astar2") and not self._layerwise_fluxes_computed and self._lwa_only is not None:
+            return self._return_interp_variables(self._nh_slice(self._lwa_only[name], lat_axis=1), interp_axis=1)
         if not self._layerwise_fluxes_computed:
             raise ValueError(f'{name} is not computed yet. Call compute_layerwise_lwa_fluxes() first.')
         return self._return_interp_variables(self._nh_slice(self._layerwise[name], lat_axis=1), interp_axis=1)
@@ -291,6 +298,11 @@ class QGFieldBase(ABC):
     ep3 = property(lambda self: self._layer("ep3"), doc="(u_e v_e cos^2)(j-1), layerwise")
     stretch_term = property(lambda self: self._layer("stretch_term"), doc="Layerwise stretching (heat-flux) term")
     ncforce = property(lambda self: self._layer("ncforce"), doc="Layerwise non-conservative forcing integral")
+    # The reference keeps the two pieces of LWA per layer in its LayerwiseFluxTermsStorage (data_storage.py:199-217;
+    # written at oopinterface.py:1085-1086, :1118-1119 and, as magnitudes, by compute_lwa_only at :665-667) without a
+    # public accessor; here they can be read like the other layer-wise fields.
+    astar1 = property(lambda self: self._layer("astar1"), doc="Layerwise cyclonic part of LWA * cos(lat)")
+    astar2 = property(lambda self: self._layer("astar2"), doc="Layerwise anticyclonic part of LWA * cos(lat)")
 
     @abstractmethod
     def _static_stability_for_tuple(self):
