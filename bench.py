@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 
 GRIDS = {"0.25": (1440, 721), "1.5": (240, 121)}
 KMAX, NLEV = 49, 37
+CPU_THREADS_PER_PROCESS_025 = 2   # see cpu_split(): 8 x 2 is the best split of the 16-core box (profiles/r02_cpu_sweep.jsonl)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -117,6 +118,23 @@ def bind_to_gpu_numa_node(index):
     return None
 
 
+def workload_config(nlon, nlat):
+    """The `config` object of the JSON line: identical for the B200 arm and the reference arm."""
+    return {"workload": f"QGFieldNHN22 {nlon}x{nlat}x{NLEV}plev->kmax{KMAX}, jb=5, both hemispheres",
+            "grid": {"nlon": nlon, "nlat": nlat, "nlev": NLEV, "kmax": KMAX}, "protocol": "NHN22", "jb": 5,
+            "data": "seeded synthetic snapshots (hn2016_falwa_b200.synthetic), zonally rotated copies per batch"}
+
+
+def cpu_split(nlon, cores):
+    """processes x OpenMP threads of the CPU arm — the best of the sweep kept in profiles/r02_cpu_sweep.jsonl
+    (tools/cpu_sweep.py on the GPU box's host cores); used by `cpu_baseline` and by `--impl reference` alike."""
+    if nlon > 1000:
+        workers = max(1, cores // CPU_THREADS_PER_PROCESS_025)
+    else:
+        workers = min(8, cores)
+    return workers
+
+
 def make_batch(nlon, nlat, batch, seed):
     """One seeded synthetic snapshot (hn2016_falwa_b200.synthetic) + zonally rotated copies of it: B distinct
     snapshots [B][nlev][nlat][nlon] without B x 8 s of host trigonometry."""
@@ -153,10 +171,13 @@ def algorithmic_bytes(nlon, nlat, nd, kmax, nlev, has_avort=True):
 _CPU_INPUT = {}
 
 
-def _cpu_init(nlon, nlat, threads):
-    """Pool initialiser: OpenMP width of this worker and its synthetic snapshot (generated once, reused every step)."""
+def _cpu_init(nlon, nlat, threads, precision):
+    """Pool initialiser: OpenMP width of this worker, arithmetic type of the native routines, and the worker's synthetic
+    snapshot (generated once, reused every step)."""
     os.environ["OMP_NUM_THREADS"] = str(threads)
     from hn2016_falwa_b200.synthetic import synthetic_snapshot
+    from oracle import f2py_shim
+    f2py_shim.set_precision(np.float32 if precision == "f32" else np.float64)
     _CPU_INPUT["inp"] = synthetic_snapshot(nlon=nlon, nlat=nlat, seed=1234 + os.getpid() % 97)
 
 
@@ -170,15 +191,16 @@ def _cpu_one(_):
 class CpuReference:
     """The CPU oracle pipeline on the host cores: `workers` processes x (cores // workers) OpenMP threads."""
 
-    def __init__(self, nlon, nlat, workers):
+    def __init__(self, nlon, nlat, workers, precision="f64", threads=None):
         import multiprocessing as mp
         import subprocess
         subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
         self.cores = os.cpu_count() or 1
         self.workers = max(1, min(workers, self.cores))
-        self.threads = max(1, self.cores // self.workers)
+        self.threads = threads or max(1, self.cores // self.workers)
+        self.precision = precision
         self.pool = mp.get_context("spawn").Pool(self.workers, initializer=_cpu_init,
-                                                 initargs=(nlon, nlat, self.threads))
+                                                 initargs=(nlon, nlat, self.threads, precision))
         self.pool.map(_cpu_one, [0] * 0)   # start the workers
 
     def step(self, snapshots):
@@ -192,8 +214,8 @@ class CpuReference:
         self.pool.join()
 
 
-def cpu_reference_rate(nlon, nlat, snapshots, workers):
-    ref = CpuReference(nlon, nlat, workers)
+def cpu_reference_rate(nlon, nlat, snapshots, workers, precision="f64", threads=None):
+    ref = CpuReference(nlon, nlat, workers, precision, threads)
     ref.step(ref.workers)            # untimed: worker start-up + input synthesis
     t0 = time.perf_counter()
     rate = ref.step(snapshots)
@@ -205,9 +227,8 @@ def cpu_reference_rate(nlon, nlat, snapshots, workers):
 def run_reference(args, nlon, nlat, rank, world):
     if rank != 0:
         return
-    big = nlon > 1000
-    workers = 2 if big else min(8, os.cpu_count() or 1)
-    per_step = workers if big else 4 * workers
+    workers = cpu_split(nlon, os.cpu_count() or 1)
+    per_step = workers if nlon > 1000 else 4 * workers
     ref = CpuReference(nlon, nlat, workers)
     for _ in range(max(1, args.warmup and 1)):
         ref.step(ref.workers)        # warm-up: worker start-up, input synthesis, library load (one pass is enough on a CPU)
@@ -215,14 +236,13 @@ def run_reference(args, nlon, nlat, rank, world):
     ref.close()
     value = float(np.mean(rates))
     cores, workers, threads = ref.cores, ref.workers, ref.threads
-    sample = f"{per_step} synthetic {nlon}x{nlat} snapshot(s) per step, {workers} processes x {threads} OpenMP threads"
+    sample = f"{per_step} synthetic {nlon}x{nlat} snapshot(s) per step, {workers} processes x {threads} OpenMP threads, fp64"
     line = {
         "impl": "reference", "metric": "snapshots/sec, QGFieldNHN22 full pipeline", "value": value,
         "unit": "snapshots/s", "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": args.warmup,
         "ms_per_step": 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"QGFieldNHN22 {nlon}x{nlat}x{NLEV}plev->kmax{KMAX}, jb=5, both hemispheres",
-                   "snapshots_per_step": per_step},
+        "dtype": "f64", "data": "synthetic", "config": workload_config(nlon, nlat),
+        "run": {"snapshots_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "snapshots/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "snapshots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU oracle (C++/NumPy restatement, fp64); the reference's Fortran cannot be built in this image",
@@ -320,10 +340,19 @@ def run_b200(args, nlon, nlat, rank, world, local_rank):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         return world * B * e2e_steps / float(te.item())
 
-    e2e_steps = max(1, min(args.steps, 4))
+    e2e_steps = max(1, args.steps)
     e2e = {"value": time_e2e(hs, (hu, hv, ht)), "unit": "snapshots/s",
            "h2d_bytes_per_step": int(hs.h2d_bytes // e2e_steps), "d2h_bytes_per_step": int(hs.d2h_bytes // e2e_steps),
            "chunk": args.chunk, "steps": e2e_steps, "input_dtype": "f64"}
+
+    class _CopyOnly:   # the same transfers with no kernels: what the host <-> device path of this box sustains
+        def __init__(self, stream):
+            self.stream = stream
+
+        def run(self, *srcs, out, cycles):
+            self.stream.copy_only(*srcs, out, cycles=cycles)
+    e2e["ceiling"] = {"value": time_e2e(_CopyOnly(hs), (hu, hv, ht)), "unit": "snapshots/s",
+                      "what": "the same H2D + D2H copies (all ranks at once), no kernels"}
     # the same stream with float32 host inputs (ERA5's native precision), widened to fp64 on the device (ingest kernel)
     hs32 = engine.HostStream(plan, chunk=args.chunk, want_lwa3d=True, method=args.method, input_dtype=torch.float32)
     h32 = tuple(engine.HostStream.pinned(x.shape, torch.float32).copy_(x) for x in (hu, hv, ht))
@@ -344,8 +373,21 @@ def run_b200(args, nlon, nlat, rank, world, local_rank):
                              packing=packing, flip_lat=True, flip_lev=True)
     hs16.run(*h16, out=out)
     e2e["packed_int16_inputs"] = {"value": time_e2e(hs16, h16),
-                                  "h2d_bytes_per_step": int(hs16.h2d_bytes // e2e_steps)}
-    del hs16, h16
+                                  "h2d_bytes_per_step": int(hs16.h2d_bytes // e2e_steps),
+                                  "ceiling": time_e2e(_CopyOnly(hs16), h16)}
+    # ... and when only the reference states and the 2-D budget terms are wanted back (no 3-D LWA: 125 MB instead of
+    # 532 MB of results per snapshot)
+    hs2d = engine.HostStream(plan, chunk=args.chunk, want_lwa3d=False, method=args.method, input_dtype=torch.int16,
+                             packing=packing, flip_lat=True, flip_lev=True)
+    out2 = hs2d.alloc_outputs(B)
+    hs2d.run(*h16, out=out2)
+    saved_out, out = out, out2
+    e2e["packed_int16_inputs_2d_outputs"] = {"value": time_e2e(hs2d, h16),
+                                             "h2d_bytes_per_step": int(hs2d.h2d_bytes // e2e_steps),
+                                             "d2h_bytes_per_step": int(hs2d.d2h_bytes // e2e_steps),
+                                             "ceiling": time_e2e(_CopyOnly(hs2d), h16)}
+    out = saved_out
+    del hs16, h16, hs2d, out2
 
     # ---- per-kernel shares (CUDA events inside the library) and the roofline of the top kernel --
     roofline, kernels = None, {}
@@ -382,24 +424,187 @@ def run_b200(args, nlon, nlat, rank, world, local_rank):
         if world == 1 and not args.no_cpu_baseline:
             if "cpus" in _ORIG_AFFINITY:   # the CPU baseline uses every host core again
                 os.sched_setaffinity(0, _ORIG_AFFINITY["cpus"])
-            snaps = 1 if nlon > 1000 else 8
-            rate, cores, workers, threads, wall = cpu_reference_rate(nlon, nlat, snaps, workers=1 if nlon > 1000 else 8)
+            workers = cpu_split(nlon, os.cpu_count() or 1)   # the same split as `--impl reference`
+            snaps = workers if nlon > 1000 else 4 * workers
+            rate, cores, workers, threads, wall = cpu_reference_rate(nlon, nlat, snaps, workers=workers)
             cpu = {"value": rate, "unit": "snapshots/s", "cores": cores, "kind": "port",
                    "sample": f"{snaps} synthetic {nlon}x{nlat} snapshot(s), {workers} process(es) x {threads} OpenMP "
-                             f"threads, {wall:.1f} s wall"}
+                             f"threads, fp64, {wall:.1f} s wall"}
+            if args.cpu_extra:   # the arithmetic type the reference ships (fp32) and a single core
+                r32, _, _, _, w32 = cpu_reference_rate(nlon, nlat, snaps, workers=workers, precision="f32")
+                r1, _, _, _, w1 = cpu_reference_rate(nlon, nlat, 1, workers=1, threads=1)
+                cpu["fp32_as_shipped"] = {"value": r32, "sample": f"same split, fp32 native routines, {w32:.1f} s wall"}
+                cpu["single_core"] = {"value": r1, "sample": f"1 process x 1 thread, fp64, {w1:.1f} s wall"}
         line = {
             "metric": "snapshots/sec, QGFieldNHN22 full pipeline", "value": value, "unit": "snapshots/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"QGFieldNHN22 {nlon}x{nlat}x{NLEV}plev->kmax{KMAX}, jb=5, both hemispheres",
-                       "snapshots_per_step_per_gpu": B, "l2": "inputs of one step exceed L2 (B x 0.92 GB at 0.25 deg)",
-                       "lwa_method": args.method},
+            "config": workload_config(nlon, nlat),
+            "run": {"snapshots_per_step_per_gpu": B, "l2": "inputs of one step exceed L2 (B x 0.92 GB at 0.25 deg)",
+                    "lwa_method": args.method},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "kernels": kernels,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs 4 and 5 (kept as JSON lines under profiles/; the headline is config 3)
+# ------------------------------------------------------------------------------------------------
+def _year_inputs(nt):
+    from hn2016_falwa_b200.synthetic import synthetic_snapshot
+    base = [synthetic_snapshot(nlon=240, nlat=121, seed=100 + k) for k in range(8)]
+    xlon, ylat, plev = base[0][:3]
+    u, v, t = (np.empty((nt,) + base[0][3].shape) for _ in range(3))
+    for k in range(nt):
+        sn, sh = base[k % 8], (k // 8) % 240
+        u[k], v[k], t[k] = (np.roll(sn[i], sh, axis=-1) for i in (3, 4, 5))
+    return xlon, ylat, plev, u, v, t
+
+
+def run_config4(args, rank, world, local_rank):
+    """One year of 6-hourly 1.5-degree snapshots (1460 time steps) through QGDataset, time-sharded over the ranks:
+    host arrays in, host arrays out (reference states + barotropic terms; 3-D LWA with --keep-3d)."""
+    nt = args.nt or 1460
+    cfg = {"workload": f"QGDataset(QGFieldNHN22), {nt} snapshots 240x121x{NLEV}plev->kmax{KMAX} (BASELINE config 4)",
+           "grid": {"nlon": 240, "nlat": 121, "nlev": NLEV, "kmax": KMAX}, "protocol": "NHN22", "jb": 5}
+    metric = "snapshots/sec, one year of 6-hourly 1.5-degree snapshots through QGDataset"
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        workers = cpu_split(240, os.cpu_count() or 1)
+        ref = CpuReference(240, 121, workers)
+        ref.step(workers)
+        rates = [ref.step(4 * workers) for _ in range(max(1, args.steps))]
+        ref.close()
+        v = float(np.mean(rates))
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "snapshots/s", "n_gpus": args.gpus,
+                          "steps": max(1, args.steps), "warmup": args.warmup, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": v, "unit": "snapshots/s", "cores": ref.cores, "kind": "port",
+                                           "sample": f"{4 * workers} snapshots per step, {workers} processes x "
+                                                     f"{ref.threads} threads"},
+                          "e2e": {"value": v, "unit": "snapshots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}),
+              flush=True)
+        return
+    import torch
+    import torch.distributed as dist
+    from hn2016_falwa_b200 import _lib, xarrayinterface as xi
+    from hn2016_falwa_b200.oopinterface import QGFieldNHN22
+    _lib.require_cuda()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    xlon, ylat, plev, u, v, t = _year_inputs(nt)
+    coords = dict(time=np.arange(nt), level=plev, latitude=ylat, longitude=xlon)
+    dims = ("time", "level", "latitude", "longitude")
+    mk = lambda a, n: xi.SimpleDataArray(a, dims, coords, name=n)
+    ds = xi.SimpleDataset(dict(u=mk(u, "u"), v=mk(v, "v"), t=mk(t, "t")))
+    times = []
+    n0 = _lib.launch_count()
+    for it in range(args.warmup + args.steps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        q = xi.QGDataset(ds, qgfield=QGFieldNHN22, keep_3d=args.keep_3d, chunk=128)
+        q.compute_lwa_and_barotropic_fluxes(return_dataset=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if it >= args.warmup:
+            times.append(float(tt.item()))
+        lo, hi = q.shard
+        nbytes_in = 3 * (hi - lo) * u[0].nbytes
+        nbytes_out = sum(a.nbytes for a in q._store.values())
+        del q
+    launches = _lib.launch_count() - n0
+    if rank == 0:
+        sec = float(np.mean(times))
+        print(json.dumps({"metric": metric, "value": nt / sec, "unit": "snapshots/s", "n_gpus": world, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                          "run": {"keep_3d": bool(args.keep_3d), "chunk": 128},
+                          "e2e": {"value": nt / sec, "unit": "snapshots/s", "h2d_bytes_per_step": int(nbytes_in),
+                                  "d2h_bytes_per_step": int(nbytes_out),
+                                  "what": "QGDataset is host arrays in, host arrays out: value is end to end"},
+                          "gpu_launches": int(launches)}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_config5(args, rank, world, local_rank):
+    """BarotropicField / basis equivalent latitude + LWA of 1460 2-D 0.25-degree absolute-vorticity fields, batched."""
+    nt = args.nt or 1460
+    nlat, nlon, chunk = 721, 1440, 146
+    cfg = {"workload": f"BarotropicField eqvlat + LWA, {nt} fields {nlon}x{nlat} (BASELINE config 5)",
+           "grid": {"nlon": nlon, "nlat": nlat}}
+    metric = "fields/sec, 2-D equivalent latitude + LWA of 0.25-degree absolute vorticity"
+    ylat = np.linspace(-90, 90, nlat)
+    xlon = np.linspace(0, 360, nlon, endpoint=False)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import basis2d
+        rng = np.random.default_rng(1234)
+        pv = (2 * 7.29e-5 * np.sin(np.deg2rad(ylat))[:, None] + 8e-5 * np.cos(np.deg2rad(ylat))[:, None] *
+              np.exp(-((ylat[:, None] - 36) / 10) ** 2) * np.cos(3 * np.deg2rad(xlon)[None, :]) +
+              1e-6 * rng.standard_normal((nlat, nlon)))
+        t0 = time.perf_counter()
+        basis2d.barotropic_eqvlat_lwa(xlon, ylat, pv)
+        v = 1.0 / (time.perf_counter() - t0)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "fields/s", "n_gpus": args.gpus,
+                          "steps": 1, "warmup": 0, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": v, "unit": "fields/s", "cores": 1, "kind": "port",
+                                           "sample": "one field, NumPy restatement of basis.eqvlat_fawa + basis.lwa"},
+                          "e2e": {"value": v, "unit": "fields/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}),
+              flush=True)
+        return
+    import torch
+    from hn2016_falwa_b200 import _lib
+    from hn2016_falwa_b200.barotropic_field import BarotropicBatch
+    _lib.require_cuda()
+    torch.cuda.set_device(local_rank)
+    lo, hi = (nt * rank) // world, (nt * (rank + 1)) // world      # time shards
+    phi = torch.deg2rad(torch.tensor(ylat, device="cuda"))[None, :, None]
+    lam = torch.deg2rad(torch.tensor(xlon, device="cuda"))[None, None, :]
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+
+    def make(t0, n):
+        ph = (torch.arange(t0, t0 + n, device="cuda", dtype=torch.float64) * 0.05)[:, None, None]
+        return (2 * 7.29e-5 * torch.sin(phi) + 8e-5 * torch.cos(phi) * torch.exp(-((torch.rad2deg(phi) - 36) / 10) ** 2)
+                * torch.cos(3 * lam + ph) + 1e-6 * torch.randn((n, nlat, nlon), device="cuda", dtype=torch.float64,
+                                                               generator=g))
+    BarotropicBatch(xlon, ylat, make(0, 2)).compute()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = 0.0
+    for t0 in range(lo, hi, chunk):
+        pv = make(t0, min(chunk, hi - t0))
+        torch.cuda.synchronize()
+        e0.record()
+        BarotropicBatch(xlon, ylat, pv).compute()
+        e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps({"metric": metric, "value": nt / (ms / 1e3), "unit": "fields/s", "n_gpus": world, "steps": 1,
+                          "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic (generated on the device)",
+                          "config": cfg, "gpu_launches": int(_lib.launch_count() - n0), "e2e": None}), flush=True)
 
 
 def main():
@@ -413,11 +618,21 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--method", type=int, default=0, help="LWA algorithm: 0 automatic (windowed sums), 1 double loop, 2 interval scan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-extra", action="store_true", help="cpu_baseline also in fp32 (as shipped) and on one core")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5],
+                    help="BASELINE.json config: 3 = the headline (default), 4 = one year of 1.5-degree snapshots through "
+                         "QGDataset, 5 = 2-D BarotropicField batch of 1460 0.25-degree fields")
+    ap.add_argument("--nt", type=int, default=0, help="configs 4 / 5: number of time steps (default 1460)")
+    ap.add_argument("--keep-3d", action="store_true", help="config 4: also bring the 3-D fields back to the host")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     nlon, nlat = GRIDS[args.grid]
+    if args.config == 4:
+        return run_config4(args, rank, world, local_rank)
+    if args.config == 5:
+        return run_config5(args, rank, world, local_rank)
     if args.impl == "reference":
         run_reference(args, nlon, nlat, rank, world)
     else:

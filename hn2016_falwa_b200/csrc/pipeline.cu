@@ -437,7 +437,7 @@ struct ColumnLevelPlain : ColumnLevelBase {
 // EXT = true: the LWA pieces never exist as 3-D intermediates — lwa_window_kernel has already written the 3-D LWA and
 // the vertical sums of astar1 / astar2 / ua1 / ua2 (/ ncforce) — and this kernel only walks u, v and theta.
 template <bool SPECIAL, bool EXT>
-__global__ void __launch_bounds__(256, SPECIAL ? 2 : 3)
+__global__ void __launch_bounds__(256, SPECIAL ? 2 : (EXT ? 4 : 3))
 flux_column_kernel(FusedFluxArgs p, double* __restrict__ hs /* [b][nhemi][nd][imax] */) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int jfirst = p.jb + 1, jbrow = (p.jb >= 1) ? p.jb : p.nd;
@@ -525,10 +525,18 @@ flux_column_kernel(FusedFluxArgs p, double* __restrict__ hs /* [b][nhemi][nd][im
         ep43 = 0.5 * ep43 / (tg[1] - tg[0]);
         ep4 = ep41 * (ep42 + ep43);
     }
+    // With the LWA pieces gone (EXT) a level is three 8-byte loads per thread: two levels are requested ahead so that
+    // enough bytes are in flight per SM to cover the DRAM latency at the full bandwidth.
+    constexpr bool DEEP = EXT && !SPECIAL;
     Lv cur = fetch(2);
+    Lv nx2 = cur;
+    if (DEEP) nx2 = fetch(kmax >= 3 ? 3 : 2);
     for (int k = 2; k <= kmax; ++k) {
         Lv nxt = cur;
-        if (k < kmax) nxt = fetch(k + 1);
+        if (DEEP) {
+            nxt = nx2;
+            if (k + 2 <= kmax) nx2 = fetch(k + 2);
+        } else if (k < kmax) nxt = fetch(k + 1);
         const double w = p.vw[k - 1];
         const double wd = w * p.dc;
         s_u = s_u + cur.u0 * wd;
@@ -1321,6 +1329,7 @@ static int lwa_fluxes_impl(const falwa_plan* P, int batch, const double* qgpv, c
     //         2 = interval scan, 3 = windowed sums
     const bool use_window = (method == 0 || method == 3) && !l3d && win_supported(nlon, nd, qgpv, u, ncforce);
     const bool use_scan = !use_window && (method != 1) && scan_supported(nd);
+    bool fused_walk = false;
     ScanTables tabs;
     if (use_window) {
         // 3-D LWA and the vertical sums of astar1, astar2, ua1, ua2 (, ncforce) in one walk over the levels
@@ -1345,7 +1354,20 @@ static int lwa_fluxes_impl(const falwa_plan* P, int batch, const double* qgpv, c
         w.slot_a1 = O_ASTAR1; w.slot_a2 = O_ASTAR2; w.slot_lwa = O_LWA; w.slot_ua1 = O_UA1; w.slot_ua2 = O_UA2;
         w.slot_ncf = O_NCF;
         w.mask_count = nullptr;
-        if ((rc = lwa_window_launch(w, 1, qgpv, u, ncforce, nlat, batch, batch * nhemi, st))) return rc;
+        // without ncforce the column walk (pointwise flux terms and their vertical sums) is part of the same kernel
+        fused_walk = !ncforce && tune_int("FALWA_FUSED_WALK", 0);   // measured: no faster than the two kernels
+        if (fused_walk) {
+            if ((rc = hsum.alloc((size_t)batch * nhemi * nd * nlon, st))) return rc;
+            w.uu = u; w.vv = v; w.pt = theta;
+            w.tref = ptref_st; w.t_batch = (size_t)kmax * nlat; w.t_kstride = nlat;
+            for (int h = 0; h < 2; ++h) { w.t_row0[h] = nd - 1; w.t_rstep[h] = h ? -1 : 1; }
+            w.f11 = p.f11; w.prof = prof.d; w.clat = d + P->o_clat; w.sinphi = d + P->o_sinphi;
+            w.om = P->omega; w.dz = P->dz; w.prefac = P->prefactor; w.ep42fac = p.ep42fac;
+            w.hs = hsum.d;
+            w.slot_ep1 = O_EP1; w.slot_ep2 = O_EP2; w.slot_ep3 = O_EP3; w.slot_ep4 = O_EP4; w.slot_ubaro = O_UBARO;
+            w.slot_fphi = O_FPHI;
+        }
+        if ((rc = lwa_window_launch(w, fused_walk ? 2 : 1, qgpv, u, ncforce, nlat, batch, batch * nhemi, st))) return rc;
     } else if (use_scan) {
         // LWA pieces a1, a2, ua2 (, ncforce3d) of every level by the interval scan, in the global frame
         const int narr = ncforce ? 4 : 3, nprob = batch * nhemi;
@@ -1382,6 +1404,9 @@ static int lwa_fluxes_impl(const falwa_plan* P, int batch, const double* qgpv, c
             FALWA_KERNEL("fused_flux_layerwise_kernel", st);
             if (use_scan) fused_flux_kernel<false><<<grid, block, 0, st>>>(p);
             else fused_flux_kernel<true><<<grid, block, 0, st>>>(p);
+        } else if (use_window && fused_walk) {   // only the two rows with special rules are left to walk
+            FALWA_KERNEL("flux_special_rows_kernel", st);
+            flux_column_kernel<true, true><<<dim3(ceil_div(nlon, 256), 2, batch * nhemi), 256, 0, st>>>(p, hsum.d);
         } else if (use_window) {
             if ((rc = hsum.alloc((size_t)batch * nhemi * nd * nlon, st))) return rc;
             FALWA_KERNEL("flux_uvt_column_kernel", st);

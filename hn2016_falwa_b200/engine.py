@@ -417,6 +417,30 @@ class HostStream:
             if e0 is not None:
                 self.trace.append(("h2d", lo, e0, self._mark(self.s_in)))
 
+    def copy_only(self, u, v, t, out, cycles=1):
+        """The host <-> device traffic of ``run`` with no kernels in between: the same pinned inputs, chunk by chunk
+        into the two device slots on the input stream, and result-sized device buffers back into ``out`` on the output
+        stream.  What this sustains is the ceiling of the end-to-end rate on this box (bench.py: ``e2e.ceiling``)."""
+        host = [u, v, t]
+        n = int(u.shape[0])
+        self.h2d_bytes = self.d2h_bytes = 0
+        names = [k for k in ("qref", "uref", "ptref", "out2d", "lwa") if k in out and isinstance(out[k], torch.Tensor)]
+        dev = {k: torch.empty((self.chunk,) + tuple(out[k].shape[1:]), dtype=out[k].dtype, device="cuda") for k in names}
+        main = torch.cuda.current_stream()
+        for e in self.ev_free:
+            e.record(main)
+        bounds = [(lo, min(n, lo + self.chunk)) for lo in range(0, n, self.chunk)] * int(cycles)
+        for c, (lo, hi) in enumerate(bounds):
+            slot = c & 1
+            self._h2d(slot, host, lo, hi)
+            self.ev_free[slot].record(self.s_in)       # nothing reads the slot: free as soon as the copy is done
+            with torch.cuda.stream(self.s_out):
+                for k in names:
+                    out[k][lo:hi].copy_(dev[k][:hi - lo], non_blocking=True)
+                    self.d2h_bytes += (hi - lo) * dev[k][0].numel() * 8
+        self.s_in.synchronize()
+        self.s_out.synchronize()
+
     def run(self, u, v, t, out=None, cycles=1):
         """u, v, t: pinned host tensors [N][nlev][nlat][nlon] of ``input_dtype`` (NumPy arrays are staged through
         pinned memory first).  Returns the dict of pinned host result tensors (``out`` is reused when given).

@@ -91,10 +91,15 @@ def convert_reference_barotropic(ref_data_dir="/root/reference/tests/data", out=
     from falwa.barotropic_field import BarotropicField      # the reference's unmodified module
     xlon = np.linspace(0, 360., 512, endpoint=False)
     ylat = np.linspace(-90, 90., 256, endpoint=True)
-    c1 = BarotropicField(xlon, ylat, pv_field=av)
-    c2 = BarotropicField(xlon, ylat, pv_field=av, return_partitioned_lwa=True)
+    # the file holds float32; handed over as such (like the reference's test does) NumPy carries float32 through the
+    # reference's bin edges and sums, so the answer key proper is made from the same values widened to float64 and the
+    # single-precision run is kept for a comparison at the reference's own tolerance (rtol 1e-5)
+    c1 = BarotropicField(xlon, ylat, pv_field=av.astype(np.float64))
+    c2 = BarotropicField(xlon, ylat, pv_field=av.astype(np.float64), return_partitioned_lwa=True)
     assert np.isclose(c1.lwa, c2.lwa.sum(axis=0)).all()     # the reference's own assertion
-    np.savez_compressed(out, absolute_vorticity=av, equivalent_latitudes=c1.equivalent_latitudes, lwa=c1.lwa)
+    c32 = BarotropicField(xlon, ylat, pv_field=av)
+    np.savez_compressed(out, absolute_vorticity=av, equivalent_latitudes=c1.equivalent_latitudes, lwa=c1.lwa,
+                        equivalent_latitudes_f32_input=np.asarray(c32.equivalent_latitudes, dtype=np.float64))
     return out
 
 
