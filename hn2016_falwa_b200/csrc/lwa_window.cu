@@ -55,17 +55,6 @@ struct WinArgs {
     double *lwa, *out2d; const double* vw; double dc; size_t lwa_batch, lwa_plane, o2_batch, o2_plane;
     int slot_a1, slot_a2, slot_lwa, slot_ua1, slot_ua2, slot_ncf;
     unsigned long long* mask_count;         // optional: [0] anticyclonic pairs, [1] cyclonic pairs
-    // MODE 1, fused column walk (compute_flux_dirinv.f90:118-171 and oopinterface.py:405-420, :964-982): the pointwise
-    // flux terms of every grid point and their vertical sums, from the u tile that is on chip anyway plus v and theta
-    // read once from global memory.  vv / pt: [batch][kmax][in_rows][imax] like pv.
-    const double *uu, *vv, *pt;
-    const double* tref; size_t t_batch; int t_kstride; int t_row0[2], t_rstep[2];
-    const double* f11;                      // [batch][2][kmax]: heat-term factor per level (south, north)
-    const double* prof;                     // [batch][4][kmax]: ts0, tn0, ...
-    const double *clat, *sinphi;            // |cos(lat)| of the global rows [in_rows]; sin(phi_j) [nd+2]
-    double om, dz, prefac, ep42fac;
-    double* hs;                             // [batch][nhemi][nd][imax]: own-row eddy-momentum sums (baro_post_kernel)
-    int slot_ep1, slot_ep2, slot_ep3, slot_ep4, slot_ubaro, slot_fphi;
 };
 
 __device__ __forceinline__ uint32_t win_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -101,9 +90,9 @@ constexpr int kWinTile = kWinMaxRows * kWinCols;     // doubles of one (rows x 8
 // (one aa8 between the stages) — then the per-level tables.  Lanes of the last group that lie past the last row compute
 // on whatever sits at their (in-bounds, thanks to this order and the tail pad) addresses and never store.
 struct WinSmem {
-    size_t off_keys, off_pe, off_pp, off_tiles, off_q, off_u, off_cs, off_t, off_c0, off_cl, off_bar, total;
+    size_t off_keys, off_pe, off_pp, off_tiles, off_q, off_u, off_cs, off_bar, total;
 };
-__host__ __device__ inline WinSmem win_smem_layout(int nd, int nfields, bool fuse = false) {
+__host__ __device__ inline WinSmem win_smem_layout(int nd, int nfields) {
     WinSmem s;
     size_t o = 0;
     s.off_keys = o; o += (size_t)kWinCols * kWinKeyPitch * 4;
@@ -113,9 +102,6 @@ __host__ __device__ inline WinSmem win_smem_layout(int nd, int nfields, bool fus
     s.off_q = o; o += (size_t)2 * nd * 8;
     s.off_u = o; o += (size_t)2 * nd * 8;
     s.off_cs = o; o += (size_t)nd * 8;
-    s.off_t = o; if (fuse) o += (size_t)2 * nd * 8;      // tref of a level (two buffers)
-    s.off_c0 = o; if (fuse) o += (size_t)nd * 8;         // cos(phi_j)
-    s.off_cl = o; if (fuse) o += (size_t)nd * 8;         // |cos(lat)| of the row
     s.off_bar = o; o += 32;
     s.total = o + 256;
     return s;
@@ -171,25 +157,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const double (&a)[4]) {
                  "r"(__double2hiint(a[1])), "r"(__double2loint(a[2])), "r"(__double2hiint(a[2])),
                  "r"(__double2loint(a[3])), "r"(__double2hiint(a[3])) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, double (&a)[8]) {
-    uint32_t v[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int x = 0; x < 8; ++x) a[x] = __hiloint2double((int)v[2 * x + 1], (int)v[2 * x]);
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const double (&a)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-                 ::"r"(taddr), "r"(__double2loint(a[0])), "r"(__double2hiint(a[0])), "r"(__double2loint(a[1])),
-                 "r"(__double2hiint(a[1])), "r"(__double2loint(a[2])), "r"(__double2hiint(a[2])),
-                 "r"(__double2loint(a[3])), "r"(__double2hiint(a[3])), "r"(__double2loint(a[4])),
-                 "r"(__double2hiint(a[4])), "r"(__double2loint(a[5])), "r"(__double2hiint(a[5])),
-                 "r"(__double2loint(a[6])), "r"(__double2hiint(a[6])), "r"(__double2loint(a[7])),
-                 "r"(__double2hiint(a[7])) : "memory");
-}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // One window step of a threshold row: diff = q - Q; in the set (and still inside this lane's window) the pair adds
@@ -214,7 +181,7 @@ __device__ __forceinline__ void win_pair(double qv, double Qj, double av, double
     (void)HAS_NC;
 }
 
-template <int MODE, bool HAS_NC, bool COUNT, int NW, bool FUSE>
+template <int MODE, bool HAS_NC, bool COUNT, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_u,
                   const __grid_constant__ CUtensorMap tm_n, const WinArgs p) {
@@ -227,8 +194,7 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     constexpr int SD = (HAS_NC ? 4 : 3) * kWinTile;                      // doubles between the two stages
     constexpr unsigned FULL = 0xffffffffu;
     const int nd = p.nd;
-    static_assert(!FUSE || (MODE == 1 && !HAS_NC), "the fused column walk exists for the accumulating mode without ncforce");
-    const WinSmem L = win_smem_layout(nd, NF, FUSE);
+    const WinSmem L = win_smem_layout(nd, NF);
     double* tiles = reinterpret_cast<double*>(win_raw + L.off_tiles);   // [stage][q | u | aa8 | nc][rows][8]
     int* keys = reinterpret_cast<int*>(win_raw + L.off_keys);           // [8][P], hemispheric row index
     int* PE = reinterpret_cast<int*>(win_raw + L.off_pe);               // [8][P]: PE[x] = max key of rows < x
@@ -236,9 +202,6 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     double* Qh = reinterpret_cast<double*>(win_raw + L.off_q);          // [2][nd] thresholds of a level
     double* Ur = reinterpret_cast<double*>(win_raw + L.off_u);          // [2][nd] uref of a level
     double* abcs = reinterpret_cast<double*>(win_raw + L.off_cs);       // [nd] a dphi cos(phi_j)
-    double* Tr = reinterpret_cast<double*>(win_raw + L.off_t);          // [2][nd] tref of a level          (FUSE)
-    double* cs0 = reinterpret_cast<double*>(win_raw + L.off_c0);        // [nd] cos(phi_j)                  (FUSE)
-    double* clr = reinterpret_cast<double*>(win_raw + L.off_cl);        // [nd] |cos(lat)| of the row       (FUSE)
     uint64_t* bars = reinterpret_cast<uint64_t*>(win_raw + L.off_bar);  // [2] "tile of this stage has landed"
 
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
@@ -267,10 +230,8 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     // thresholds of hemispheric row tid + 1: per-thread source pointers, one level stride
     const bool trow = tid < nd && tid + 1 >= p.jstart && tid + 1 <= p.jend;
     const double* qsrc = trow ? p.qref + (size_t)b * p.q_batch + p.q_row0[h] + p.q_rstep[h] * tid : nullptr;
-    const double* usrc = ((FUSE ? tid < nd : trow) && p.uref)   // (the column walk needs uref on every row)
-                             ? p.uref + (size_t)b * p.u_batch + p.u_row0[h] + p.u_rstep[h] * tid : nullptr;
+    const double* usrc = (trow && p.uref) ? p.uref + (size_t)b * p.u_batch + p.u_row0[h] + p.u_rstep[h] * tid : nullptr;
     const double qsg = p.q_sg[h];
-    const double* tsrc = (FUSE && tid < nd) ? p.tref + (size_t)b * p.t_batch + p.t_row0[h] + p.t_rstep[h] * tid : nullptr;
 
     if (tid == 0) {
         win_mbar_init(&bars[0], 1);
@@ -295,11 +256,6 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         abcs[tid] = p.ab * p.cosphi[tid + 1];
         Qh[tid] = qsrc ? __fma_rn(qsg, qsrc[(size_t)(kbeg - 1) * p.q_kstride], 0.0) : 0.0;
         Ur[tid] = usrc ? usrc[(size_t)(kbeg - 1) * p.u_kstride] : 0.0;
-        if (FUSE) {
-            Tr[tid] = tsrc[(size_t)(kbeg - 1) * p.t_kstride];
-            cs0[tid] = p.cosphi[tid + 1];
-            clr[tid] = p.clat[fr.out_row0 + (fr.rev ? nd - 1 - tid : tid)];
-        }
     }
     if (tid < kWinCols) { PE[tid * P] = INT_MIN; PP[tid * P + nd] = INT_MAX; }
     if (MODE == 1) {   // levels 1 and kmax of the 3-D LWA are zero (compute_flux_dirinv.f90 touches k = 2 .. kmax-1)
@@ -315,9 +271,8 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     }
 
     // accumulator file in tensor memory (MODE 1): this thread's columns of group gi start at tacc + gi * TCOL
-    constexpr int TCOL = FUSE ? 16 : (HAS_NC ? 10 : 8);
+    constexpr int TCOL = HAS_NC ? 10 : 8;
     constexpr unsigned TMEM_COLS = (NW / 4) * GPW * TCOL <= 256 ? 256 : 512;
-    static_assert((NW / 4) * GPW * TCOL <= 512, "accumulator file exceeds the tensor memory of an SM");
     uint32_t tacc = 0;
     if (MODE == 1) {
         uint32_t* tbase = reinterpret_cast<uint32_t*>(bars + 2);
@@ -330,7 +285,6 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 #pragma unroll
         for (int gi = 0; gi < GPW; ++gi) {
             tmem_st8(tacc + gi * TCOL, zero);
-            if (FUSE) tmem_st8(tacc + gi * TCOL + 8, zero);
             if (HAS_NC) tmem_st2(tacc + gi * TCOL + 8, 0.0);
         }
         tmem_wait_st();
@@ -360,15 +314,6 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     uint32_t a_key = win_smem(keys) + (uint32_t)((c * P + j00) * 4);     // ... its key; PE / PP follow at fixed offsets
     uint32_t a_tab = win_smem(Qh) + (uint32_t)(j00 * 8);                 // ... its threshold; Ur / abcs at fixed offsets
     const uint32_t o_ur = (uint32_t)((Ur - Qh) * 8), o_cs = (uint32_t)((abcs - Qh) * 8);
-    const uint32_t o_tr = (uint32_t)((Tr - Qh) * 8), o_c0 = (uint32_t)((cs0 - Qh) * 8), o_cl = (uint32_t)((clr - Qh) * 8);
-    long long d_v = FUSE ? (long long)(p.vv - p.lwa) : 0, d_t = FUSE ? (long long)(p.pt - p.lwa) : 0;
-    asm volatile("" : "+l"(d_v), "+l"(d_t));
-    const double* f11 = FUSE ? p.f11 + ((size_t)b * 2 + (fr.rev ? 0 : 1)) * p.kmax : nullptr;
-    unsigned ownm = 0;        // rows whose eddy-momentum sum a neighbour needs: j >= jstart
-#pragma unroll
-    for (int gi = 0; gi < GPW; ++gi)
-        if (j00 + 4 * NW * gi + 1 >= p.jstart && j00 + 4 * NW * gi < nd) ownm |= 1u << gi;
-    asm volatile("" : "+r"(ownm));
     double* out_k = (MODE == 1 ? p.lwa + (size_t)b * p.lwa_batch + (size_t)(kbeg - 1) * p.lwa_plane
                                : p.a1 + (size_t)b * p.out_batch + (size_t)(kbeg - 1) * p.out_plane) +
                     (size_t)(fr.out_row0 + m00) * p.out_pitch + i0 + c;
@@ -380,8 +325,6 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     const double sgn = fr.sg;
 
     double wd = (MODE == 1) ? p.vw[kbeg - 1] * p.dc : 0.0;
-    double vnx = 0.0, tnx = 0.0;
-    if (FUSE && (validm & 1) && colok) { vnx = ld_stream(out_k + d_v); tnx = ld_stream(out_k + d_t); }
     for (int li = 0; li < nlev; ++li) {
         const int s = li & 1, k = kbeg + li;
         uint32_t a_t = a_t0 + (uint32_t)(s * SD * 8);                     // this lane's element of group 0 in this stage
@@ -390,12 +333,10 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         const uint32_t TAb = (uint32_t)((HAS_NC ? (s ? -kWinTile : 3 * kWinTile) : 2 * kWinTile) * 8);   // aa8 from q
         // thresholds and weight of the next level travel while this one is computed
         const bool more = li + 1 < nlev;
-        double Qn = 0.0, Un = 0.0, Tn = 0.0, wdn = 0.0;
+        double Qn = 0.0, Un = 0.0, wdn = 0.0;
         if (more && qsrc) Qn = qsrc[(size_t)k * p.q_kstride];
         if (more && usrc) Un = usrc[(size_t)k * p.u_kstride];
-        if (FUSE && more && tsrc) Tn = tsrc[(size_t)k * p.t_kstride];
         if (MODE == 1 && more) wdn = p.vw[k];
-        const double f11k = FUSE ? f11[k - 1] : 0.0;
         win_mbar_wait(&bars[s], (unsigned)((li >> 1) & 1));
 
         // ---- phase 1: hemispheric-frame PV (sign, -0 -> +0) and its keys ---------------------------
@@ -461,15 +402,6 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             if (gi < ngroups) {   // warp-uniform
                 const bool act = (actm >> gi) & 1;
                 const uint32_t at = a_t + gi * gbytes, ak = a_key + gi * GK, aq = a_q + gi * GT;
-                // fused column walk: v and theta of this point were requested one group ago; now request those of the
-                // next group this warp will work on (the first group of the next level after the last one of this)
-                const double v0 = vnx, t0 = tnx;
-                if (FUSE) {
-                    const bool lastg = gi + 1 >= ngroups;
-                    const double* nx = lastg ? out_k + out_lev : o + out_gstep;
-                    const bool want = lastg ? (more && (validm & 1)) : ((validm >> ((gi + 1) % GPW)) & 1);
-                    if (want && colok) { vnx = ld_stream(nx + d_v); tnx = ld_stream(nx + d_t); }
-                }
                 const double Qj = lds64(aq);
                 const int kq = win_key(Qj);
                 const int kqc = max(kq, INT_MIN + 1);   // "may exceed Q_j":      key >= kqc  (never true at PE[0])
@@ -503,33 +435,10 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     // a1 = A1, a2 = A2;  ua2 = a dphi cos(phi_j) B - uref_j (a1 + a2)   (compute_flux_dirinv.f90:96-113)
                     // (lanes past the last row and inactive rows carry A1 = A2 = B = N = 0; they store nothing)
                     const double lw = A1 + A2;
-                    const double urv = lds64(aq + o_ur);
-                    const double x1 = urv * lw;
+                    const double x1 = lds64(aq + o_ur) * lw;
                     const double u2 = __fma_rn(lds64(a_tab + o_cs + gi * GT), B, -x1);
                     const bool store = (storem >> gi) & 1;
-                    if (FUSE) {
-                        // pointwise terms of this grid point (compute_flux_dirinv.f90:118-158, oopinterface.py:964-982)
-                        const double u0 = lds64o<TU * 8>(at), ur = urv, tr = lds64(aq + o_tr);
-                        const double c0 = lds64(a_tab + o_c0 + gi * GT), cl = lds64(a_tab + o_cl + gi * GT);
-                        const double du = u0 - ur, sv = sgn * v0, dth = t0 - tr;
-                        double e1 = -0.5 * (du * du);
-                        e1 = e1 + 0.5 * (sv * sv);
-                        e1 = e1 - 0.5 * (dth * dth) * f11k;
-                        e1 = act ? e1 * c0 : 0.0;                              // rows jstart .. jend only
-                        const double gt = ((ownm >> gi) & 1) ? du * c0 * c0 * sv : 0.0;
-                        double a[8];
-                        tmem_ld16(tacc + gi * TCOL, a);
-                        a[0] = __fma_rn(A1, wd, a[0]);
-                        a[1] = __fma_rn(A2, wd, a[1]);
-                        a[2] = __fma_rn(x1, wd, a[2]);
-                        a[3] = __fma_rn(u2, wd, a[3]);
-                        a[4] = __fma_rn(u0, wd, a[4]);
-                        a[5] = __fma_rn(-((du * v0) * cl), wd, a[5]);
-                        a[6] = __fma_rn(gt, wd, a[6]);
-                        a[7] = __fma_rn(e1, wd, a[7]);
-                        tmem_st16(tacc + gi * TCOL, a);
-                        if (store) st_stream(o, fabs(lw));
-                    } else if (MODE == 1) {
+                    if (MODE == 1) {
                         double a[4];
                         tmem_ld8(tacc + gi * TCOL, a);
                         a[0] = __fma_rn(A1, wd, a[0]);
@@ -558,68 +467,12 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         if (more && tid < nd) {
             Qh[(s ^ 1) * nd + tid] = __fma_rn(qsg, Qn, 0.0);
             Ur[(s ^ 1) * nd + tid] = Un;
-            if (FUSE) Tr[(s ^ 1) * nd + tid] = Tn;
         }
         wd = wdn * p.dc;
         if (MODE == 1) tmem_wait_st();
     }
 
-    if (FUSE) {
-        // the column walk's tail: level kmax enters the means of u and of the meridional flux vector only
-        // (oopinterface.py:405-420, :964-982), the low-level heat flux comes from levels 1 and 2
-        // (compute_flux_dirinv.f90:160-171); then every vertical sum of this tile goes out
-        double* o2 = p.out2d + (size_t)b * p.o2_batch + (size_t)(fr.out_row0 + m00) * p.out_pitch + i0 + c;
-        const long long d_u = (long long)(p.uu - p.lwa);
-        const double wdk = p.vw[p.kmax - 1] * p.dc;
-        const double* tg = p.prof + (size_t)b * 4 * p.kmax + (fr.rev ? 0 : p.kmax);      // ts0 south / tn0 north
-        const double tg20 = tg[2] - tg[0], tg10 = tg[1] - tg[0];
-        const size_t ulast = (size_t)b * p.u_batch + (size_t)(p.kmax - 1) * p.u_kstride + p.u_row0[h];
-        const size_t tfirst = (size_t)b * p.t_batch + p.t_row0[h];
-        const double* top = out_k;                        // this lane's element of group 0 at level kmax
-#pragma unroll
-        for (int gi = 0; gi < GPW; ++gi) {
-            double a[8];
-            tmem_ld16(tacc + gi * TCOL, a);
-            const int j0 = j00 + 4 * NW * gi;
-            if (((validm >> gi) & 1) && colok) {
-                const double* ok = top + (long long)gi * out_gstep;
-                const double* o0 = ok - (long long)(p.kmax - 1) * out_lev;       // level 1
-                const double* o1 = o0 + out_lev;                                 // level 2
-                const double cl = clr[j0], c0 = cs0[j0];
-                {
-                    const double u0 = ok[d_u], v0 = ok[d_v], ur = p.uref ? p.uref[ulast + (long long)p.u_rstep[h] * j0] : 0.0;
-                    a[4] = __fma_rn(u0, wdk, a[4]);
-                    a[5] = __fma_rn(-(((u0 - ur) * v0) * cl), wdk, a[5]);
-                }
-                double ep4 = 0.0;
-                if ((actm >> gi) & 1) {
-                    const double tr0 = p.tref[tfirst + (long long)p.t_rstep[h] * j0];
-                    const double tr1 = p.tref[tfirst + (size_t)p.t_kstride + (long long)p.t_rstep[h] * j0];
-                    const double ep41 = 2. * p.om * p.sinphi[j0 + 1] * c0 * p.dz / p.prefac;
-                    const double ep42 = p.ep42fac * (sgn * o1[d_v]) * (o1[d_t] - tr1) / tg20;
-                    double ep43 = (sgn * o0[d_v]) * (o0[d_t] - tr0);
-                    ep43 = 0.5 * ep43 / tg10;
-                    ep4 = ep41 * (ep42 + ep43);
-                }
-                p.hs[(((size_t)b * p.nhemi + h) * nd + j0) * p.imax + i0 + c] = a[6];
-                if ((storem >> gi) & 1) {
-                    double* o = o2 + (long long)gi * out_gstep;
-                    o[(size_t)p.slot_a1 * p.o2_plane] = a[0];
-                    o[(size_t)p.slot_a2 * p.o2_plane] = a[1];
-                    o[(size_t)p.slot_lwa * p.o2_plane] = a[0] + a[1];
-                    o[(size_t)p.slot_ua1 * p.o2_plane] = a[2];
-                    o[(size_t)p.slot_ua2 * p.o2_plane] = a[3];
-                    o[(size_t)p.slot_ep1 * p.o2_plane] = a[7];
-                    o[(size_t)p.slot_ep2 * p.o2_plane] = 0.0;    // filled from the own-row sums by baro_post_kernel; the two
-                    o[(size_t)p.slot_ep3 * p.o2_plane] = 0.0;    // rows with special rules by flux_column_kernel<true, .>
-                    o[(size_t)p.slot_ep4 * p.o2_plane] = ep4;
-                    o[(size_t)p.slot_ncf * p.o2_plane] = (fr.sg < 0.0) ? -0.0 : 0.0;
-                    o[(size_t)p.slot_ubaro * p.o2_plane] = a[4];
-                    o[(size_t)p.slot_fphi * p.o2_plane] = a[5];
-                }
-            }
-        }
-    } else if (MODE == 1) {
+    if (MODE == 1) {
         double* o2 = p.out2d + (size_t)b * p.o2_batch + (size_t)(fr.out_row0 + m00) * p.out_pitch + i0 + c;
 #pragma unroll
         for (int gi = 0; gi < GPW; ++gi) {
@@ -636,8 +489,6 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                 if (HAS_NC) o[(size_t)p.slot_ncf * p.o2_plane] = (fr.sg < 0.0) ? -an : an;
             }
         }
-    }
-    if (MODE == 1) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (w == 0) tmem_dealloc(*reinterpret_cast<uint32_t*>(bars + 2), TMEM_COLS);
@@ -693,15 +544,6 @@ static bool win_supported(int imax, int nd, const void* pv, const void* uu, cons
     return nd >= 4 && nd <= kWinMaxRows && (imax % 2 == 0) && al(pv) && al(uu) && (!nc || al(nc)) && win_encoder() != nullptr;
 }
 
-template <int NW>
-static int win_launch_fused(const CUtensorMap& tq, const CUtensorMap& tu, const CUtensorMap& tn, const WinArgs& a, dim3 grid,
-                            size_t smem, cudaStream_t st) {
-    auto kern = lwa_window_kernel<1, false, false, NW, true>;
-    FALWA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, NW * 32, smem, st>>>(tq, tu, tn, a);
-    return 0;
-}
-
 template <int MODE, int NW>
 static int win_launch_mode(const CUtensorMap& tq, const CUtensorMap& tu, const CUtensorMap& tn, const WinArgs& a, bool has_nc,
                            dim3 grid, size_t smem, cudaStream_t st) {
@@ -711,12 +553,11 @@ static int win_launch_mode(const CUtensorMap& tq, const CUtensorMap& tu, const C
         return 0;
     };
     const bool count = a.mask_count != nullptr;
-    if (has_nc) return count ? go(lwa_window_kernel<MODE, true, true, NW, false>) : go(lwa_window_kernel<MODE, true, false, NW, false>);
-    return count ? go(lwa_window_kernel<MODE, false, true, NW, false>) : go(lwa_window_kernel<MODE, false, false, NW, false>);
+    if (has_nc) return count ? go(lwa_window_kernel<MODE, true, true, NW>) : go(lwa_window_kernel<MODE, true, false, NW>);
+    return count ? go(lwa_window_kernel<MODE, false, true, NW>) : go(lwa_window_kernel<MODE, false, false, NW>);
 }
 
 // pv / uu / nc: [batch][kmax][in_rows][imax]; a.k_first / k_count / frames / thresholds / outputs filled by the caller
-// mode: 0 = 3-D pieces per level, 1 = vertical sums + 3-D LWA, 2 = mode 1 with the column walk fused in
 static int lwa_window_launch(WinArgs a, int mode, const double* pv, const double* uu, const double* nc, int in_rows,
                              int batch, int nprob, cudaStream_t st) {
     const int nbox = (a.nd + 255) / 256;
@@ -729,18 +570,14 @@ static int lwa_window_launch(WinArgs a, int mode, const double* pv, const double
     if ((rc = win_tensor_map(&tu, uu, a.imax, in_rows, a.kmax, batch, boxrows))) return rc;
     if ((rc = win_tensor_map(&tn, nc ? nc : pv, a.imax, in_rows, a.kmax, batch, boxrows))) return rc;
     const int tiles = ceil_div(a.imax, kWinCols);
-    if (mode >= 1) a.k_per_cta = a.k_count;
+    if (mode == 1) a.k_per_cta = a.k_count;
     else a.k_per_cta = std::max(1, std::min(a.k_count, ceil_div((long long)a.k_count * tiles * nprob, 148 * 8)));
     const int chunks = ceil_div(a.k_count, a.k_per_cta);
-    const size_t smem = win_smem_layout(a.nd, nc ? 3 : 2, mode == 2).total;
+    const size_t smem = win_smem_layout(a.nd, nc ? 3 : 2).total;
     dim3 grid(tiles, chunks, nprob);
     FALWA_KERNEL("lwa_window_kernel", st);
     static const int nw = tune_int("FALWA_WIN_WARPS", 24);
-    if (mode == 2) {
-        if (nw == 16) rc = win_launch_fused<16>(tq, tu, tn, a, grid, smem, st);
-        else if (nw == 32) rc = win_launch_fused<32>(tq, tu, tn, a, grid, smem, st);
-        else rc = win_launch_fused<24>(tq, tu, tn, a, grid, smem, st);
-    } else if (mode == 1 && nw == 24) rc = win_launch_mode<1, 24>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
+    if (mode == 1 && nw == 24) rc = win_launch_mode<1, 24>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
     else if (mode == 1 && nw == 32) rc = win_launch_mode<1, 32>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
     else rc = mode == 1 ? win_launch_mode<1, 16>(tq, tu, tn, a, nc != nullptr, grid, smem, st)
                         : win_launch_mode<0, 16>(tq, tu, tn, a, nc != nullptr, grid, smem, st);

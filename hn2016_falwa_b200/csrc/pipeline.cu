@@ -1329,7 +1329,6 @@ static int lwa_fluxes_impl(const falwa_plan* P, int batch, const double* qgpv, c
     //         2 = interval scan, 3 = windowed sums
     const bool use_window = (method == 0 || method == 3) && !l3d && win_supported(nlon, nd, qgpv, u, ncforce);
     const bool use_scan = !use_window && (method != 1) && scan_supported(nd);
-    bool fused_walk = false;
     ScanTables tabs;
     if (use_window) {
         // 3-D LWA and the vertical sums of astar1, astar2, ua1, ua2 (, ncforce) in one walk over the levels
@@ -1354,20 +1353,7 @@ static int lwa_fluxes_impl(const falwa_plan* P, int batch, const double* qgpv, c
         w.slot_a1 = O_ASTAR1; w.slot_a2 = O_ASTAR2; w.slot_lwa = O_LWA; w.slot_ua1 = O_UA1; w.slot_ua2 = O_UA2;
         w.slot_ncf = O_NCF;
         w.mask_count = nullptr;
-        // without ncforce the column walk (pointwise flux terms and their vertical sums) is part of the same kernel
-        fused_walk = !ncforce && tune_int("FALWA_FUSED_WALK", 0);   // measured: no faster than the two kernels
-        if (fused_walk) {
-            if ((rc = hsum.alloc((size_t)batch * nhemi * nd * nlon, st))) return rc;
-            w.uu = u; w.vv = v; w.pt = theta;
-            w.tref = ptref_st; w.t_batch = (size_t)kmax * nlat; w.t_kstride = nlat;
-            for (int h = 0; h < 2; ++h) { w.t_row0[h] = nd - 1; w.t_rstep[h] = h ? -1 : 1; }
-            w.f11 = p.f11; w.prof = prof.d; w.clat = d + P->o_clat; w.sinphi = d + P->o_sinphi;
-            w.om = P->omega; w.dz = P->dz; w.prefac = P->prefactor; w.ep42fac = p.ep42fac;
-            w.hs = hsum.d;
-            w.slot_ep1 = O_EP1; w.slot_ep2 = O_EP2; w.slot_ep3 = O_EP3; w.slot_ep4 = O_EP4; w.slot_ubaro = O_UBARO;
-            w.slot_fphi = O_FPHI;
-        }
-        if ((rc = lwa_window_launch(w, fused_walk ? 2 : 1, qgpv, u, ncforce, nlat, batch, batch * nhemi, st))) return rc;
+        if ((rc = lwa_window_launch(w, 1, qgpv, u, ncforce, nlat, batch, batch * nhemi, st))) return rc;
     } else if (use_scan) {
         // LWA pieces a1, a2, ua2 (, ncforce3d) of every level by the interval scan, in the global frame
         const int narr = ncforce ? 4 : 3, nprob = batch * nhemi;
@@ -1404,9 +1390,6 @@ static int lwa_fluxes_impl(const falwa_plan* P, int batch, const double* qgpv, c
             FALWA_KERNEL("fused_flux_layerwise_kernel", st);
             if (use_scan) fused_flux_kernel<false><<<grid, block, 0, st>>>(p);
             else fused_flux_kernel<true><<<grid, block, 0, st>>>(p);
-        } else if (use_window && fused_walk) {   // only the two rows with special rules are left to walk
-            FALWA_KERNEL("flux_special_rows_kernel", st);
-            flux_column_kernel<true, true><<<dim3(ceil_div(nlon, 256), 2, batch * nhemi), 256, 0, st>>>(p, hsum.d);
         } else if (use_window) {
             if ((rc = hsum.alloc((size_t)batch * nhemi * nd * nlon, st))) return rc;
             FALWA_KERNEL("flux_uvt_column_kernel", st);
