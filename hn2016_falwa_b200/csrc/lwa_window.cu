@@ -64,6 +64,9 @@ __device__ __forceinline__ void win_mbar_init(uint64_t* bar, unsigned count) {
 __device__ __forceinline__ void win_mbar_expect(uint64_t* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(win_smem(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void win_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(win_smem(bar)) : "memory");
+}
 __device__ __forceinline__ void win_mbar_wait(uint64_t* bar, unsigned parity) {
     unsigned ok = 0;
     const uint32_t a = win_smem(bar);
@@ -86,23 +89,26 @@ __device__ __forceinline__ int win_key(double x) {
 // Shared-memory plan.  The tile stride is a compile-time constant so that, from the address of q(row, col), the
 // operands u(row, col) and aa(row) sit at immediate offsets (one address register per window step).
 constexpr int kWinTile = kWinMaxRows * kWinCols;     // doubles of one (rows x 8) tile slot
-// Bound arrays first, then the tiles — without ncforce [q0 | u0 | aa | q1 | u1 | aa], with it [q0 | u0 | n0 | aa | q1 | u1 | n1]
-// (one aa8 between the stages) — then the per-level tables.  Lanes of the last group that lie past the last row compute
-// on whatever sits at their (in-bounds, thanks to this order and the tail pad) addresses and never store.
+// Keys and bound arrays first, then the tiles — without ncforce [q0 | u0 | aa | q1 | u1 | aa], with it
+// [q0 | u0 | n0 | aa | q1 | u1 | n1] (one aa8 between the stages) — then the per-level tables.  Lanes of the last group
+// that lie past the last row compute on whatever sits at their (in-bounds, thanks to this order and the tail pad)
+// addresses and never store.  The bound arrays PE | PP exist once per level in flight (two without ncforce; with it the
+// third tile leaves room for one).
 struct WinSmem {
-    size_t off_keys, off_pe, off_pp, off_tiles, off_q, off_u, off_cs, off_bar, total;
+    int nbound;              // buffers of (PE | PP)
+    size_t off_keys, off_pe, off_tiles, off_q, off_u, off_cs, off_bar, total;
 };
 __host__ __device__ inline WinSmem win_smem_layout(int nd, int nfields) {
     WinSmem s;
+    s.nbound = nfields == 3 ? 1 : 2;
     size_t o = 0;
     s.off_keys = o; o += (size_t)kWinCols * kWinKeyPitch * 4;
-    s.off_pe = o; o += (size_t)kWinCols * kWinKeyPitch * 4;
-    s.off_pp = o; o += (size_t)kWinCols * kWinKeyPitch * 4;
+    s.off_pe = o; o += (size_t)s.nbound * 2 * kWinCols * kWinKeyPitch * 4;
     s.off_tiles = o; o += (size_t)(nfields == 3 ? 7 : 6) * kWinTile * 8;
     s.off_q = o; o += (size_t)2 * nd * 8;
     s.off_u = o; o += (size_t)2 * nd * 8;
     s.off_cs = o; o += (size_t)nd * 8;
-    s.off_bar = o; o += 32;
+    s.off_bar = o; o += 64;
     s.total = o + 256;
     return s;
 }
@@ -181,28 +187,41 @@ __device__ __forceinline__ void win_pair(double qv, double Qj, double av, double
     (void)HAS_NC;
 }
 
+// Roles.  NW compute warps own the 4-row groups (group g belongs to warp g % NW) and do nothing but the windowed sums;
+// kWinScan scan warps prepare each level for them — the hemispheric-frame PV and its keys, the two bound arrays of
+// every column, the thresholds of the level — one level ahead, and one of their threads issues the TMA loads.  The
+// hand-over is three mbarriers per stage: full (the tile has landed: TMA transaction count), ready (keys, bounds and
+// thresholds of the level are in place: one arrival per scan warp) and done (a compute warp has finished the level: one
+// arrival per compute warp; the stage and the bound buffer may be refilled).  No warp ever waits at a CTA-wide barrier
+// inside the level walk.
+constexpr int kWinScan = 8;   // one per column of the tile in the bound scans
+
 template <int MODE, bool HAS_NC, bool COUNT, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
+__global__ void __launch_bounds__((NW + kWinScan) * 32, 1)
 lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_u,
                   const __grid_constant__ CUtensorMap tm_n, const WinArgs p) {
     extern __shared__ __align__(1024) unsigned char win_raw[];
-    constexpr int NT = NW * 32;
-    constexpr int GPW = kWinMaxRows / (4 * NW);                          // 4-row groups a warp owns
+    constexpr int NT = (NW + kWinScan) * 32;
+    constexpr int GPW = kWinMaxRows / (4 * NW);                          // 4-row groups a compute warp owns
     constexpr int NF = HAS_NC ? 3 : 2;
+    constexpr int NB = HAS_NC ? 1 : 2;                                   // bound buffers (win_smem_layout)
     constexpr int P = kWinKeyPitch;
     constexpr int TU = kWinTile, TN = 2 * kWinTile;                      // u, nc relative to q (doubles)
     constexpr int SD = (HAS_NC ? 4 : 3) * kWinTile;                      // doubles between the two stages
+    constexpr int KB = 2 * kWinCols * P;                                 // ints of one (PE | PP) buffer
     constexpr unsigned FULL = 0xffffffffu;
     const int nd = p.nd;
     const WinSmem L = win_smem_layout(nd, NF);
     double* tiles = reinterpret_cast<double*>(win_raw + L.off_tiles);   // [stage][q | u | aa8 | nc][rows][8]
     int* keys = reinterpret_cast<int*>(win_raw + L.off_keys);           // [8][P], hemispheric row index
-    int* PE = reinterpret_cast<int*>(win_raw + L.off_pe);               // [8][P]: PE[x] = max key of rows < x
-    int* PP = reinterpret_cast<int*>(win_raw + L.off_pp);               // [8][P]: PP[x] = min key of rows >= x
+    int* PEPP = reinterpret_cast<int*>(win_raw + L.off_pe);             // [NB][PE | PP][8][P]
     double* Qh = reinterpret_cast<double*>(win_raw + L.off_q);          // [2][nd] thresholds of a level
     double* Ur = reinterpret_cast<double*>(win_raw + L.off_u);          // [2][nd] uref of a level
     double* abcs = reinterpret_cast<double*>(win_raw + L.off_cs);       // [nd] a dphi cos(phi_j)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(win_raw + L.off_bar);  // [2] "tile of this stage has landed"
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(win_raw + L.off_bar);   // [2]
+    uint64_t* bar_ready = bar_full + 2;                                       // [2]
+    uint64_t* bar_done = bar_full + 4;                                        // [2]
+    uint32_t* tbase = reinterpret_cast<uint32_t*>(bar_full + 6);
 
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int c = lane & 7, r = lane >> 3;
@@ -214,34 +233,18 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     const int kend = min(kbeg + p.k_per_cta, p.k_first + p.k_count);    // exclusive
     const int nlev = kend - kbeg;
     if (nlev <= 0) return;
-    const unsigned box_bytes = (unsigned)(p.boxrows * kWinCols * 8);
+    const double sgn = fr.sg;
+    // completion of level L by the compute warps: the (L >> 1)-th phase of done[L & 1]
+    auto wait_done = [&](int lev) { win_mbar_wait(&bar_done[lev & 1], (unsigned)((lev >> 1) & 1)); };
 
-    auto issue = [&](int li) {   // one elected thread: all boxes of level kbeg + li into stage li & 1
-        const int s = li & 1, k = kbeg + li;
-        win_mbar_expect(&bars[s], box_bytes * p.nbox * NF);
-        for (int bx = 0; bx < p.nbox; ++bx) {
-            const int row = fr.in_row0 + bx * p.boxrows;
-            double* dst = tiles + (size_t)s * SD + (size_t)bx * p.boxrows * kWinCols;
-            win_tma_load(dst, &tm_q, &bars[s], i0, row, k - 1, b);
-            win_tma_load(dst + TU, &tm_u, &bars[s], i0, row, k - 1, b);
-            if (HAS_NC) win_tma_load(dst + TN, &tm_n, &bars[s], i0, row, k - 1, b);
+    // ---- set-up by everybody -------------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            win_mbar_init(&bar_full[s], 1);
+            win_mbar_init(&bar_ready[s], kWinScan);
+            win_mbar_init(&bar_done[s], NW);
         }
-    };
-    // thresholds of hemispheric row tid + 1: per-thread source pointers, one level stride
-    const bool trow = tid < nd && tid + 1 >= p.jstart && tid + 1 <= p.jend;
-    const double* qsrc = trow ? p.qref + (size_t)b * p.q_batch + p.q_row0[h] + p.q_rstep[h] * tid : nullptr;
-    const double* usrc = (trow && p.uref) ? p.uref + (size_t)b * p.u_batch + p.u_row0[h] + p.u_rstep[h] * tid : nullptr;
-    const double qsg = p.q_sg[h];
-
-    if (tid == 0) {
-        win_mbar_init(&bars[0], 1);
-        win_mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
-        issue(0);
-        if (nlev > 1) issue(1);
     }
     for (int t = tid; t < nd * kWinCols; t += NT) {   // a dphi cos(phi) of every tile row
         const int m = t >> 3;
@@ -252,12 +255,12 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     for (int t = nd + tid; t < kWinSpan * 32; t += NT)   // rows beyond the column: neutral for the minima
 #pragma unroll
         for (int cc = 0; cc < kWinCols; ++cc) keys[cc * P + t] = INT_MAX;
-    if (tid < nd) {
-        abcs[tid] = p.ab * p.cosphi[tid + 1];
-        Qh[tid] = qsrc ? __fma_rn(qsg, qsrc[(size_t)(kbeg - 1) * p.q_kstride], 0.0) : 0.0;
-        Ur[tid] = usrc ? usrc[(size_t)(kbeg - 1) * p.u_kstride] : 0.0;
+    if (tid < nd) abcs[tid] = p.ab * p.cosphi[tid + 1];
+    if (tid < kWinCols * NB) {   // sentinels of both bound buffers: PE[0] = -inf, PP[nd] = +inf
+        int* base = PEPP + (tid / kWinCols) * KB + (tid % kWinCols) * P;
+        base[0] = INT_MIN;
+        base[kWinCols * P + nd] = INT_MAX;
     }
-    if (tid < kWinCols) { PE[tid * P] = INT_MIN; PP[tid * P + nd] = INT_MAX; }
     if (MODE == 1) {   // levels 1 and kmax of the 3-D LWA are zero (compute_flux_dirinv.f90 touches k = 2 .. kmax-1)
         for (int t = tid; t < nd * kWinCols; t += NT) {
             const int m = t >> 3, cc = t & 7;
@@ -269,237 +272,278 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             }
         }
     }
-
-    // accumulator file in tensor memory (MODE 1): this thread's columns of group gi start at tacc + gi * TCOL
+    // accumulator file in tensor memory (MODE 1): a compute thread's columns of group gi start at tacc + gi * TCOL
     constexpr int TCOL = HAS_NC ? 10 : 8;
-    constexpr unsigned TMEM_COLS = (NW / 4) * GPW * TCOL <= 256 ? 256 : 512;
-    uint32_t tacc = 0;
-    if (MODE == 1) {
-        uint32_t* tbase = reinterpret_cast<uint32_t*>(bars + 2);
-        if (w == 0) tmem_alloc(tbase, TMEM_COLS);
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tacc = *tbase + ((uint32_t)((w & 3) * 32) << 16) + (uint32_t)((w >> 2) * GPW * TCOL);
-        const double zero[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int gi = 0; gi < GPW; ++gi) {
-            tmem_st8(tacc + gi * TCOL, zero);
-            if (HAS_NC) tmem_st2(tacc + gi * TCOL + 8, 0.0);
-        }
-        tmem_wait_st();
-    }
-    unsigned cnt_c = 0, cnt_a = 0;
-    // this lane's element of group 0 of its warp; groups of a warp are NW groups = 4 NW rows apart.  What a lane does
-    // for a group does not depend on the level: one bit per group.
-    const int j00 = 4 * w + r;
-    const int m00 = fr.rev ? nd - 1 - j00 : j00;
-    const int mstep = fr.rev ? -4 * NW : 4 * NW;                      // tile rows between consecutive groups of a warp
-    unsigned validm = 0, actm = 0, storem = 0;
-#pragma unroll
-    for (int gi = 0; gi < GPW; ++gi) {
-        const int j0 = j00 + 4 * NW * gi;
-        const bool valid = j0 < nd;
-        if (valid) validm |= 1u << gi;
-        if (valid && colok && j0 + 1 >= p.jstart && j0 + 1 <= p.jend) actm |= 1u << gi;
-        if (valid && colok && !(fr.skip_first && j0 == 0)) storem |= 1u << gi;
-    }
-    asm volatile("" : "+r"(validm), "+r"(actm), "+r"(storem));          // keep the bits; do not re-derive them per level
-    const int ngroups = (nd - 4 * w + 4 * NW - 1) / (4 * NW);            // groups of this warp that exist (warp-uniform)
-    // Everything the level walk needs is held as 32-bit shared addresses / 64-bit global pointers that the compiler
-    // must treat as opaque values (it otherwise re-derives them from the kernel parameters in every group).
-    uint32_t stepb = fr.rev ? 64u : 0xffffffc0u;                         // bytes per row step toward the equator
-    uint32_t gbytes = (uint32_t)(mstep * kWinCols * 8);                  // bytes between consecutive groups of a warp
-    uint32_t a_t0 = win_smem(tiles) + (uint32_t)((m00 * kWinCols + c) * 8);   // this lane's element of group 0, stage 0
-    uint32_t a_key = win_smem(keys) + (uint32_t)((c * P + j00) * 4);     // ... its key; PE / PP follow at fixed offsets
-    uint32_t a_tab = win_smem(Qh) + (uint32_t)(j00 * 8);                 // ... its threshold; Ur / abcs at fixed offsets
-    const uint32_t o_ur = (uint32_t)((Ur - Qh) * 8), o_cs = (uint32_t)((abcs - Qh) * 8);
-    double* out_k = (MODE == 1 ? p.lwa + (size_t)b * p.lwa_batch + (size_t)(kbeg - 1) * p.lwa_plane
-                               : p.a1 + (size_t)b * p.out_batch + (size_t)(kbeg - 1) * p.out_plane) +
-                    (size_t)(fr.out_row0 + m00) * p.out_pitch + i0 + c;
-    long long out_lev = (long long)((MODE == 1) ? p.lwa_plane : p.out_plane);
-    long long out_gstep = (long long)mstep * p.out_pitch;
-    asm volatile("" : "+r"(stepb), "+r"(gbytes), "+r"(a_t0), "+r"(a_key), "+r"(a_tab), "+l"(out_k), "+l"(out_lev), "+l"(out_gstep));
-    constexpr int KPE = kWinCols * P * 4, KPP = 2 * kWinCols * P * 4;    // PE, PP relative to keys (bytes)
-    constexpr int GK = 4 * NW * 4, GT = 4 * NW * 8;                      // key / table bytes between groups of a warp
-    const double sgn = fr.sg;
+    constexpr unsigned TMEM_COLS = ((NW + 3) / 4) * GPW * TCOL <= 256 ? 256 : 512;
+    if (MODE == 1 && w == 0) tmem_alloc(tbase, TMEM_COLS);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    double wd = (MODE == 1) ? p.vw[kbeg - 1] * p.dc : 0.0;
-    for (int li = 0; li < nlev; ++li) {
-        const int s = li & 1, k = kbeg + li;
-        uint32_t a_t = a_t0 + (uint32_t)(s * SD * 8);                     // this lane's element of group 0 in this stage
-        uint32_t a_q = a_tab + (uint32_t)(s * nd * 8);                    // table buffers alternate like the tile stages
-        asm volatile("" : "+r"(a_t), "+r"(a_q));
-        const uint32_t TAb = (uint32_t)((HAS_NC ? (s ? -kWinTile : 3 * kWinTile) : 2 * kWinTile) * 8);   // aa8 from q
-        // thresholds and weight of the next level travel while this one is computed
-        const bool more = li + 1 < nlev;
-        double Qn = 0.0, Un = 0.0, wdn = 0.0;
-        if (more && qsrc) Qn = qsrc[(size_t)k * p.q_kstride];
-        if (more && usrc) Un = usrc[(size_t)k * p.u_kstride];
-        if (MODE == 1 && more) wdn = p.vw[k];
-        win_mbar_wait(&bars[s], (unsigned)((li >> 1) & 1));
-
-        // ---- phase 1: hemispheric-frame PV (sign, -0 -> +0) and its keys ---------------------------
-        {
-            double q[GPW];
-#pragma unroll
-            for (int gi = 0; gi < GPW; ++gi) q[gi] = ((validm >> gi) & 1) ? lds64(a_t + gi * gbytes) : 0.0;
-#pragma unroll
-            for (int gi = 0; gi < GPW; ++gi)
-                if ((validm >> gi) & 1) {
-                    const double qh = __fma_rn(sgn, q[gi], 0.0);
-                    if (sgn != 1.0) sts64(a_t + gi * gbytes, qh);
-                    sts32(a_key + gi * GK, win_key(qh));
-                }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // see the TMA issue below
-        __syncthreads();
-        // Every warp has finished the previous level: its stage is free.  The load of level li + 1 has the rest of
-        // this level to land.
-        if (tid == 0 && li >= 1 && more) issue(li + 1);
-        // ---- phase 2: the two monotone bound arrays of every column, one warp per (column, direction) -
-        {
-            int incl[kWinSpan];
-            if (w < 8) {   // PE[x] = max key over rows < x  (PE[0] = -inf); rows beyond nd do not reach entries <= nd
-                const int* kp = keys + w * P + kWinSpan * lane;
-                int run = INT_MIN;
-#pragma unroll
-                for (int t = 0; t < kWinSpan; ++t) { run = max(run, kp[t]); incl[t] = run; }
-                int ex = run;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int n = __shfl_up_sync(FULL, ex, d);
-                    if (lane >= d) ex = max(ex, n);
-                }
-                int off = __shfl_up_sync(FULL, ex, 1);
-                if (lane == 0) off = INT_MIN;
-                int* op = PE + w * P + kWinSpan * lane + 1;
-#pragma unroll
-                for (int t = 0; t < kWinSpan; ++t) op[t] = max(off, incl[t]);
-            } else if (w < 16) {       // PP[x] = min key over rows >= x  (PP[nd] = +inf; rows beyond nd hold +inf keys)
-                const int* kp = keys + (w - 8) * P + kWinSpan * lane;
-                int run = INT_MAX;
-#pragma unroll
-                for (int t = kWinSpan - 1; t >= 0; --t) { run = min(run, kp[t]); incl[t] = run; }
-                int ex = run;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int n = __shfl_down_sync(FULL, ex, d);
-                    if (lane + d < 32) ex = min(ex, n);
-                }
-                int off = __shfl_down_sync(FULL, ex, 1);
-                if (lane == 31) off = INT_MAX;
-                int* op = PP + (w - 8) * P + kWinSpan * lane;
-#pragma unroll
-                for (int t = 0; t < kWinSpan; ++t) op[t] = min(off, incl[t]);
+    if (w >= NW) {
+        // =====================================================================================================
+        // scan warps: tile -> keys -> bounds, thresholds, TMA issue
+        // =====================================================================================================
+        const int ws = w - NW, stid = tid - NW * 32;
+        const unsigned box_bytes = (unsigned)(p.boxrows * kWinCols * 8);
+        auto issue = [&](int li) {   // one thread: all boxes of level kbeg + li into stage li & 1
+            const int s = li & 1, k = kbeg + li;
+            win_mbar_expect(&bar_full[s], box_bytes * p.nbox * NF);
+            for (int bx = 0; bx < p.nbox; ++bx) {
+                const int row = fr.in_row0 + bx * p.boxrows;
+                double* dst = tiles + (size_t)s * SD + (size_t)bx * p.boxrows * kWinCols;
+                win_tma_load(dst, &tm_q, &bar_full[s], i0, row, k - 1, b);
+                win_tma_load(dst + TU, &tm_u, &bar_full[s], i0, row, k - 1, b);
+                if (HAS_NC) win_tma_load(dst + TN, &tm_n, &bar_full[s], i0, row, k - 1, b);
             }
+        };
+        if (stid == 0) {
+            issue(0);
+            if (nlev > 1) issue(1);
         }
-        __syncthreads();
-        // ---- main: the two windowed sums of every threshold row ----------------------------------------
-        double* o = out_k;
+        const double qsg = p.q_sg[h];
+        constexpr int TPT = (kWinMaxRows + kWinScan * 32 - 1) / (kWinScan * 32);   // threshold rows per scan thread
+        for (int li = 0; li < nlev; ++li) {
+            const int s = li & 1, k = kbeg + li;
+            double* const tq = tiles + (size_t)s * SD;
+            int* const PE = PEPP + (li % NB) * KB;
+            int* const PP = PE + kWinCols * P;
+            // thresholds of this level: requested now, stored once the buffers are known to be free
+            double Qv[TPT], Uv[TPT];
+#pragma unroll
+            for (int x = 0; x < TPT; ++x) {
+                const int j0 = stid + x * kWinScan * 32;
+                Qv[x] = Uv[x] = 0.0;
+                if (j0 < nd && j0 + 1 >= p.jstart && j0 + 1 <= p.jend) {
+                    Qv[x] = p.qref[(size_t)b * p.q_batch + (size_t)(k - 1) * p.q_kstride + p.q_row0[h] + p.q_rstep[h] * j0];
+                    if (p.uref) Uv[x] = p.uref[(size_t)b * p.u_batch + (size_t)(k - 1) * p.u_kstride + p.u_row0[h] + p.u_rstep[h] * j0];
+                }
+            }
+            if (li >= 2) {   // the compute warps have left level li - 2: its stage and table buffer are free
+                wait_done(li - 2);
+                if (stid == 0) issue(li);
+            }
+            if (NB == 1 && li >= 1) wait_done(li - 1);   // a single bound buffer: its readers must be gone too
+#pragma unroll
+            for (int x = 0; x < TPT; ++x) {
+                const int j0 = stid + x * kWinScan * 32;
+                if (j0 < nd) { Qh[s * nd + j0] = __fma_rn(qsg, Qv[x], 0.0); Ur[s * nd + j0] = Uv[x]; }
+            }
+            win_mbar_wait(&bar_full[s], (unsigned)((li >> 1) & 1));
+            // phase 1: hemispheric-frame PV (sign, -0 -> +0) and its keys; four groups of a warp in flight at a time
+            for (int g0 = ws; 4 * g0 < nd; g0 += 4 * kWinScan) {
+                double qv[4];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int j0 = 4 * (g0 + x * kWinScan) + r;
+                    qv[x] = (j0 < nd) ? tq[(fr.rev ? nd - 1 - j0 : j0) * kWinCols + c] : 0.0;
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int j0 = 4 * (g0 + x * kWinScan) + r;
+                    if (j0 < nd) {
+                        const double qh = __fma_rn(sgn, qv[x], 0.0);
+                        if (sgn != 1.0) tq[(fr.rev ? nd - 1 - j0 : j0) * kWinCols + c] = qh;
+                        keys[c * P + j0] = win_key(qh);
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile is refilled by the async proxy later
+            asm volatile("bar.sync 1, %0;" ::"n"(kWinScan * 32) : "memory");
+            // phase 2: the two monotone bound arrays of column ws, from one read of its keys: a lane takes 13
+            // consecutive rows, PE[x] = max key over rows < x (rows beyond nd do not reach entries <= nd),
+            // PP[x] = min key over rows >= x (rows beyond nd hold +inf keys)
+            {
+                static_assert(kWinScan == kWinCols, "one scan warp per column");
+                const int* kp = keys + ws * P + kWinSpan * lane;
+                int kv[kWinSpan], mx[kWinSpan], mn[kWinSpan];
+#pragma unroll
+                for (int t = 0; t < kWinSpan; ++t) kv[t] = kp[t];
+                int rmx = INT_MIN, rmn = INT_MAX;
+#pragma unroll
+                for (int t = 0; t < kWinSpan; ++t) {
+                    rmx = max(rmx, kv[t]); mx[t] = rmx;
+                    rmn = min(rmn, kv[kWinSpan - 1 - t]); mn[kWinSpan - 1 - t] = rmn;
+                }
+                int ex = rmx, en = rmn;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int a = __shfl_up_sync(FULL, ex, d), bb = __shfl_down_sync(FULL, en, d);
+                    if (lane >= d) ex = max(ex, a);
+                    if (lane + d < 32) en = min(en, bb);
+                }
+                int offx = __shfl_up_sync(FULL, ex, 1), offn = __shfl_down_sync(FULL, en, 1);
+                if (lane == 0) offx = INT_MIN;
+                if (lane == 31) offn = INT_MAX;
+                int* opx = PE + ws * P + kWinSpan * lane + 1;
+                int* opn = PP + ws * P + kWinSpan * lane;
+#pragma unroll
+                for (int t = 0; t < kWinSpan; ++t) { opx[t] = max(offx, mx[t]); opn[t] = min(offn, mn[t]); }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kWinScan * 32) : "memory");   // keys are rewritten next level
+            if (lane == 0) win_mbar_arrive(&bar_ready[s]);
+        }
+    } else {
+        // =====================================================================================================
+        // compute warps
+        // =====================================================================================================
+        uint32_t tacc = 0;
+        if (MODE == 1) {
+            tacc = *tbase + ((uint32_t)((w & 3) * 32) << 16) + (uint32_t)((w >> 2) * GPW * TCOL);
+            const double zero[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int gi = 0; gi < GPW; ++gi) {
+                tmem_st8(tacc + gi * TCOL, zero);
+                if (HAS_NC) tmem_st2(tacc + gi * TCOL + 8, 0.0);
+            }
+            tmem_wait_st();
+        }
+        unsigned cnt_c = 0, cnt_a = 0;
+        // this lane's element of group 0 of its warp; groups of a warp are NW groups = 4 NW rows apart.  What a lane
+        // does for a group does not depend on the level: one bit per group.
+        const int j00 = 4 * w + r;
+        const int m00 = fr.rev ? nd - 1 - j00 : j00;
+        const int mstep = fr.rev ? -4 * NW : 4 * NW;                  // tile rows between consecutive groups of a warp
+        unsigned actm = 0, storem = 0;
 #pragma unroll
         for (int gi = 0; gi < GPW; ++gi) {
-            if (gi < ngroups) {   // warp-uniform
-                const bool act = (actm >> gi) & 1;
-                const uint32_t at = a_t + gi * gbytes, ak = a_key + gi * GK, aq = a_q + gi * GT;
-                const double Qj = lds64(aq);
-                const int kq = win_key(Qj);
-                const int kqc = max(kq, INT_MIN + 1);   // "may exceed Q_j":      key >= kqc  (never true at PE[0])
-                const int kqa = min(kq, INT_MAX - 1);   // "may not exceed Q_j":  key <= kqa  (never true at PP[nd])
-                double A1 = 0.0, A2 = 0.0, B = 0.0, N = 0.0;
-                {   // cyclonic side: rows j0-1, j0-2, ... while some row at or beyond may exceed Q_j
-                    uint32_t t = at, pk = ak;
-                    bool mine = act && (lds32o<KPE>(pk) >= kqc);
-                    while (__any_sync(FULL, mine)) {
-                        if (mine) { t += stepb; pk -= 4; }     // finished lanes keep re-reading their last row
-                        const double qv = lds64(t), uv = lds64o<TU * 8>(t), av = lds64(t + TAb);
-                        const double nv = HAS_NC ? lds64o<TN * 8>(t) : 0.0;
-                        const int pe = lds32o<KPE>(pk);
-                        win_pair<false, HAS_NC, COUNT>(qv, Qj, av, uv, nv, mine, A1, B, N, cnt_c);
-                        mine = mine && (pe >= kqc);
-                    }
-                }
-                {   // anticyclonic side: rows j0, j0+1, ... while some row at or beyond may not exceed Q_j
-                    uint32_t t = at, pk = ak;
-                    bool mine = act && (lds32o<KPP>(pk) <= kqa);
-                    while (__any_sync(FULL, mine)) {
-                        const double qv = lds64(t), uv = lds64o<TU * 8>(t), av = lds64(t + TAb);
-                        const double nv = HAS_NC ? lds64o<TN * 8>(t) : 0.0;
-                        const int pp = lds32o<KPP + 4>(pk);
-                        win_pair<true, HAS_NC, COUNT>(qv, Qj, av, uv, nv, mine, A2, B, N, cnt_a);
-                        mine = mine && (pp <= kqa);
-                        if (mine) { t -= stepb; pk += 4; }
-                    }
-                }
-                {
-                    // a1 = A1, a2 = A2;  ua2 = a dphi cos(phi_j) B - uref_j (a1 + a2)   (compute_flux_dirinv.f90:96-113)
-                    // (lanes past the last row and inactive rows carry A1 = A2 = B = N = 0; they store nothing)
-                    const double lw = A1 + A2;
-                    const double x1 = lds64(aq + o_ur) * lw;
-                    const double u2 = __fma_rn(lds64(a_tab + o_cs + gi * GT), B, -x1);
-                    const bool store = (storem >> gi) & 1;
-                    if (MODE == 1) {
-                        double a[4];
-                        tmem_ld8(tacc + gi * TCOL, a);
-                        a[0] = __fma_rn(A1, wd, a[0]);
-                        a[1] = __fma_rn(A2, wd, a[1]);
-                        a[2] = __fma_rn(x1, wd, a[2]);
-                        a[3] = __fma_rn(u2, wd, a[3]);
-                        tmem_st8(tacc + gi * TCOL, a);
-                        if (HAS_NC) {
-                            double an;
-                            tmem_ld2(tacc + gi * TCOL + 8, an);
-                            tmem_st2(tacc + gi * TCOL + 8, __fma_rn(N, wd, an));
+            const int j0 = j00 + 4 * NW * gi;
+            const bool valid = j0 < nd;
+            if (valid && colok && j0 + 1 >= p.jstart && j0 + 1 <= p.jend) actm |= 1u << gi;
+            if (valid && colok && !(fr.skip_first && j0 == 0)) storem |= 1u << gi;
+        }
+        asm volatile("" : "+r"(actm), "+r"(storem));                    // keep the bits; do not re-derive them per level
+        const int ngroups = (nd - 4 * w + 4 * NW - 1) / (4 * NW);        // groups of this warp that exist (warp-uniform)
+        // Everything the level walk needs is held as 32-bit shared addresses / 64-bit global pointers that the compiler
+        // must treat as opaque values (it otherwise re-derives them from the kernel parameters in every group).
+        uint32_t stepb = fr.rev ? 64u : 0xffffffc0u;                     // bytes per row step toward the equator
+        uint32_t gbytes = (uint32_t)(mstep * kWinCols * 8);              // bytes between consecutive groups of a warp
+        uint32_t a_t0 = win_smem(tiles) + (uint32_t)((m00 * kWinCols + c) * 8);   // this lane's element of group 0, stage 0
+        uint32_t a_pe0 = win_smem(PEPP) + (uint32_t)((c * P + j00) * 4);  // ... its entry of PE (buffer 0); PP follows
+        uint32_t a_tab = win_smem(Qh) + (uint32_t)(j00 * 8);             // ... its threshold; Ur / abcs at fixed offsets
+        const uint32_t o_ur = (uint32_t)((Ur - Qh) * 8), o_cs = (uint32_t)((abcs - Qh) * 8);
+        double* out_k = (MODE == 1 ? p.lwa + (size_t)b * p.lwa_batch + (size_t)(kbeg - 1) * p.lwa_plane
+                                   : p.a1 + (size_t)b * p.out_batch + (size_t)(kbeg - 1) * p.out_plane) +
+                        (size_t)(fr.out_row0 + m00) * p.out_pitch + i0 + c;
+        long long out_lev = (long long)((MODE == 1) ? p.lwa_plane : p.out_plane);
+        long long out_gstep = (long long)mstep * p.out_pitch;
+        asm volatile("" : "+r"(stepb), "+r"(gbytes), "+r"(a_t0), "+r"(a_pe0), "+r"(a_tab), "+l"(out_k), "+l"(out_lev), "+l"(out_gstep));
+        constexpr int KPP = kWinCols * P * 4;                            // PP relative to PE (bytes)
+        constexpr int GK = 4 * NW * 4, GT = 4 * NW * 8;                  // key / table bytes between groups of a warp
+
+        for (int li = 0; li < nlev; ++li) {
+            const int s = li & 1, k = kbeg + li;
+            uint32_t a_t = a_t0 + (uint32_t)(s * SD * 8);                 // this lane's element of group 0 in this stage
+            uint32_t a_q = a_tab + (uint32_t)(s * nd * 8);                // table buffers alternate like the tile stages
+            uint32_t a_k = a_pe0 + (uint32_t)((li % NB) * KB * 4);        // ... and the bound buffers
+            asm volatile("" : "+r"(a_t), "+r"(a_q), "+r"(a_k));
+            const uint32_t TAb = (uint32_t)((HAS_NC ? (s ? -kWinTile : 3 * kWinTile) : 2 * kWinTile) * 8);   // aa8 from q
+            const double wd = (MODE == 1) ? p.vw[k - 1] * p.dc : 0.0;
+            win_mbar_wait(&bar_ready[s], (unsigned)((li >> 1) & 1));     // keys, bounds and thresholds are in place
+            win_mbar_wait(&bar_full[s], (unsigned)((li >> 1) & 1));      // (complete by now: observed for the TMA writes)
+            double* o = out_k;
+#pragma unroll
+            for (int gi = 0; gi < GPW; ++gi) {
+                if (gi < ngroups) {   // warp-uniform
+                    const bool act = (actm >> gi) & 1;
+                    const uint32_t at = a_t + gi * gbytes, ak = a_k + gi * GK, aq = a_q + gi * GT;
+                    const double Qj = lds64(aq);
+                    const int kq = win_key(Qj);
+                    const int kqc = max(kq, INT_MIN + 1);   // "may exceed Q_j":      key >= kqc  (never true at PE[0])
+                    const int kqa = min(kq, INT_MAX - 1);   // "may not exceed Q_j":  key <= kqa  (never true at PP[nd])
+                    double A1 = 0.0, A2 = 0.0, B = 0.0, N = 0.0;
+                    {   // cyclonic side: rows j0-1, j0-2, ... while some row at or beyond may exceed Q_j
+                        uint32_t t = at, pk = ak;
+                        bool mine = act && (lds32(pk) >= kqc);
+                        while (__any_sync(FULL, mine)) {
+                            if (mine) { t += stepb; pk -= 4; }     // finished lanes keep re-reading their last row
+                            const double qv = lds64(t), uv = lds64o<TU * 8>(t), av = lds64(t + TAb);
+                            const double nv = HAS_NC ? lds64o<TN * 8>(t) : 0.0;
+                            const int pe = lds32(pk);
+                            win_pair<false, HAS_NC, COUNT>(qv, Qj, av, uv, nv, mine, A1, B, N, cnt_c);
+                            mine = mine && (pe >= kqc);
                         }
-                        if (store) st_stream(o, fabs(lw));
-                    } else if (store) {
-                        o[0] = A1;
-                        o[p.a2 - p.a1] = A2;
-                        if (p.u2) o[p.u2 - p.a1] = u2;
-                        if (HAS_NC && p.ncf) o[p.ncf - p.a1] = N;
                     }
-                    o += out_gstep;
+                    {   // anticyclonic side: rows j0, j0+1, ... while some row at or beyond may not exceed Q_j
+                        uint32_t t = at, pk = ak;
+                        bool mine = act && (lds32o<KPP>(pk) <= kqa);
+                        while (__any_sync(FULL, mine)) {
+                            const double qv = lds64(t), uv = lds64o<TU * 8>(t), av = lds64(t + TAb);
+                            const double nv = HAS_NC ? lds64o<TN * 8>(t) : 0.0;
+                            const int pp = lds32o<KPP + 4>(pk);
+                            win_pair<true, HAS_NC, COUNT>(qv, Qj, av, uv, nv, mine, A2, B, N, cnt_a);
+                            mine = mine && (pp <= kqa);
+                            if (mine) { t -= stepb; pk += 4; }
+                        }
+                    }
+                    {
+                        // a1 = A1, a2 = A2;  ua2 = a dphi cos(phi_j) B - uref_j (a1 + a2)   (compute_flux_dirinv.f90:96-113)
+                        // (lanes past the last row and inactive rows carry A1 = A2 = B = N = 0; they store nothing)
+                        const double lw = A1 + A2;
+                        const double x1 = lds64(aq + o_ur) * lw;
+                        const double u2 = __fma_rn(lds64(a_tab + o_cs + gi * GT), B, -x1);
+                        const bool store = (storem >> gi) & 1;
+                        if (MODE == 1) {
+                            double a[4];
+                            tmem_ld8(tacc + gi * TCOL, a);
+                            a[0] = __fma_rn(A1, wd, a[0]);
+                            a[1] = __fma_rn(A2, wd, a[1]);
+                            a[2] = __fma_rn(x1, wd, a[2]);
+                            a[3] = __fma_rn(u2, wd, a[3]);
+                            tmem_st8(tacc + gi * TCOL, a);
+                            if (HAS_NC) {
+                                double an;
+                                tmem_ld2(tacc + gi * TCOL + 8, an);
+                                tmem_st2(tacc + gi * TCOL + 8, __fma_rn(N, wd, an));
+                            }
+                            if (store) st_stream(o, fabs(lw));
+                        } else if (store) {
+                            o[0] = A1;
+                            o[p.a2 - p.a1] = A2;
+                            if (p.u2) o[p.u2 - p.a1] = u2;
+                            if (HAS_NC && p.ncf) o[p.ncf - p.a1] = N;
+                        }
+                        o += out_gstep;
+                    }
+                }
+            }
+            out_k += out_lev;
+            if (MODE == 1) tmem_wait_st();
+            __syncwarp();
+            if (lane == 0) win_mbar_arrive(&bar_done[s]);   // this warp has left the level
+        }
+
+        if (MODE == 1) {
+            double* o2 = p.out2d + (size_t)b * p.o2_batch + (size_t)(fr.out_row0 + m00) * p.out_pitch + i0 + c;
+#pragma unroll
+            for (int gi = 0; gi < GPW; ++gi) {
+                double a[4], an = 0.0;
+                tmem_ld8(tacc + gi * TCOL, a);
+                if (HAS_NC) tmem_ld2(tacc + gi * TCOL + 8, an);
+                if ((storem >> gi) & 1) {
+                    double* o = o2 + (long long)gi * out_gstep;
+                    o[(size_t)p.slot_a1 * p.o2_plane] = a[0];
+                    o[(size_t)p.slot_a2 * p.o2_plane] = a[1];
+                    o[(size_t)p.slot_lwa * p.o2_plane] = a[0] + a[1];
+                    o[(size_t)p.slot_ua1 * p.o2_plane] = a[2];
+                    o[(size_t)p.slot_ua2 * p.o2_plane] = a[3];
+                    if (HAS_NC) o[(size_t)p.slot_ncf * p.o2_plane] = (fr.sg < 0.0) ? -an : an;
                 }
             }
         }
-        out_k += out_lev;
-        // next level's thresholds into the other table buffer (its last readers finished a level ago)
-        if (more && tid < nd) {
-            Qh[(s ^ 1) * nd + tid] = __fma_rn(qsg, Qn, 0.0);
-            Ur[(s ^ 1) * nd + tid] = Un;
-        }
-        wd = wdn * p.dc;
-        if (MODE == 1) tmem_wait_st();
-    }
-
-    if (MODE == 1) {
-        double* o2 = p.out2d + (size_t)b * p.o2_batch + (size_t)(fr.out_row0 + m00) * p.out_pitch + i0 + c;
-#pragma unroll
-        for (int gi = 0; gi < GPW; ++gi) {
-            double a[4], an = 0.0;
-            tmem_ld8(tacc + gi * TCOL, a);
-            if (HAS_NC) tmem_ld2(tacc + gi * TCOL + 8, an);
-            if ((storem >> gi) & 1) {
-                double* o = o2 + (long long)gi * out_gstep;
-                o[(size_t)p.slot_a1 * p.o2_plane] = a[0];
-                o[(size_t)p.slot_a2 * p.o2_plane] = a[1];
-                o[(size_t)p.slot_lwa * p.o2_plane] = a[0] + a[1];
-                o[(size_t)p.slot_ua1 * p.o2_plane] = a[2];
-                o[(size_t)p.slot_ua2 * p.o2_plane] = a[3];
-                if (HAS_NC) o[(size_t)p.slot_ncf * p.o2_plane] = (fr.sg < 0.0) ? -an : an;
+        if (COUNT && p.mask_count) {
+            cnt_c = __reduce_add_sync(FULL, cnt_c);
+            cnt_a = __reduce_add_sync(FULL, cnt_a);
+            if (lane == 0 && (cnt_c | cnt_a)) {
+                atomicAdd(&p.mask_count[0], (unsigned long long)cnt_a);
+                atomicAdd(&p.mask_count[1], (unsigned long long)cnt_c);
             }
         }
+    }
+    if (MODE == 1) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (w == 0) tmem_dealloc(*reinterpret_cast<uint32_t*>(bars + 2), TMEM_COLS);
-    }
-    if (COUNT && p.mask_count) {
-        cnt_c = __reduce_add_sync(FULL, cnt_c);
-        cnt_a = __reduce_add_sync(FULL, cnt_a);
-        if (lane == 0 && (cnt_c | cnt_a)) {
-            atomicAdd(&p.mask_count[0], (unsigned long long)cnt_a);
-            atomicAdd(&p.mask_count[1], (unsigned long long)cnt_c);
-        }
+        if (w == 0) tmem_dealloc(*tbase, TMEM_COLS);
     }
 }
 
@@ -549,7 +593,7 @@ static int win_launch_mode(const CUtensorMap& tq, const CUtensorMap& tu, const C
                            dim3 grid, size_t smem, cudaStream_t st) {
     auto go = [&](auto kern) -> int {
         FALWA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, NW * 32, smem, st>>>(tq, tu, tn, a);
+        kern<<<grid, (NW + kWinScan) * 32, smem, st>>>(tq, tu, tn, a);
         return 0;
     };
     const bool count = a.mask_count != nullptr;
@@ -576,9 +620,8 @@ static int lwa_window_launch(WinArgs a, int mode, const double* pv, const double
     const size_t smem = win_smem_layout(a.nd, nc ? 3 : 2).total;
     dim3 grid(tiles, chunks, nprob);
     FALWA_KERNEL("lwa_window_kernel", st);
-    static const int nw = tune_int("FALWA_WIN_WARPS", 24);
+    static const int nw = tune_int("FALWA_WIN_WARPS", 16);
     if (mode == 1 && nw == 24) rc = win_launch_mode<1, 24>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
-    else if (mode == 1 && nw == 32) rc = win_launch_mode<1, 32>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
     else rc = mode == 1 ? win_launch_mode<1, 16>(tq, tu, tn, a, nc != nullptr, grid, smem, st)
                         : win_launch_mode<0, 16>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
     if (rc) return rc;
