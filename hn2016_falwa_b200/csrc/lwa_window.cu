@@ -55,6 +55,7 @@ struct WinArgs {
     double *lwa, *out2d; const double* vw; double dc; size_t lwa_batch, lwa_plane, o2_batch, o2_plane;
     int slot_a1, slot_a2, slot_lwa, slot_ua1, slot_ua2, slot_ncf;
     unsigned long long* mask_count;         // optional: [0] anticyclonic pairs, [1] cyclonic pairs
+    int dbg;                                // timing experiments only (FALWA_WIN_DEBUG): 1 = no window loops, 2 = no scans
 };
 
 __device__ __forceinline__ uint32_t win_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -88,27 +89,26 @@ __device__ __forceinline__ int win_key(double x) {
 
 // Shared-memory plan.  The tile stride is a compile-time constant so that, from the address of q(row, col), the
 // operands u(row, col) and aa(row) sit at immediate offsets (one address register per window step).
-constexpr int kWinTile = kWinMaxRows * kWinCols;     // doubles of one (rows x 8) tile slot
-// Keys and bound arrays first, then the tiles — without ncforce [q0 | u0 | aa | q1 | u1 | aa], with it
-// [q0 | u0 | n0 | aa | q1 | u1 | n1] (one aa8 between the stages) — then the per-level tables.  Lanes of the last group
-// that lie past the last row compute on whatever sits at their (in-bounds, thanks to this order and the tail pad)
-// addresses and never store.  The bound arrays PE | PP exist once per level in flight (two without ncforce; with it the
-// third tile leaves room for one).
+// Keys and bound arrays first, then the tile stages [q | u (| nc)] — three stages of 368-row slots when the column fits
+// and there is no ncforce tile (TMA runs two levels ahead of the compute warps), else two stages of 384-row slots — then
+// the per-level tables.  Lanes of the last group that lie past the last row compute on whatever sits at their
+// (in-bounds, thanks to this order and the tail pad) addresses and never store.  The bound arrays PE | PP exist twice
+// (two levels in flight) unless the ncforce tile takes the room.
+__host__ __device__ constexpr int win_tile_rows(int nstage) { return nstage == 3 ? 368 : kWinMaxRows; }
 struct WinSmem {
-    int nbound;              // buffers of (PE | PP)
     size_t off_keys, off_pe, off_tiles, off_q, off_u, off_cs, off_bar, total;
 };
-__host__ __device__ inline WinSmem win_smem_layout(int nd, int nfields) {
+__host__ __device__ inline WinSmem win_smem_layout(int nd, int nfields, int nstage) {
     WinSmem s;
-    s.nbound = nfields == 3 ? 1 : 2;
+    const int nbound = nfields == 3 ? 1 : 2;
     size_t o = 0;
     s.off_keys = o; o += (size_t)kWinCols * kWinKeyPitch * 4;
-    s.off_pe = o; o += (size_t)s.nbound * 2 * kWinCols * kWinKeyPitch * 4;
-    s.off_tiles = o; o += (size_t)(nfields == 3 ? 7 : 6) * kWinTile * 8;
-    s.off_q = o; o += (size_t)2 * nd * 8;
-    s.off_u = o; o += (size_t)2 * nd * 8;
+    s.off_pe = o; o += (size_t)nbound * 2 * kWinCols * kWinKeyPitch * 4;
+    s.off_tiles = o; o += (size_t)nstage * nfields * win_tile_rows(nstage) * kWinCols * 8;
+    s.off_q = o; o += (size_t)nstage * nd * 8;
+    s.off_u = o; o += (size_t)nstage * nd * 8;
     s.off_cs = o; o += (size_t)nd * 8;
-    s.off_bar = o; o += 64;
+    s.off_bar = o; o += 128;
     s.total = o + 256;
     return s;
 }
@@ -196,7 +196,7 @@ __device__ __forceinline__ void win_pair(double qv, double Qj, double av, double
 // inside the level walk.
 constexpr int kWinScan = 8;   // one per column of the tile in the bound scans
 
-template <int MODE, bool HAS_NC, bool COUNT, int NW>
+template <int MODE, bool HAS_NC, bool COUNT, int NW, int NSTAGE>
 __global__ void __launch_bounds__((NW + kWinScan) * 32, 1)
 lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_u,
                   const __grid_constant__ CUtensorMap tm_n, const WinArgs p) {
@@ -206,22 +206,24 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     constexpr int NF = HAS_NC ? 3 : 2;
     constexpr int NB = HAS_NC ? 1 : 2;                                   // bound buffers (win_smem_layout)
     constexpr int P = kWinKeyPitch;
-    constexpr int TU = kWinTile, TN = 2 * kWinTile;                      // u, nc relative to q (doubles)
-    constexpr int SD = (HAS_NC ? 4 : 3) * kWinTile;                      // doubles between the two stages
+    constexpr int TILE = win_tile_rows(NSTAGE) * kWinCols;               // doubles of one (rows x 8) tile slot
+    constexpr int TU = TILE, TN = 2 * TILE;                              // u, nc relative to q (doubles)
+    constexpr int SD = NF * TILE;                                        // doubles between consecutive stages
     constexpr int KB = 2 * kWinCols * P;                                 // ints of one (PE | PP) buffer
     constexpr unsigned FULL = 0xffffffffu;
     const int nd = p.nd;
-    const WinSmem L = win_smem_layout(nd, NF);
-    double* tiles = reinterpret_cast<double*>(win_raw + L.off_tiles);   // [stage][q | u | aa8 | nc][rows][8]
+    const WinSmem L = win_smem_layout(nd, NF, NSTAGE);
+    double* tiles = reinterpret_cast<double*>(win_raw + L.off_tiles);   // [stage][q | u | nc][rows][8]
     int* keys = reinterpret_cast<int*>(win_raw + L.off_keys);           // [8][P], hemispheric row index
     int* PEPP = reinterpret_cast<int*>(win_raw + L.off_pe);             // [NB][PE | PP][8][P]
-    double* Qh = reinterpret_cast<double*>(win_raw + L.off_q);          // [2][nd] thresholds of a level
-    double* Ur = reinterpret_cast<double*>(win_raw + L.off_u);          // [2][nd] uref of a level
-    double* abcs = reinterpret_cast<double*>(win_raw + L.off_cs);       // [nd] a dphi cos(phi_j)
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(win_raw + L.off_bar);   // [2]
-    uint64_t* bar_ready = bar_full + 2;                                       // [2]
-    uint64_t* bar_done = bar_full + 4;                                        // [2]
-    uint32_t* tbase = reinterpret_cast<uint32_t*>(bar_full + 6);
+    double* Qh = reinterpret_cast<double*>(win_raw + L.off_q);          // [NSTAGE][nd] thresholds of a level
+    double* Ur = reinterpret_cast<double*>(win_raw + L.off_u);          // [NSTAGE][nd] uref of a level
+    double* abcs = reinterpret_cast<double*>(win_raw + L.off_cs);       // [nd] a dphi cos(phi_j): the LWA weight of a row
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(win_raw + L.off_bar);   // [NSTAGE]
+    uint64_t* bar_ready = bar_full + NSTAGE;                                  // [NSTAGE]
+    uint64_t* bar_done = bar_full + 2 * NSTAGE;                               // [NSTAGE]
+    uint32_t* tbase = reinterpret_cast<uint32_t*>(bar_full + 3 * NSTAGE);
+    unsigned* left = reinterpret_cast<unsigned*>(tbase + 2);                  // [NSTAGE] compute warps that left a level
 
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int c = lane & 7, r = lane >> 3;
@@ -234,23 +236,30 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     const int nlev = kend - kbeg;
     if (nlev <= 0) return;
     const double sgn = fr.sg;
-    // completion of level L by the compute warps: the (L >> 1)-th phase of done[L & 1]
-    auto wait_done = [&](int lev) { win_mbar_wait(&bar_done[lev & 1], (unsigned)((lev >> 1) & 1)); };
+    // completion of level L by the compute warps: the (L / NSTAGE)-th phase of done[L % NSTAGE]
+    auto wait_done = [&](int lev) { win_mbar_wait(&bar_done[lev % NSTAGE], (unsigned)((lev / NSTAGE) & 1)); };
+    const unsigned box_bytes = (unsigned)(p.boxrows * kWinCols * 8);
+    auto issue = [&](int li) {   // one thread: all boxes of level kbeg + li into stage li % NSTAGE
+        const int s = li % NSTAGE, k = kbeg + li;
+        win_mbar_expect(&bar_full[s], box_bytes * p.nbox * NF);
+        for (int bx = 0; bx < p.nbox; ++bx) {
+            const int row = fr.in_row0 + bx * p.boxrows;
+            double* dst = tiles + (size_t)s * SD + (size_t)bx * p.boxrows * kWinCols;
+            win_tma_load(dst, &tm_q, &bar_full[s], i0, row, k - 1, b);
+            win_tma_load(dst + TU, &tm_u, &bar_full[s], i0, row, k - 1, b);
+            if (HAS_NC) win_tma_load(dst + TN, &tm_n, &bar_full[s], i0, row, k - 1, b);
+        }
+    };
 
     // ---- set-up by everybody -------------------------------------------------------------------------------
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NSTAGE; ++s) {
             win_mbar_init(&bar_full[s], 1);
             win_mbar_init(&bar_ready[s], kWinScan);
             win_mbar_init(&bar_done[s], NW);
+            left[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int t = tid; t < nd * kWinCols; t += NT) {   // a dphi cos(phi) of every tile row
-        const int m = t >> 3;
-        const double v = p.ab * p.cosphi[fr.rev ? nd - m : m + 1];
-        tiles[(HAS_NC ? 3 : 2) * kWinTile + t] = v;
-        if (!HAS_NC) tiles[5 * kWinTile + t] = v;
     }
     for (int t = nd + tid; t < kWinSpan * 32; t += NT)   // rows beyond the column: neutral for the minima
 #pragma unroll
@@ -279,32 +288,18 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == NW * 32)   // the first levels; later ones are requested by the compute warp that frees a stage
+        for (int li = 0; li < NSTAGE && li < nlev; ++li) issue(li);
 
     if (w >= NW) {
         // =====================================================================================================
         // scan warps: tile -> keys -> bounds, thresholds, TMA issue
         // =====================================================================================================
         const int ws = w - NW, stid = tid - NW * 32;
-        const unsigned box_bytes = (unsigned)(p.boxrows * kWinCols * 8);
-        auto issue = [&](int li) {   // one thread: all boxes of level kbeg + li into stage li & 1
-            const int s = li & 1, k = kbeg + li;
-            win_mbar_expect(&bar_full[s], box_bytes * p.nbox * NF);
-            for (int bx = 0; bx < p.nbox; ++bx) {
-                const int row = fr.in_row0 + bx * p.boxrows;
-                double* dst = tiles + (size_t)s * SD + (size_t)bx * p.boxrows * kWinCols;
-                win_tma_load(dst, &tm_q, &bar_full[s], i0, row, k - 1, b);
-                win_tma_load(dst + TU, &tm_u, &bar_full[s], i0, row, k - 1, b);
-                if (HAS_NC) win_tma_load(dst + TN, &tm_n, &bar_full[s], i0, row, k - 1, b);
-            }
-        };
-        if (stid == 0) {
-            issue(0);
-            if (nlev > 1) issue(1);
-        }
         const double qsg = p.q_sg[h];
         constexpr int TPT = (kWinMaxRows + kWinScan * 32 - 1) / (kWinScan * 32);   // threshold rows per scan thread
         for (int li = 0; li < nlev; ++li) {
-            const int s = li & 1, k = kbeg + li;
+            const int s = li % NSTAGE, k = kbeg + li;
             double* const tq = tiles + (size_t)s * SD;
             int* const PE = PEPP + (li % NB) * KB;
             int* const PP = PE + kWinCols * P;
@@ -319,19 +314,9 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     if (p.uref) Uv[x] = p.uref[(size_t)b * p.u_batch + (size_t)(k - 1) * p.u_kstride + p.u_row0[h] + p.u_rstep[h] * j0];
                 }
             }
-            if (li >= 2) {   // the compute warps have left level li - 2: its stage and table buffer are free
-                wait_done(li - 2);
-                if (stid == 0) issue(li);
-            }
-            if (NB == 1 && li >= 1) wait_done(li - 1);   // a single bound buffer: its readers must be gone too
-#pragma unroll
-            for (int x = 0; x < TPT; ++x) {
-                const int j0 = stid + x * kWinScan * 32;
-                if (j0 < nd) { Qh[s * nd + j0] = __fma_rn(qsg, Qv[x], 0.0); Ur[s * nd + j0] = Uv[x]; }
-            }
-            win_mbar_wait(&bar_full[s], (unsigned)((li >> 1) & 1));
+            win_mbar_wait(&bar_full[s], (unsigned)((li / NSTAGE) & 1));
             // phase 1: hemispheric-frame PV (sign, -0 -> +0) and its keys; four groups of a warp in flight at a time
-            for (int g0 = ws; 4 * g0 < nd; g0 += 4 * kWinScan) {
+            for (int g0 = ws; 4 * g0 < nd && p.dbg != 2; g0 += 4 * kWinScan) {
                 double qv[4];
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
@@ -350,6 +335,13 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile is refilled by the async proxy later
             asm volatile("bar.sync 1, %0;" ::"n"(kWinScan * 32) : "memory");
+            // the bound buffer of this level was read by the compute warps NB levels ago (the table buffer NSTAGE ago)
+            if (li >= NB) wait_done(li - NB);
+#pragma unroll
+            for (int x = 0; x < TPT; ++x) {
+                const int j0 = stid + x * kWinScan * 32;
+                if (j0 < nd) { Qh[s * nd + j0] = __fma_rn(qsg, Qv[x], 0.0); Ur[s * nd + j0] = Uv[x]; }
+            }
             // phase 2: the two monotone bound arrays of column ws, from one read of its keys: a lane takes 13
             // consecutive rows, PE[x] = max key over rows < x (rows beyond nd do not reach entries <= nd),
             // PP[x] = min key over rows >= x (rows beyond nd hold +inf keys)
@@ -412,6 +404,7 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             if (valid && colok && j0 + 1 >= p.jstart && j0 + 1 <= p.jend) actm |= 1u << gi;
             if (valid && colok && !(fr.skip_first && j0 == 0)) storem |= 1u << gi;
         }
+        if (p.dbg == 1) actm = 0;
         asm volatile("" : "+r"(actm), "+r"(storem));                    // keep the bits; do not re-derive them per level
         const int ngroups = (nd - 4 * w + 4 * NW - 1) / (4 * NW);        // groups of this warp that exist (warp-uniform)
         // Everything the level walk needs is held as 32-bit shared addresses / 64-bit global pointers that the compiler
@@ -432,32 +425,32 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         constexpr int GK = 4 * NW * 4, GT = 4 * NW * 8;                  // key / table bytes between groups of a warp
 
         for (int li = 0; li < nlev; ++li) {
-            const int s = li & 1, k = kbeg + li;
+            const int s = li % NSTAGE, k = kbeg + li;
             uint32_t a_t = a_t0 + (uint32_t)(s * SD * 8);                 // this lane's element of group 0 in this stage
-            uint32_t a_q = a_tab + (uint32_t)(s * nd * 8);                // table buffers alternate like the tile stages
+            uint32_t a_q = a_tab + (uint32_t)(s * nd * 8);                // table buffers rotate like the tile stages
             uint32_t a_k = a_pe0 + (uint32_t)((li % NB) * KB * 4);        // ... and the bound buffers
             asm volatile("" : "+r"(a_t), "+r"(a_q), "+r"(a_k));
-            const uint32_t TAb = (uint32_t)((HAS_NC ? (s ? -kWinTile : 3 * kWinTile) : 2 * kWinTile) * 8);   // aa8 from q
             const double wd = (MODE == 1) ? p.vw[k - 1] * p.dc : 0.0;
-            win_mbar_wait(&bar_ready[s], (unsigned)((li >> 1) & 1));     // keys, bounds and thresholds are in place
-            win_mbar_wait(&bar_full[s], (unsigned)((li >> 1) & 1));      // (complete by now: observed for the TMA writes)
+            win_mbar_wait(&bar_ready[s], (unsigned)((li / NSTAGE) & 1)); // keys, bounds and thresholds are in place
+            win_mbar_wait(&bar_full[s], (unsigned)((li / NSTAGE) & 1));  // (complete by now: observed for the TMA writes)
             double* o = out_k;
 #pragma unroll
             for (int gi = 0; gi < GPW; ++gi) {
                 if (gi < ngroups) {   // warp-uniform
                     const bool act = (actm >> gi) & 1;
                     const uint32_t at = a_t + gi * gbytes, ak = a_k + gi * GK, aq = a_q + gi * GT;
+                    const uint32_t aw = a_tab + o_cs + gi * GT;          // the LWA weight a dphi cos(phi) of this row
                     const double Qj = lds64(aq);
                     const int kq = win_key(Qj);
                     const int kqc = max(kq, INT_MIN + 1);   // "may exceed Q_j":      key >= kqc  (never true at PE[0])
                     const int kqa = min(kq, INT_MAX - 1);   // "may not exceed Q_j":  key <= kqa  (never true at PP[nd])
                     double A1 = 0.0, A2 = 0.0, B = 0.0, N = 0.0;
                     {   // cyclonic side: rows j0-1, j0-2, ... while some row at or beyond may exceed Q_j
-                        uint32_t t = at, pk = ak;
+                        uint32_t t = at, pk = ak, pa = aw;
                         bool mine = act && (lds32(pk) >= kqc);
                         while (__any_sync(FULL, mine)) {
-                            if (mine) { t += stepb; pk -= 4; }     // finished lanes keep re-reading their last row
-                            const double qv = lds64(t), uv = lds64o<TU * 8>(t), av = lds64(t + TAb);
+                            if (mine) { t += stepb; pk -= 4; pa -= 8; }     // finished lanes keep re-reading their last row
+                            const double qv = lds64(t), uv = lds64o<TU * 8>(t), av = lds64(pa);
                             const double nv = HAS_NC ? lds64o<TN * 8>(t) : 0.0;
                             const int pe = lds32(pk);
                             win_pair<false, HAS_NC, COUNT>(qv, Qj, av, uv, nv, mine, A1, B, N, cnt_c);
@@ -465,15 +458,15 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                         }
                     }
                     {   // anticyclonic side: rows j0, j0+1, ... while some row at or beyond may not exceed Q_j
-                        uint32_t t = at, pk = ak;
+                        uint32_t t = at, pk = ak, pa = aw;
                         bool mine = act && (lds32o<KPP>(pk) <= kqa);
                         while (__any_sync(FULL, mine)) {
-                            const double qv = lds64(t), uv = lds64o<TU * 8>(t), av = lds64(t + TAb);
+                            const double qv = lds64(t), uv = lds64o<TU * 8>(t), av = lds64(pa);
                             const double nv = HAS_NC ? lds64o<TN * 8>(t) : 0.0;
                             const int pp = lds32o<KPP + 4>(pk);
                             win_pair<true, HAS_NC, COUNT>(qv, Qj, av, uv, nv, mine, A2, B, N, cnt_a);
                             mine = mine && (pp <= kqa);
-                            if (mine) { t -= stepb; pk += 4; }
+                            if (mine) { t -= stepb; pk += 4; pa += 8; }
                         }
                     }
                     {
@@ -481,7 +474,7 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                         // (lanes past the last row and inactive rows carry A1 = A2 = B = N = 0; they store nothing)
                         const double lw = A1 + A2;
                         const double x1 = lds64(aq + o_ur) * lw;
-                        const double u2 = __fma_rn(lds64(a_tab + o_cs + gi * GT), B, -x1);
+                        const double u2 = __fma_rn(lds64(aw), B, -x1);
                         const bool store = (storem >> gi) & 1;
                         if (MODE == 1) {
                             double a[4];
@@ -509,8 +502,19 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             }
             out_k += out_lev;
             if (MODE == 1) tmem_wait_st();
+            // this warp has left the level; the last one to do so refills the stage with level li + NSTAGE
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) win_mbar_arrive(&bar_done[s]);   // this warp has left the level
+            if (lane == 0) {
+                win_mbar_arrive(&bar_done[s]);
+                __threadfence_block();
+                if (atomicAdd(&left[s], 1u) == (unsigned)(NW - 1)) {
+                    left[s] = 0;
+                    __threadfence_block();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (li + NSTAGE < nlev) issue(li + NSTAGE);
+                }
+            }
         }
 
         if (MODE == 1) {
@@ -590,20 +594,23 @@ static bool win_supported(int imax, int nd, const void* pv, const void* uu, cons
 
 template <int MODE, int NW>
 static int win_launch_mode(const CUtensorMap& tq, const CUtensorMap& tu, const CUtensorMap& tn, const WinArgs& a, bool has_nc,
-                           dim3 grid, size_t smem, cudaStream_t st) {
+                           bool three_stages, dim3 grid, size_t smem, cudaStream_t st) {
     auto go = [&](auto kern) -> int {
         FALWA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, (NW + kWinScan) * 32, smem, st>>>(tq, tu, tn, a);
         return 0;
     };
     const bool count = a.mask_count != nullptr;
-    if (has_nc) return count ? go(lwa_window_kernel<MODE, true, true, NW>) : go(lwa_window_kernel<MODE, true, false, NW>);
-    return count ? go(lwa_window_kernel<MODE, false, true, NW>) : go(lwa_window_kernel<MODE, false, false, NW>);
+    if (has_nc) return count ? go(lwa_window_kernel<MODE, true, true, NW, 2>) : go(lwa_window_kernel<MODE, true, false, NW, 2>);
+    if (count) return go(lwa_window_kernel<MODE, false, true, NW, 2>);
+    if (MODE == 1 && three_stages) return go(lwa_window_kernel<1, false, false, NW, 3>);
+    return go(lwa_window_kernel<MODE, false, false, NW, 2>);
 }
 
 // pv / uu / nc: [batch][kmax][in_rows][imax]; a.k_first / k_count / frames / thresholds / outputs filled by the caller
 static int lwa_window_launch(WinArgs a, int mode, const double* pv, const double* uu, const double* nc, int in_rows,
                              int batch, int nprob, cudaStream_t st) {
+    a.dbg = tune_int("FALWA_WIN_DEBUG", 0);
     const int nbox = (a.nd + 255) / 256;
     int boxrows = (a.nd + nbox - 1) / nbox;
     boxrows += boxrows & 1;
@@ -617,13 +624,15 @@ static int lwa_window_launch(WinArgs a, int mode, const double* pv, const double
     if (mode == 1) a.k_per_cta = a.k_count;
     else a.k_per_cta = std::max(1, std::min(a.k_count, ceil_div((long long)a.k_count * tiles * nprob, 148 * 8)));
     const int chunks = ceil_div(a.k_count, a.k_per_cta);
-    const size_t smem = win_smem_layout(a.nd, nc ? 3 : 2).total;
+    // three tile stages (TMA two levels ahead) where the column fits the smaller slots: the hot path
+    const bool three = mode == 1 && !nc && !a.mask_count && nbox * boxrows <= win_tile_rows(3) && tune_int("FALWA_WIN_STAGES", 3) == 3;
+    const size_t smem = win_smem_layout(a.nd, nc ? 3 : 2, three ? 3 : 2).total;
     dim3 grid(tiles, chunks, nprob);
     FALWA_KERNEL("lwa_window_kernel", st);
     static const int nw = tune_int("FALWA_WIN_WARPS", 16);
-    if (mode == 1 && nw == 24) rc = win_launch_mode<1, 24>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
-    else rc = mode == 1 ? win_launch_mode<1, 16>(tq, tu, tn, a, nc != nullptr, grid, smem, st)
-                        : win_launch_mode<0, 16>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
+    if (mode == 1 && nw == 24) rc = win_launch_mode<1, 24>(tq, tu, tn, a, nc != nullptr, three, grid, smem, st);
+    else rc = mode == 1 ? win_launch_mode<1, 16>(tq, tu, tn, a, nc != nullptr, three, grid, smem, st)
+                        : win_launch_mode<0, 16>(tq, tu, tn, a, nc != nullptr, false, grid, smem, st);
     if (rc) return rc;
     FALWA_LAUNCH_CHECK();
     return 0;
