@@ -55,6 +55,7 @@ struct WinArgs {
     double *lwa, *out2d; const double* vw; double dc; size_t lwa_batch, lwa_plane, o2_batch, o2_plane;
     int slot_a1, slot_a2, slot_lwa, slot_ua1, slot_ua2, slot_ncf;
     unsigned long long* mask_count;         // optional: [0] anticyclonic pairs, [1] cyclonic pairs
+    const double *pv, *uu, *nc; int in_rows; // the tiled fields [batch][kmax][in_rows][imax] (cp.async loader)
     int dbg;                                // timing experiments only (FALWA_WIN_DEBUG): 1 = no window loops, 2 = no scans
 };
 
@@ -69,11 +70,15 @@ __device__ __forceinline__ void win_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(win_smem(bar)) : "memory");
 }
 __device__ __forceinline__ void win_mbar_wait(uint64_t* bar, unsigned parity) {
+    // try_wait with a suspend-time hint parks the warp in hardware; a failed attempt backs off before the next one, so
+    // that waiting warps do not take issue slots from the warps they are waiting for
     unsigned ok = 0;
     const uint32_t a = win_smem(bar);
-    while (!ok) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity), "r"(2000u) : "memory");
+        if (ok) break;
+        __nanosleep(200);
     }
 }
 __device__ __forceinline__ void win_tma_load(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -163,6 +168,17 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const double (&a)[4]) {
                  "r"(__double2hiint(a[1])), "r"(__double2loint(a[2])), "r"(__double2hiint(a[2])),
                  "r"(__double2loint(a[3])), "r"(__double2hiint(a[3])) : "memory");
 }
+// issue now, use later: the values may only be read after tmem_ld8_wait (which ties the registers to the wait)
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8_wait(uint32_t (&v)[8], double (&a)[4]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]) :: "memory");
+#pragma unroll
+    for (int x = 0; x < 4; ++x) a[x] = __hiloint2double((int)v[2 * x + 1], (int)v[2 * x]);
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // One window step of a threshold row: diff = q - Q; in the set (and still inside this lane's window) the pair adds
@@ -196,7 +212,7 @@ __device__ __forceinline__ void win_pair(double qv, double Qj, double av, double
 // inside the level walk.
 constexpr int kWinScan = 8;   // one per column of the tile in the bound scans
 
-template <int MODE, bool HAS_NC, bool COUNT, int NW, int NSTAGE>
+template <int MODE, bool HAS_NC, bool COUNT, int NW, int NSTAGE, bool TMA>
 __global__ void __launch_bounds__((NW + kWinScan) * 32, 1)
 lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_u,
                   const __grid_constant__ CUtensorMap tm_n, const WinArgs p) {
@@ -288,7 +304,7 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (tid == NW * 32)   // the first levels; later ones are requested by the compute warp that frees a stage
+    if (TMA && tid == NW * 32)   // the first levels; later ones are requested by the compute warp that frees a stage
         for (int li = 0; li < NSTAGE && li < nlev; ++li) issue(li);
 
     if (w >= NW) {
@@ -298,7 +314,8 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         const int ws = w - NW, stid = tid - NW * 32;
         const double qsg = p.q_sg[h];
         constexpr int TPT = (kWinMaxRows + kWinScan * 32 - 1) / (kWinScan * 32);   // threshold rows per scan thread
-        for (int li = 0; li < nlev; ++li) {
+        // everything a level needs before the compute warps may enter it
+        auto prepare = [&](int li) {
             const int s = li % NSTAGE, k = kbeg + li;
             double* const tq = tiles + (size_t)s * SD;
             int* const PE = PEPP + (li % NB) * KB;
@@ -314,7 +331,11 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     if (p.uref) Uv[x] = p.uref[(size_t)b * p.u_batch + (size_t)(k - 1) * p.u_kstride + p.u_row0[h] + p.u_rstep[h] * j0];
                 }
             }
-            win_mbar_wait(&bar_full[s], (unsigned)((li / NSTAGE) & 1));
+            if (TMA) win_mbar_wait(&bar_full[s], (unsigned)((li / NSTAGE) & 1));
+            else {   // this thread's copies of the level have landed; with the barrier, everybody's
+                asm volatile("cp.async.wait_group %0;" ::"n"(NSTAGE - 2) : "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kWinScan * 32) : "memory");
+            }
             // phase 1: hemispheric-frame PV (sign, -0 -> +0) and its keys; four groups of a warp in flight at a time
             for (int g0 = ws; 4 * g0 < nd && p.dbg != 2; g0 += 4 * kWinScan) {
                 double qv[4];
@@ -336,7 +357,7 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile is refilled by the async proxy later
             asm volatile("bar.sync 1, %0;" ::"n"(kWinScan * 32) : "memory");
             // the bound buffer of this level was read by the compute warps NB levels ago (the table buffer NSTAGE ago)
-            if (li >= NB) wait_done(li - NB);
+            if (TMA ? li >= NB : (NB == 1 && li >= 1)) wait_done(li - NB);
 #pragma unroll
             for (int x = 0; x < TPT; ++x) {
                 const int j0 = stid + x * kWinScan * 32;
@@ -374,6 +395,41 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kWinScan * 32) : "memory");   // keys are rewritten next level
             if (lane == 0) win_mbar_arrive(&bar_ready[s]);
+        };
+        if (TMA) {
+            for (int li = 0; li < nlev; ++li) prepare(li);
+        } else {
+            // The scan warps fetch the tiles themselves: 16-byte cp.async (LDGSTS), four lanes per 64-byte row segment,
+            // NSTAGE - 1 levels ahead of the compute warps.  (A TMA box of this shape is one 64-byte request per row and
+            // the engine serves ~1 row per 7 clocks: 2.6 us per level and SM, more than the level's arithmetic.)
+            const int nchunk = nd * 4;                               // 16-byte pieces of one field of the tile
+            auto load = [&](int li) {
+                const int s = li % NSTAGE, k = kbeg + li;
+                const size_t lev = ((size_t)b * p.kmax + (k - 1)) * (size_t)p.in_rows + fr.in_row0;
+                const uint32_t dst0 = win_smem(tiles + (size_t)s * SD);
+                for (int q = stid; q < nchunk; q += kWinScan * 32) {
+                    const int row = q >> 2, col = i0 + (q & 3) * 2;
+                    const size_t src = (lev + row) * (size_t)p.imax + col;
+                    const unsigned nbytes = col < p.imax ? 16u : 0u;     // past the last longitude: zeros
+                    const uint32_t dst = dst0 + (uint32_t)q * 16u;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(p.pv + (nbytes ? src : 0)), "r"(nbytes) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + TU * 8), "l"(p.uu + (nbytes ? src : 0)), "r"(nbytes) : "memory");
+                    if (HAS_NC)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + TN * 8), "l"(p.nc + (nbytes ? src : 0)), "r"(nbytes) : "memory");
+                }
+            };
+            constexpr int LA = NSTAGE - 1;                           // levels the loads run ahead
+            for (int l = 0; l < LA; ++l) {
+                if (l < nlev) load(l);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+            prepare(0);
+            for (int t = 0; t < nlev; ++t) {
+                if (t >= 1) wait_done(t - 1);        // the stage of level t + LA and the bound buffer of level t + 1 are free
+                if (t + LA < nlev) load(t + LA);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (t + 1 < nlev) prepare(t + 1);
+            }
         }
     } else {
         // =====================================================================================================
@@ -432,22 +488,34 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             asm volatile("" : "+r"(a_t), "+r"(a_q), "+r"(a_k));
             const double wd = (MODE == 1) ? p.vw[k - 1] * p.dc : 0.0;
             win_mbar_wait(&bar_ready[s], (unsigned)((li / NSTAGE) & 1)); // keys, bounds and thresholds are in place
-            win_mbar_wait(&bar_full[s], (unsigned)((li / NSTAGE) & 1));  // (complete by now: observed for the TMA writes)
+            if (TMA) win_mbar_wait(&bar_full[s], (unsigned)((li / NSTAGE) & 1));  // (complete by now: observed for the TMA writes)
             double* o = out_k;
+            // the operands a group starts with (threshold, the two first bound keys, uref, LWA weight of the row) are
+            // fetched one group ahead, the group's running sums are requested from tensor memory before its windows
+            // are walked: the latencies overlap with the arithmetic instead of heading every group
+            double Qn = lds64(a_q), urn = lds64(a_q + o_ur), wn = lds64(a_tab + o_cs);
+            int pen = lds32(a_k), ppn = lds32o<KPP>(a_k);
 #pragma unroll
             for (int gi = 0; gi < GPW; ++gi) {
                 if (gi < ngroups) {   // warp-uniform
                     const bool act = (actm >> gi) & 1;
                     const uint32_t at = a_t + gi * gbytes, ak = a_k + gi * GK, aq = a_q + gi * GT;
                     const uint32_t aw = a_tab + o_cs + gi * GT;          // the LWA weight a dphi cos(phi) of this row
-                    const double Qj = lds64(aq);
+                    const double Qj = Qn, urv = urn, wv = wn;
+                    const int pe0 = pen, pp0 = ppn;
+                    uint32_t tv[8];
+                    if (MODE == 1) tmem_ld8_issue(tacc + gi * TCOL, tv);
+                    if (gi + 1 < GPW && gi + 1 < ngroups) {
+                        Qn = lds64(aq + GT); urn = lds64(aq + GT + o_ur); wn = lds64(aw + GT);
+                        pen = lds32(ak + GK); ppn = lds32o<KPP>(ak + GK);
+                    }
                     const int kq = win_key(Qj);
                     const int kqc = max(kq, INT_MIN + 1);   // "may exceed Q_j":      key >= kqc  (never true at PE[0])
                     const int kqa = min(kq, INT_MAX - 1);   // "may not exceed Q_j":  key <= kqa  (never true at PP[nd])
                     double A1 = 0.0, A2 = 0.0, B = 0.0, N = 0.0;
                     {   // cyclonic side: rows j0-1, j0-2, ... while some row at or beyond may exceed Q_j
                         uint32_t t = at, pk = ak, pa = aw;
-                        bool mine = act && (lds32(pk) >= kqc);
+                        bool mine = act && (pe0 >= kqc);
                         while (__any_sync(FULL, mine)) {
                             if (mine) { t += stepb; pk -= 4; pa -= 8; }     // finished lanes keep re-reading their last row
                             const double qv = lds64(t), uv = lds64o<TU * 8>(t), av = lds64(pa);
@@ -459,7 +527,7 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                     }
                     {   // anticyclonic side: rows j0, j0+1, ... while some row at or beyond may not exceed Q_j
                         uint32_t t = at, pk = ak, pa = aw;
-                        bool mine = act && (lds32o<KPP>(pk) <= kqa);
+                        bool mine = act && (pp0 <= kqa);
                         while (__any_sync(FULL, mine)) {
                             const double qv = lds64(t), uv = lds64o<TU * 8>(t), av = lds64(pa);
                             const double nv = HAS_NC ? lds64o<TN * 8>(t) : 0.0;
@@ -473,12 +541,12 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                         // a1 = A1, a2 = A2;  ua2 = a dphi cos(phi_j) B - uref_j (a1 + a2)   (compute_flux_dirinv.f90:96-113)
                         // (lanes past the last row and inactive rows carry A1 = A2 = B = N = 0; they store nothing)
                         const double lw = A1 + A2;
-                        const double x1 = lds64(aq + o_ur) * lw;
-                        const double u2 = __fma_rn(lds64(aw), B, -x1);
+                        const double x1 = urv * lw;
+                        const double u2 = __fma_rn(wv, B, -x1);
                         const bool store = (storem >> gi) & 1;
                         if (MODE == 1) {
                             double a[4];
-                            tmem_ld8(tacc + gi * TCOL, a);
+                            tmem_ld8_wait(tv, a);
                             a[0] = __fma_rn(A1, wd, a[0]);
                             a[1] = __fma_rn(A2, wd, a[1]);
                             a[2] = __fma_rn(x1, wd, a[2]);
@@ -502,13 +570,13 @@ lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             }
             out_k += out_lev;
             if (MODE == 1) tmem_wait_st();
-            // this warp has left the level; the last one to do so refills the stage with level li + NSTAGE
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            // this warp has left the level (TMA variant: the last one to do so refills the stage with level li + NSTAGE)
+            if (TMA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
                 win_mbar_arrive(&bar_done[s]);
                 __threadfence_block();
-                if (atomicAdd(&left[s], 1u) == (unsigned)(NW - 1)) {
+                if (TMA && atomicAdd(&left[s], 1u) == (unsigned)(NW - 1)) {
                     left[s] = 0;
                     __threadfence_block();
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -601,16 +669,20 @@ static int win_launch_mode(const CUtensorMap& tq, const CUtensorMap& tu, const C
         return 0;
     };
     const bool count = a.mask_count != nullptr;
-    if (has_nc) return count ? go(lwa_window_kernel<MODE, true, true, NW, 2>) : go(lwa_window_kernel<MODE, true, false, NW, 2>);
-    if (count) return go(lwa_window_kernel<MODE, false, true, NW, 2>);
-    if (MODE == 1 && three_stages) return go(lwa_window_kernel<1, false, false, NW, 3>);
-    return go(lwa_window_kernel<MODE, false, false, NW, 2>);
+    if (has_nc) return count ? go(lwa_window_kernel<MODE, true, true, NW, 2, false>) : go(lwa_window_kernel<MODE, true, false, NW, 2, false>);
+    if (count) return go(lwa_window_kernel<MODE, false, true, NW, 2, false>);
+    if (MODE == 1 && three_stages) {
+        static const int tma = tune_int("FALWA_WIN_TMA", 0);   // the TMA-fed variant of the hot instantiation
+        return tma ? go(lwa_window_kernel<1, false, false, NW, 3, true>) : go(lwa_window_kernel<1, false, false, NW, 3, false>);
+    }
+    return go(lwa_window_kernel<MODE, false, false, NW, 2, false>);
 }
 
 // pv / uu / nc: [batch][kmax][in_rows][imax]; a.k_first / k_count / frames / thresholds / outputs filled by the caller
 static int lwa_window_launch(WinArgs a, int mode, const double* pv, const double* uu, const double* nc, int in_rows,
                              int batch, int nprob, cudaStream_t st) {
     a.dbg = tune_int("FALWA_WIN_DEBUG", 0);
+    a.pv = pv; a.uu = uu; a.nc = nc; a.in_rows = in_rows;
     const int nbox = (a.nd + 255) / 256;
     int boxrows = (a.nd + nbox - 1) / nbox;
     boxrows += boxrows & 1;
