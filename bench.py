@@ -322,6 +322,15 @@ def run_b200(args, nlon, nlat, rank, world, local_rank):
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- end to end: pinned host inputs -> results in pinned host memory ---------------------
+    if args.kernels_only:   # tuning runs: device-resident rate and the per-kernel times only
+        _lib.profile_enable(True)
+        step()
+        prof = _lib.profile_read()
+        _lib.profile_enable(False)
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms / args.steps,
+                              "kernels": {k: m for k, (n, m) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}}))
+        return
     hs = engine.HostStream(plan, chunk=args.chunk, want_lwa3d=True, method=args.method)
     out = hs.alloc_outputs(B)
     hs.run(hu, hv, ht, out=out)   # warm-up (allocator, pinned output pages)
@@ -618,6 +627,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--method", type=int, default=0, help="LWA algorithm: 0 automatic (windowed sums), 1 double loop, 2 interval scan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernels-only", action="store_true", help="tuning: skip the end-to-end and CPU parts")
     ap.add_argument("--cpu-extra", action="store_true", help="cpu_baseline also in fp32 (as shipped) and on one core")
     ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5],
                     help="BASELINE.json config: 3 = the headline (default), 4 = one year of 1.5-degree snapshots through "
