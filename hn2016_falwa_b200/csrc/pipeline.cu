@@ -87,8 +87,10 @@ __device__ __forceinline__ void hist_flush(unsigned long long* sh, int nb, int c
     }
 }
 
-template <bool NEED_QN, bool WITH_V>
-__global__ void __launch_bounds__(256, 2)
+// WITH_P / WITH_V: which of the two histograms (pv, absolute vorticity) this launch accumulates.  One field per launch
+// halves the registers of the software-pipelined loads (one more CTA per SM) and the two launches overlap their tails.
+template <bool NEED_QN, bool WITH_V, bool WITH_P = true>
+__global__ void __launch_bounds__(256, (WITH_V && WITH_P) ? 2 : 3)
 area_hist3_kernel(int nlon, int nlat, int kmax, int nb, const double* __restrict__ pv,
                   const double* __restrict__ avort, const unsigned long long* __restrict__ ext,
                   const double* __restrict__ da, int rows_per_block, unsigned long long* __restrict__ hist, int run,
@@ -134,12 +136,15 @@ area_hist3_kernel(int nlon, int nlat, int kmax, int nb, const double* __restrict
         int cn = -1, cv = -1, an = 0, av = 0;
         double qn = 0., qv = 0.;
         auto point = [&](double q, double w) {
-            bool edge;
-            int ind = area_bin(pmax, q, dqp, rdqp, nb, &edge);
-            if (ind != cn) { hist_flush<NEED_QN>(hN, nb, cn, an, dai, qn, scp); cn = ind; an = 0; qn = 0.; }
-            ++an;
-            if (NEED_QN) qn += daj * q;
-            if (__builtin_expect(edge, 0)) {  // rare: classify the southern bin with the reference's own division
+            bool edge = false;
+            int ind = 0;
+            if (WITH_P) {
+                ind = area_bin(pmax, q, dqp, rdqp, nb, &edge);
+                if (ind != cn) { hist_flush<NEED_QN>(hN, nb, cn, an, dai, qn, scp); cn = ind; an = 0; qn = 0.; }
+                ++an;
+                if (NEED_QN) qn += daj * q;
+            }
+            if (WITH_P && __builtin_expect(edge, 0)) {  // rare: classify the southern bin with the reference's own division
                 const double qq = -q;
                 const int is = max(1, min(nb, 1 + (int)area_bin_exact(smax - qq, dqs)));
                 const long long tq = __double2ll_rn((daj * q) * scp);
@@ -163,7 +168,8 @@ area_hist3_kernel(int nlon, int nlat, int kmax, int nb, const double* __restrict
             auto fetch8 = [&](int at, double2* A, double2* C) {
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
-                    A[v] = __ldg(reinterpret_cast<const double2*>(pv + row + at) + v);
+                    if (WITH_P) A[v] = __ldg(reinterpret_cast<const double2*>(pv + row + at) + v);
+                    else A[v] = make_double2(0., 0.);
                     if (WITH_V) C[v] = __ldg(reinterpret_cast<const double2*>(avort + row + at) + v);
                     else C[v] = make_double2(0., 0.);
                 }
@@ -180,8 +186,8 @@ area_hist3_kernel(int nlon, int nlat, int kmax, int nb, const double* __restrict
                 }
             }
         }
-        for (; i < i1; ++i) point(pv[row + i], WITH_V ? avort[row + i] : 0.0);
-        hist_flush<NEED_QN>(hN, nb, cn, an, dai, qn, scp);
+        for (; i < i1; ++i) point(WITH_P ? pv[row + i] : 0.0, WITH_V ? avort[row + i] : 0.0);
+        if (WITH_P) hist_flush<NEED_QN>(hN, nb, cn, an, dai, qn, scp);
         if (WITH_V) hist_flush<true>(hV, nb, cv, av, dai, qv, scv);
     }
     __syncthreads();
@@ -1094,6 +1100,11 @@ extern "C" int falwa_b200_reference_states(const falwa_plan* P, int batch, const
         if (P->kind == 0) {  // NH18: pv histogram with circulation sums (SOR boundary condition), no vorticity histogram
             FALWA_CUDA_TRY(cudaFuncSetAttribute(area_hist3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             area_hist3_kernel<true, false><<<hgrid, 256, smem, st>>>(nlon, nlat, kmax, nb, qgpv, avort, extd, d + P->o_da, rows, histi, hrun, area_scale, cbound);
+        } else if (tune_int("FALWA_HIST_SPLIT", 1)) {   // NHN22, one field per launch
+            FALWA_CUDA_TRY(cudaFuncSetAttribute(area_hist3_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FALWA_CUDA_TRY(cudaFuncSetAttribute(area_hist3_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            area_hist3_kernel<false, false, true><<<hgrid, 256, smem, st>>>(nlon, nlat, kmax, nb, qgpv, avort, extd, d + P->o_da, rows, histi, hrun, area_scale, cbound);
+            area_hist3_kernel<false, true, false><<<hgrid, 256, smem, st>>>(nlon, nlat, kmax, nb, qgpv, avort, extd, d + P->o_da, rows, histi, hrun, area_scale, cbound);
         } else {             // NHN22: areas of the pv histogram, areas + circulation of the vorticity histogram
             FALWA_CUDA_TRY(cudaFuncSetAttribute(area_hist3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             area_hist3_kernel<false, true><<<hgrid, 256, smem, st>>>(nlon, nlat, kmax, nb, qgpv, avort, extd, d + P->o_da, rows, histi, hrun, area_scale, cbound);
