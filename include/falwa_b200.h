@@ -259,6 +259,10 @@ int falwa_b200_profile_read(char* buf, int buflen);
 /* Host-only test hook: eigen-decomposition of a symmetric tridiagonal matrix (used by the NHN22 solve). */
 int falwa_b200_debug_symtridiag_eig(int m, double* d, const double* e, double* z);
 
+/* FP64 pipe micro-benchmark (tools/fp64_peak.py): `blocks` CTAs x 256 threads x 8 * iters dependent-chain DFMAs;
+ * elapsed milliseconds of one launch in *ms_out.  sink_dev: one device double (never written in practice). */
+int falwa_b200_debug_dfma_rate(int blocks, int iters, double* sink_dev, float* ms_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
