@@ -106,8 +106,11 @@ int falwa_b200_upward_sweep(int jmax, int kmax, int nd, int jb, int jd, const do
 /* replaces falwa.compute_flux_dirinv_nshem  (compute_flux_dirinv.f90:1-182; oopinterface.py:430, 1094)
  * 3-D outputs (imax,nd,kmax); ep4 (imax,nd).  mask_count (optional device int64[2], may be NULL)
  * receives the number of (i,j,jj,k) pairs in the anticyclonic / cyclonic sums.
- * method: 0 = automatic (interval/prefix-sum LWA where qref is monotone, brute force otherwise),
- *         1 = force the O(nd^2) brute-force double loop of the reference. */
+ * method: 0 = automatic: exact windowed sums (lwa_window.cu; fields 16-byte aligned, nd <= 384, even imax), else the
+ *             interval scan (nd <= 416), else the double loop;
+ *         1 = the O(nd^2) double loop of the reference (same summation order as the reference);
+ *         2 = interval scan (flux_scan.cu);  3 = windowed sums (falls back like 0 where unsupported).
+ * All methods form exactly the reference's sets (equal pair counts); sums agree within rounding. */
 int falwa_b200_compute_flux_dirinv_nshem(const double* pv, const double* uu, const double* vv,
                                          const double* pt, const double* ncforce, const double* tn0_host,
                                          const double* qref, const double* uref, const double* tref, int imax,
@@ -182,7 +185,8 @@ int falwa_b200_reference_states(const falwa_plan* plan, int batch, const double*
 /* compute_lwa_and_barotropic_fluxes (oopinterface.py:716-982), both hemispheres.
  *   lwa   [batch][kmax][nlat][nlon]
  *   out2d [batch][FALWA_OUT2D_COUNT][nlat][nlon], slots below.
- * ncforce may be NULL (zeros).  method: 0 = automatic, 1 = O(nd^2) brute-force LWA. */
+ * ncforce may be NULL (zeros).  method as for falwa_b200_compute_flux_dirinv_nshem (0 = automatic: the window kernel
+ * also carries the vertical sums of astar1, astar2, ua1, ua2 and writes the 3-D LWA in the same pass). */
 enum {
     FALWA_OUT2D_ASTAR1_BARO = 0, FALWA_OUT2D_ASTAR2_BARO = 1, FALWA_OUT2D_LWA_BARO = 2,
     FALWA_OUT2D_ADV_FLUX_F1 = 3, FALWA_OUT2D_ADV_FLUX_F2 = 4, FALWA_OUT2D_ADV_FLUX_F3 = 5,
