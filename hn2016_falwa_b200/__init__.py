@@ -9,4 +9,4 @@ Modules (same names and interfaces as in ``falwa`` where one exists):
   netcdf_io         undecoded NetCDF-3 input, result files
   engine            batched device-resident pipeline (Plan, QGBatch, HostStream, run_stream, ingest_field)
 """
-__version__ = "0.3.0"
+__version__ = "0.4.0"

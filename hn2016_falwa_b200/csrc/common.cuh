@@ -41,6 +41,7 @@ struct ProfileRecord {
 struct ProfileState {
     bool enabled = false;
     std::atomic<long long> launches{0};   // kernels launched by this library (any host thread)
+    std::mutex mu;                        // guards recs (the C ABI may be driven from one host thread per stream)
     std::vector<ProfileRecord> recs;
 };
 inline ProfileState& profile_state() {
@@ -60,6 +61,7 @@ struct KernelScope {
             cudaEventCreate(&r.e1);
             cudaEventRecord(r.e0, st);
             e1 = r.e1;
+            std::lock_guard<std::mutex> lock(P.mu);
             P.recs.push_back(r);
         }
     }

@@ -2,7 +2,7 @@
 #include <string>
 #include <map>
 #include <cstring>
-extern "C" const char* falwa_b200_version(void) { return "falwa_b200 0.3.0 sm_100a fp64"; }
+extern "C" const char* falwa_b200_version(void) { return "falwa_b200 0.4.0 sm_100a fp64"; }
 
 // ---- launch accounting / per-kernel timing (diagnostics for bench.py; not on the data path) ----
 extern "C" long long falwa_b200_launch_count(void) { return falwa::profile_state().launches; }
