@@ -81,3 +81,30 @@ def test_dataset_layerwise_and_lwa_only():
     q18 = xi.QGDataset(ds, qgfield=QGFieldNH18, qgfield_kwargs=dict(maxit=5, raise_error_for_nonconvergence=False))
     lo = q18.compute_lwa_only()
     assert lo["lwa"].shape == (2, 1, 49, 49, 96) and np.isfinite(lo["lwa_baro"].data).all()
+
+
+def test_config4_shape_at_the_real_grid_against_the_oracle():
+    """BASELINE.json config 4 at its real grid (240 x 121, 37 levels -> kmax 49): a time series holding the reference
+    repo's ERA-Interim snapshot among seeded synthetic ones goes through QGDataset in chunks; every snapshot is compared
+    with the CPU oracle (all 2-D budget terms, the reference states and the 3-D LWA)."""
+    from hn2016_falwa_b200 import xarrayinterface as xi
+    from hn2016_falwa_b200.oopinterface import QGFieldNHN22
+    from oracle import pipeline, testdata
+    era = testdata.load_era_snapshot()
+    snaps = [synthetic_snapshot(nlon=240, nlat=121, seed=31, t_index=k) for k in range(5)]
+    snaps.insert(2, era)
+    xlon, ylat, plev = era[:3]
+    u, v, t = (np.stack([s[i] for s in snaps]) for i in (3, 4, 5))
+    coords = dict(time=np.arange(len(snaps)), level=plev, latitude=ylat, longitude=xlon)
+    dims = ("time", "level", "latitude", "longitude")
+    mk = lambda a, n: xi.SimpleDataArray(a, dims, coords, name=n)
+    q = xi.QGDataset(xi.SimpleDataset(dict(u=mk(u, "u"), v=mk(v, "v"), t=mk(t, "t"))), qgfield=QGFieldNHN22, chunk=4)
+    q.compute_lwa_and_barotropic_fluxes(return_dataset=False)
+    names = ("qref", "uref", "ptref", "lwa_baro", "u_baro", "adv_flux_f1", "adv_flux_f2", "adv_flux_f3",
+             "convergence_zonal_advective_flux", "divergence_eddy_momentum_flux", "meridional_heat_flux", "lwa")
+    for k, s in enumerate(snaps):
+        want = pipeline.run_qgfield("nhn22", *s)
+        for name in names:
+            rtol, atol = (1e-9, 0.0) if name == "ptref" else (1e-8, 1e-9 * float(np.abs(want[name]).max()))
+            np.testing.assert_allclose(np.asarray(getattr(q, name).data)[k], want[name], rtol=rtol, atol=atol,
+                                       err_msg=f"snapshot {k}: {name}")
