@@ -452,7 +452,7 @@ theta_hemi_kernel(int nlat, int nlev, int jd, const double* __restrict__ rowmean
 // registers of 2 CTAs x 256 threads per SM without spills.
 // ---------------------------------------------------------------------------------------------
 constexpr int kStage1Rows = 8;
-template <int MODE>
+template <int MODE, int PFD>
 __global__ void __launch_bounds__(32 * kStage1Rows, 2)
 interp_qgpv_kernel(int nlon, int nlat, int nlev, int kmax, int jd, const double* __restrict__ uin,
                    const double* __restrict__ vin, const double* __restrict__ tin, const int* __restrict__ lo,
@@ -499,6 +499,15 @@ interp_qgpv_kernel(int nlon, int nlat, int nlev, int kmax, int jd, const double*
             if (l == cur + 1) n0 = L1; else if (l == lp) n0 = P; else if (l == lq) n0 = Q; else n0 = load(l);
             if (l + 1 == lp) n1 = P; else if (l + 1 == lq) n1 = Q; else n1 = load(l + 1);
             L0 = n0; L1 = n1; cur = l;
+        }
+        if (PFD > 0) {   // pull this column's own values of a level further ahead into L2 (no registers involved): the
+            const int lf = cur + PFD;   // register prefetch below then waits for an L2 hit instead of DRAM
+            if (lf < nlev) {
+                const size_t off = (size_t)lf * plane + col;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(uin + off));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(vin + off));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(tin + off));
+            }
         }
         {   // keep the two slots filled with what the schedule asks for; the loads land while levels are evaluated
             const int w1 = pf1[k], w2 = pf2[k];
@@ -547,12 +556,18 @@ int interp_qgpv_launch(int mode, int nlon, int nlat, int nlev, int kmax, int jd,
     stt.part = nullptr; stt.ext = nullptr; stt.nwx = 0;
     {
         FALWA_KERNEL("interp_qgpv_kernel", st);
-        if (mode == 0)
-            interp_qgpv_kernel<0><<<grid, block, 0, st>>>(nlon, nlat, nlev, kmax, jd, uin, vin, tin, lo, whi, wlo, fac, tb,
-                                                         d_prof6, uo, vo, to, avort, pv, plane * nlev, plane * kmax);
-        else
-            interp_qgpv_kernel<1><<<grid, block, 0, st>>>(nlon, nlat, nlev, kmax, jd, uin, vin, tin, lo, whi, wlo, fac, tb,
-                                                         d_prof6, uo, vo, to, avort, pv, plane * nlev, plane * kmax);
+        static const int pfd = tune_int("FALWA_STAGE1_PFD", 6);
+        auto go = [&](auto kern) {
+            kern<<<grid, block, 0, st>>>(nlon, nlat, nlev, kmax, jd, uin, vin, tin, lo, whi, wlo, fac, tb, d_prof6, uo, vo, to,
+                                         avort, pv, plane * nlev, plane * kmax);
+        };
+        if (mode == 0) {
+            if (pfd == 0) go(interp_qgpv_kernel<0, 0>); else if (pfd == 8) go(interp_qgpv_kernel<0, 8>);
+            else if (pfd == 10) go(interp_qgpv_kernel<0, 10>); else if (pfd == 14) go(interp_qgpv_kernel<0, 14>); else go(interp_qgpv_kernel<0, 6>);
+        } else {
+            if (pfd == 0) go(interp_qgpv_kernel<1, 0>); else if (pfd == 8) go(interp_qgpv_kernel<1, 8>);
+            else if (pfd == 10) go(interp_qgpv_kernel<1, 10>); else if (pfd == 14) go(interp_qgpv_kernel<1, 14>); else go(interp_qgpv_kernel<1, 6>);
+        }
     }
     FALWA_LAUNCH_CHECK();
     { FALWA_KERNEL("polar_rows_kernel", st); polar_rows_kernel<<<dim3(kmax, 2, batch), 256, 0, st>>>(nlon, nlat, kmax, mode == 1, avort, pv, plane * kmax, stt); }
