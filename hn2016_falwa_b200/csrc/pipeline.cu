@@ -545,11 +545,13 @@ flux_column_kernel(FusedFluxArgs p, double* __restrict__ hs /* [b][nhemi][nd][im
         } else if (k < kmax) nxt = fetch(k + 1);
         const double w = p.vw[k - 1];
         const double wd = w * p.dc;
-        s_u = s_u + cur.u0 * wd;
-        s_fphi = s_fphi + (-(((cur.u0 - cur.ur) * cur.v0) * cl)) * wd;
+        // (EXT: the running sums take one fused multiply-add per term, like the LWA sums of lwa_window_kernel)
+        auto accw = [&](double sum, double x) -> double { return EXT ? __fma_rn(x, wd, sum) : sum + x * wd; };
+        s_u = accw(s_u, cur.u0);
+        s_fphi = accw(s_fphi, -(((cur.u0 - cur.ur) * cur.v0) * cl));
         if (k < kmax) {
             const size_t lev = (size_t)(k - 1) * plane;
-            if (own_g) s_g = s_g + ((cur.u0 - cur.ur) * c0 * c0 * (sg * cur.v0)) * wd;
+            if (own_g) s_g = accw(s_g, (cur.u0 - cur.ur) * c0 * c0 * (sg * cur.v0));
             double e1 = 0, x_ua1 = 0;
             if (in_range) {
                 const double vv0 = sg * cur.v0;
@@ -567,7 +569,7 @@ flux_column_kernel(FusedFluxArgs p, double* __restrict__ hs /* [b][nhemi][nd][im
                 s_ua2 = s_ua2 + cur.u2 * wd;
                 s_nc = s_nc + cur.nc * wd;
             }
-            s_ep1 = s_ep1 + e1 * wd;
+            s_ep1 = accw(s_ep1, e1);
             if (first) s_e3 = s_e3 + ((cur.um - cur.urm) * cm * cm * (sg * cur.vm)) * wd;
             if (brow) {  // compute_flux_dirinv.f90:173-178
                 double wk = wd;
