@@ -118,11 +118,14 @@ def bind_to_gpu_numa_node(index):
     return None
 
 
-def workload_config(nlon, nlat):
+def workload_config(nlon, nlat, data="analytic"):
     """The `config` object of the JSON line: identical for the B200 arm and the reference arm."""
+    what = ("seeded synthetic snapshots (hn2016_falwa_b200.synthetic), zonally rotated copies per batch" if data == "analytic"
+            else "the reference's ERA-Interim 2005-01-23 00Z snapshot bilinearly interpolated to the grid, zonally rotated "
+                 "copies per batch")
     return {"workload": f"QGFieldNHN22 {nlon}x{nlat}x{NLEV}plev->kmax{KMAX}, jb=5, both hemispheres",
             "grid": {"nlon": nlon, "nlat": nlat, "nlev": NLEV, "kmax": KMAX}, "protocol": "NHN22", "jb": 5,
-            "data": "seeded synthetic snapshots (hn2016_falwa_b200.synthetic), zonally rotated copies per batch"}
+            "data": what}
 
 
 def cpu_split(nlon, cores):
@@ -135,11 +138,20 @@ def cpu_split(nlon, cores):
     return workers
 
 
-def make_batch(nlon, nlat, batch, seed):
+REAL_SNAPSHOT = os.path.join(ROOT, "tests", "golden", "era_interim_2005-01-23_00Z.npz")
+
+
+def make_batch(nlon, nlat, batch, seed, data="analytic"):
     """One seeded synthetic snapshot (hn2016_falwa_b200.synthetic) + zonally rotated copies of it: B distinct
-    snapshots [B][nlev][nlat][nlon] without B x 8 s of host trigonometry."""
-    from hn2016_falwa_b200.synthetic import synthetic_snapshot
-    xlon, ylat, plev, u, v, t = synthetic_snapshot(nlon=nlon, nlat=nlat, seed=seed)
+    snapshots [B][nlev][nlat][nlon] without B x 8 s of host trigonometry.  data="upsampled": SURVEY.md §8(d)(i), the
+    reference's own 1.5-degree ERA-Interim snapshot (tests/golden) bilinearly interpolated to the grid — large
+    meanders, i.e. LWA windows an order of magnitude longer than the analytic waves'."""
+    from hn2016_falwa_b200.synthetic import load_packed_snapshot, synthetic_snapshot, upsampled_snapshot
+    if data == "upsampled":
+        x0, y0, plev, u0, v0, t0 = load_packed_snapshot(REAL_SNAPSHOT)
+        xlon, ylat, u, v, t = upsampled_snapshot(x0, y0, u0, v0, t0, nlon, nlat)
+    else:
+        xlon, ylat, plev, u, v, t = synthetic_snapshot(nlon=nlon, nlat=nlat, seed=seed)
     shifts = [(b * 37 * nlon) // 360 for b in range(batch)]
     return xlon, ylat, plev, u, v, t, shifts
 
@@ -241,7 +253,7 @@ def run_reference(args, nlon, nlat, rank, world):
         "impl": "reference", "metric": "snapshots/sec, QGFieldNHN22 full pipeline", "value": value,
         "unit": "snapshots/s", "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": args.warmup,
         "ms_per_step": 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(nlon, nlat),
+        "dtype": "f64", "data": "synthetic", "config": workload_config(nlon, nlat, args.data),
         "run": {"snapshots_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "snapshots/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "snapshots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -277,7 +289,7 @@ def run_b200(args, nlon, nlat, rank, world, local_rank):
             os.dup2(saved, 1)
             os.close(saved)
     B = args.batch
-    xlon, ylat, plev, u, v, t, shifts = make_batch(nlon, nlat, B, seed=1234 + rank)
+    xlon, ylat, plev, u, v, t, shifts = make_batch(nlon, nlat, B, seed=1234 + rank, data=args.data)
     # plan via the public class (validates the grid exactly like the reference's constructor)
     f0 = QGFieldNHN22(xlon, ylat, plev, u, v, t)
     plan = f0._plan
@@ -448,7 +460,7 @@ def run_b200(args, nlon, nlat, rank, world, local_rank):
             "metric": "snapshots/sec, QGFieldNHN22 full pipeline", "value": value, "unit": "snapshots/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(nlon, nlat),
+            "config": workload_config(nlon, nlat, args.data),
             "run": {"snapshots_per_step_per_gpu": B, "l2": "inputs of one step exceed L2 (B x 0.92 GB at 0.25 deg)",
                     "lwa_method": args.method},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
@@ -625,6 +637,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=1, help="snapshots per H2D/D2H chunk of the end-to-end run")
     ap.add_argument("--grid", default="0.25", choices=sorted(GRIDS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--data", default="analytic", choices=["analytic", "upsampled"],
+                    help="analytic: seeded synthetic waves (default, SURVEY 8(d)(ii)); upsampled: the real 1.5-degree "
+                         "snapshot interpolated to the grid (SURVEY 8(d)(i))")
     ap.add_argument("--method", type=int, default=0, help="LWA algorithm: 0 automatic (windowed sums), 1 double loop, 2 interval scan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels-only", action="store_true", help="tuning: skip the end-to-end and CPU parts")

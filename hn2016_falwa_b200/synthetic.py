@@ -38,3 +38,39 @@ def synthetic_snapshot(nlon=240, nlat=121, plev=ERA_PLEV, seed=1234, t_index=0):
             v = v + amp * env * vert * wave_s
             t = t + 0.3 * amp * env * np.exp(-zp / 15000.0) * wave
     return xlon, ylat, plev.copy(), u, v, t
+
+
+def upsampled_snapshot(xlon, ylat, u, v, t, nlon=1440, nlat=721):
+    """a real coarse snapshot (e.g. the 1.5° ERA-Interim one) brought to an ERA5-shaped grid by
+    bilinear interpolation, periodic in longitude; the levels stay as they are.  ``ylat`` ascending, pole to pole.
+
+    Returns xlon2, ylat2, u2, v2, t2 with fields of shape (nlev, nlat, nlon), float64."""
+    xlon = np.asarray(xlon, dtype=np.float64)
+    ylat = np.asarray(ylat, dtype=np.float64)
+    xlon2 = np.linspace(0.0, 360.0, nlon, endpoint=False)
+    ylat2 = np.linspace(-90.0, 90.0, nlat, endpoint=True)
+    fx = (xlon2 - xlon[0]) / (xlon[1] - xlon[0])
+    i0 = np.floor(fx).astype(np.int64)
+    wx = fx - i0
+    i1 = (i0 + 1) % xlon.size
+    i0 = i0 % xlon.size
+    fy = np.clip((ylat2 - ylat[0]) / (ylat[1] - ylat[0]), 0.0, ylat.size - 1.0)
+    j0 = np.minimum(np.floor(fy).astype(np.int64), ylat.size - 2)
+    wy = (fy - j0)[None, :, None]
+    out = []
+    for a in (u, v, t):
+        a = np.asarray(a, dtype=np.float64)
+        rows = a[:, j0, :] * (1.0 - wy) + a[:, j0 + 1, :] * wy
+        out.append(np.ascontiguousarray(rows[:, :, i0] * (1.0 - wx) + rows[:, :, i1] * wx))
+    return (xlon2, ylat2, *out)
+
+
+def load_packed_snapshot(npz_path):
+    """Decode a CF-packed snapshot kept as .npz (int16 u, v, t with `<name>_scale` / `<name>_offset`, `longitude`,
+    `latitude` descending, `level` ascending — the layout of the reference's tests/data files) into the orientation the
+    QGField classes expect: latitude ascending, pressure descending.  -> xlon, ylat, plev, u, v, t (float64)."""
+    z = np.load(npz_path)
+    fields = [np.ascontiguousarray((z[n].astype(np.float64) * float(z[n + "_scale"]) + float(z[n + "_offset"]))[::-1, ::-1, :])
+              for n in "uvt"]
+    return (z["longitude"].astype(np.float64), z["latitude"].astype(np.float64)[::-1].copy(),
+            z["level"].astype(np.float64)[::-1].copy(), *fields)
