@@ -171,6 +171,7 @@ def algorithmic_bytes(nlon, nlat, nd, kmax, nlev, has_avort=True):
         "lwa_scan_kernel": 2 * (2 * hemi3 + 3 * hemi3),                        # read pv, u; write a1, a2, ua2
         "flux_column_kernel": 2 * (6 * hemi3 + hemi3 + 12 * hemi2),            # read a1,a2,ua2,u,v,theta; write lwa + 2-D
         "lwa_window_kernel": 2 * (2 * hemi3 + hemi3 + 5 * hemi2),              # read pv, u; write lwa + 5 vertical sums
+        "lwa_prefix_kernel": 2 * (2 * hemi3 + hemi3 + 5 * hemi2),              # same traffic, other algorithm
         "flux_uvt_column_kernel": 2 * (3 * hemi3 + 8 * hemi2),                 # read u, v, theta; write 2-D sums
         "baro_post_kernel": 2 * f3 + 8 * f2,
         "pipeline": 3 * f3in + 4 * f3 + f3 + 12 * f2,                         # 3056.6 MB at 0.25°

@@ -224,8 +224,8 @@ extern "C" int falwa_b200_compute_flux_dirinv_nshem(
     dim3 block(32, 8);
     dim3 grid(ceil_div(imax, 32), ceil_div(nrows, 8), kmax - 2);
     // method: 0 = automatic (windowed sums, else interval scan, else the double loop), 1 = double loop,
-    //         2 = interval scan, 3 = windowed sums
-    const bool use_window = (method == 0 || method == 3) && is_nhem && win_supported(imax, nd, pv, uu, ncforce);
+    //         2 = interval scan, 3 = windowed sums, 4 = prefix sums over threshold intervals
+    const bool use_window = (method == 0 || method == 3 || method == 4) && is_nhem && win_supported(imax, nd, pv, uu, ncforce);
     const bool use_scan = !use_window && (method != 1) && is_nhem && scan_supported(nd);
     ScanTables tabs;
     if (use_window) {  // astar1, astar2, ua2, ncforce3d by exact windowed sums (lwa_window.cu), the pointwise terms afterwards
@@ -240,6 +240,12 @@ extern "C" int falwa_b200_compute_flux_dirinv_nshem(
         w.out_batch = 0; w.out_plane = (size_t)nd * imax; w.out_pitch = imax;
         w.mask_count = p.mask_count;
         if ((rc = lwa_window_launch(w, 0, pv, uu, ncforce, jmax, 1, 1, st))) return rc;
+        if (method == 4) {   // prefix sums (lwa_prefix.cu) for astar1, astar2, ua2 and the pair counts; it does not carry
+                             // ncforce, so ncforce3d stays the window kernel's
+            if (mask_count) FALWA_CUDA_TRY(cudaMemsetAsync(mask_count, 0, 2 * sizeof(int64_t), st));
+            w.ncf = nullptr;
+            if ((rc = lwa_prefix_launch(w, 0, pv, uu, jmax, 1, 1, nullptr, 0, st))) return rc;
+        }
         { FALWA_KERNEL("flux_pointwise_kernel", st); flux_bruteforce_kernel<false><<<grid, block, 0, st>>>(p); }
     } else if (use_scan) {  // astar1, astar2, ua2, ncforce3d by the interval scan, the pointwise terms afterwards
         if ((rc = tabs.alloc(1, nd, kmax, st))) return rc;
@@ -303,7 +309,7 @@ extern "C" int falwa_b200_compute_lwa_only_nhn22(const double* pv, const double*
     dim3 block(32, 8);
     dim3 grid(ceil_div(imax, 32), ceil_div(nrows, 8), kmax - 2);
     ScanTables tabs;
-    if ((method == 0 || method == 3) && is_nhem && win_supported(imax, nd, pv, uu, nullptr)) {
+    if ((method == 0 || method == 3 || method == 4) && is_nhem && win_supported(imax, nd, pv, uu, nullptr)) {
         WinArgs w{};
         w.imax = imax; w.nd = nd; w.kmax = kmax; w.jstart = p.jstart; w.jend = p.jend; w.nhemi = 1;
         w.k_first = 2; w.k_count = kmax - 2;
@@ -314,7 +320,9 @@ extern "C" int falwa_b200_compute_lwa_only_nhn22(const double* pv, const double*
         w.a1 = astar1; w.a2 = astar2; w.u2 = nullptr; w.ncf = nullptr;
         w.out_batch = 0; w.out_plane = (size_t)nd * imax; w.out_pitch = imax;
         w.mask_count = nullptr;
-        if ((rc = lwa_window_launch(w, 0, pv, uu, nullptr, jmax, 1, 1, st))) return rc;
+        if (method == 4) rc = lwa_prefix_launch(w, 0, pv, uu, jmax, 1, 1, nullptr, 0, st);
+        else rc = lwa_window_launch(w, 0, pv, uu, nullptr, jmax, 1, 1, st);
+        if (rc) return rc;
     } else if ((method != 1) && is_nhem && scan_supported(nd)) {
         if ((rc = tabs.alloc(1, nd, kmax, st))) return rc;
         ThrArgs t{};

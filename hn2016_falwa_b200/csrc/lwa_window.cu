@@ -184,8 +184,9 @@ __device__ __forceinline__ void win_pair(double qv, double Qj, double av, double
 template <int MODE, bool HAS_NC, bool COUNT, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 lwa_window_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_u,
-                  const __grid_constant__ CUtensorMap tm_n, const WinArgs p) {
+                  const __grid_constant__ CUtensorMap tm_n, const WinArgs p, const int* __restrict__ sel, int sel_want) {
     extern __shared__ __align__(1024) unsigned char win_raw[];
+    if (sel && sel[blockIdx.z] != sel_want) return;    // the prefix kernel (lwa_prefix.cu) owns this problem
     constexpr int NT = NW * 32;
     constexpr int GPW = kWinMaxRows / (4 * NW);                          // 4-row groups a warp owns
     constexpr int NF = HAS_NC ? 3 : 2;
@@ -546,10 +547,10 @@ static bool win_supported(int imax, int nd, const void* pv, const void* uu, cons
 
 template <int MODE, int NW>
 static int win_launch_mode(const CUtensorMap& tq, const CUtensorMap& tu, const CUtensorMap& tn, const WinArgs& a, bool has_nc,
-                           dim3 grid, size_t smem, cudaStream_t st) {
+                           dim3 grid, size_t smem, cudaStream_t st, const int* sel, int sel_want) {
     auto go = [&](auto kern) -> int {
         FALWA_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, NW * 32, smem, st>>>(tq, tu, tn, a);
+        kern<<<grid, NW * 32, smem, st>>>(tq, tu, tn, a, sel, sel_want);
         return 0;
     };
     const bool count = a.mask_count != nullptr;
@@ -559,7 +560,7 @@ static int win_launch_mode(const CUtensorMap& tq, const CUtensorMap& tu, const C
 
 // pv / uu / nc: [batch][kmax][in_rows][imax]; a.k_first / k_count / frames / thresholds / outputs filled by the caller
 static int lwa_window_launch(WinArgs a, int mode, const double* pv, const double* uu, const double* nc, int in_rows,
-                             int batch, int nprob, cudaStream_t st) {
+                             int batch, int nprob, cudaStream_t st, const int* sel = nullptr, int sel_want = 0) {
     const int nbox = (a.nd + 255) / 256;
     int boxrows = (a.nd + nbox - 1) / nbox;
     boxrows += boxrows & 1;
@@ -577,10 +578,10 @@ static int lwa_window_launch(WinArgs a, int mode, const double* pv, const double
     dim3 grid(tiles, chunks, nprob);
     FALWA_KERNEL("lwa_window_kernel", st);
     static const int nw = tune_int("FALWA_WIN_WARPS", 24);
-    if (mode == 1 && nw == 24) rc = win_launch_mode<1, 24>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
-    else if (mode == 1 && nw == 32) rc = win_launch_mode<1, 32>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
-    else rc = mode == 1 ? win_launch_mode<1, 16>(tq, tu, tn, a, nc != nullptr, grid, smem, st)
-                        : win_launch_mode<0, 16>(tq, tu, tn, a, nc != nullptr, grid, smem, st);
+    if (mode == 1 && nw == 24) rc = win_launch_mode<1, 24>(tq, tu, tn, a, nc != nullptr, grid, smem, st, sel, sel_want);
+    else if (mode == 1 && nw == 32) rc = win_launch_mode<1, 32>(tq, tu, tn, a, nc != nullptr, grid, smem, st, sel, sel_want);
+    else rc = mode == 1 ? win_launch_mode<1, 16>(tq, tu, tn, a, nc != nullptr, grid, smem, st, sel, sel_want)
+                        : win_launch_mode<0, 16>(tq, tu, tn, a, nc != nullptr, grid, smem, st, sel, sel_want);
     if (rc) return rc;
     FALWA_LAUNCH_CHECK();
     return 0;

@@ -1306,7 +1306,7 @@ static int lwa_fluxes_impl(const falwa_plan* P, int batch, const double* qgpv, c
     const int nhemi = north_only ? 1 : 2;
     const size_t f3 = (size_t)kmax * nlat * nlon;
     int rc;
-    DeviceScratch<double> tmp, hsum;
+    DeviceScratch<double> tmp, hsum, lsel;
     DeviceTable prof;
     {   // profiles [batch][4][kmax] followed by the per-level factor of the ep1 heat term, [batch][2][kmax]
         std::vector<double> hp(profiles_host, profiles_host + (size_t)batch * 4 * kmax);
@@ -1340,7 +1340,12 @@ static int lwa_fluxes_impl(const falwa_plan* P, int batch, const double* qgpv, c
     }
     // method: 0 = automatic (windowed sums, else interval scan, else the double loop), 1 = double loop,
     //         2 = interval scan, 3 = windowed sums
-    const bool use_window = (method == 0 || method == 3) && !l3d && win_supported(nlon, nd, qgpv, u, ncforce);
+    const bool use_window = (method == 0 || method == 3 || method == 4) && !l3d && win_supported(nlon, nd, qgpv, u, ncforce);
+    // 0: per (snapshot, hemisphere) the windowed sums or the prefix sums, by the sampled displacement of its PV contours;
+    // 3 / 4: one of them everywhere (FALWA_LWA_KERNEL=window|prefix does the same for method 0)
+    static const int lwa_force = tune_int("FALWA_LWA_FORCE", -1);       // -1 automatic, 0 window, 1 prefix
+    static const int lwa_rows = tune_int("FALWA_LWA_SWITCH_ROWS", 6);   // mean displacement (rows) above which prefix sums win
+    const int pfx_mode = !pfx_supported(nlon, nd, qgpv, u, ncforce) ? 0 : (method == 3 ? 0 : (method == 4 ? 1 : (lwa_force >= 0 ? lwa_force : -1)));
     const bool use_scan = !use_window && (method != 1) && scan_supported(nd);
     ScanTables tabs;
     if (use_window) {
@@ -1366,7 +1371,31 @@ static int lwa_fluxes_impl(const falwa_plan* P, int batch, const double* qgpv, c
         w.slot_a1 = O_ASTAR1; w.slot_a2 = O_ASTAR2; w.slot_lwa = O_LWA; w.slot_ua1 = O_UA1; w.slot_ua2 = O_UA2;
         w.slot_ncf = O_NCF;
         w.mask_count = nullptr;
-        if ((rc = lwa_window_launch(w, 1, qgpv, u, ncforce, nlat, batch, batch * nhemi, st))) return rc;
+        const int nprob = batch * nhemi;
+        if (pfx_mode == 0) {
+            if ((rc = lwa_window_launch(w, 1, qgpv, u, ncforce, nlat, batch, nprob, st))) return rc;
+        } else if (pfx_mode == 1) {
+            if ((rc = lwa_prefix_launch(w, 1, qgpv, u, nlat, batch, nprob, nullptr, 0, st))) return rc;
+        } else {
+            if ((rc = lsel.alloc((size_t)3 * nprob, st))) return rc;
+            unsigned long long* acc = reinterpret_cast<unsigned long long*>(lsel.d);
+            int* sel = reinterpret_cast<int*>(lsel.d + 2 * nprob);
+            FALWA_CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(unsigned long long) * 2 * nprob, st));
+            PfxProbeArgs pa{};
+            pa.imax = nlon; pa.nd = nd; pa.kmax = kmax; pa.jstart = w.jstart; pa.jend = w.jend; pa.nhemi = nhemi; pa.in_rows = nlat;
+            pa.pv = qgpv; pa.in_batch = f3; pa.in_plane = (size_t)nlat * nlon;
+            pa.qref = w.qref; pa.q_batch = w.q_batch; pa.q_kstride = w.q_kstride;
+            for (int h = 0; h < 2; ++h) {
+                pa.in_row0[h] = nd - 1; pa.in_rstep[h] = h ? -1 : 1; pa.sg[h] = h ? -1.0 : 1.0;
+                pa.q_row0[h] = w.q_row0[h]; pa.q_rstep[h] = w.q_rstep[h]; pa.q_sg[h] = w.q_sg[h];
+            }
+            pa.acc = acc;
+            { FALWA_KERNEL("lwa_probe_kernel", st); lwa_probe_kernel<<<dim3(ceil_div(kmax - 2, 8), nprob), 256, 0, st>>>(pa);
+              lwa_select_kernel<<<ceil_div(nprob, 128), 128, 0, st>>>(acc, sel, nprob, (double)lwa_rows, -1); }
+            FALWA_LAUNCH_CHECK();
+            if ((rc = lwa_window_launch(w, 1, qgpv, u, ncforce, nlat, batch, nprob, st, sel, 0))) return rc;
+            if ((rc = lwa_prefix_launch(w, 1, qgpv, u, nlat, batch, nprob, sel, 1, st))) return rc;
+        }
     } else if (use_scan) {
         // LWA pieces a1, a2, ua2 (, ncforce3d) of every level by the interval scan, in the global frame
         const int narr = ncforce ? 4 : 3, nprob = batch * nhemi;

@@ -19,8 +19,9 @@ from . import _lib
 from ._lib import check, dptr, hptr, stream_ptr
 
 # LWA methods of compute_flux_dirinv_nshem / compute_lwa_only_nhn22: 0 = default (exact windowed sums, lwa_window.cu),
-# 1 = the reference's double loop, 2 = interval scan (flux_scan.cu)
-LWA_METHODS = (0, 1, 2)
+# 1 = the reference's double loop, 2 = interval scan (flux_scan.cu), 4 = prefix sums over threshold intervals
+# (lwa_prefix.cu; what the pipeline switches to where the PV contours meander far)
+LWA_METHODS = (0, 1, 2, 4)
 
 
 def _dev(x, ndim):

@@ -109,7 +109,10 @@ int falwa_b200_upward_sweep(int jmax, int kmax, int nd, int jb, int jd, const do
  * method: 0 = automatic: exact windowed sums (lwa_window.cu; fields 16-byte aligned, nd <= 384, even imax), else the
  *             interval scan (nd <= 416), else the double loop;
  *         1 = the O(nd^2) double loop of the reference (same summation order as the reference);
- *         2 = interval scan (flux_scan.cu);  3 = windowed sums (falls back like 0 where unsupported).
+ *         2 = interval scan (flux_scan.cu);  3 = windowed sums (falls back like 0 where unsupported);
+ *         4 = prefix sums over threshold intervals (lwa_prefix.cu: 64-bit fixed-point difference arrays, cost independent
+ *             of how far the PV contours are displaced; it does not carry ncforce — ncforce3d then comes from the
+ *             windowed sums; same support conditions as 3).
  * All methods form exactly the reference's sets (equal pair counts); sums agree within rounding. */
 int falwa_b200_compute_flux_dirinv_nshem(const double* pv, const double* uu, const double* vv,
                                          const double* pt, const double* ncforce, const double* tn0_host,
@@ -185,8 +188,10 @@ int falwa_b200_reference_states(const falwa_plan* plan, int batch, const double*
 /* compute_lwa_and_barotropic_fluxes (oopinterface.py:716-982), both hemispheres.
  *   lwa   [batch][kmax][nlat][nlon]
  *   out2d [batch][FALWA_OUT2D_COUNT][nlat][nlon], slots below.
- * ncforce may be NULL (zeros).  method as for falwa_b200_compute_flux_dirinv_nshem (0 = automatic: the window kernel
- * also carries the vertical sums of astar1, astar2, ua1, ua2 and writes the 3-D LWA in the same pass). */
+ * ncforce may be NULL (zeros).  method as for falwa_b200_compute_flux_dirinv_nshem.  0 = automatic: a sampling kernel
+ * measures, per (snapshot, hemisphere), how many rows the PV contours are displaced on average; weakly displaced ones
+ * go to the windowed sums, strongly meandering ones to the prefix sums (with ncforce: always the windowed sums).  Both
+ * kernels also carry the vertical sums of astar1, astar2, ua1, ua2 and write the 3-D LWA in the same pass. */
 enum {
     FALWA_OUT2D_ASTAR1_BARO = 0, FALWA_OUT2D_ASTAR2_BARO = 1, FALWA_OUT2D_LWA_BARO = 2,
     FALWA_OUT2D_ADV_FLUX_F1 = 3, FALWA_OUT2D_ADV_FLUX_F2 = 4, FALWA_OUT2D_ADV_FLUX_F3 = 5,

@@ -158,7 +158,7 @@ def test_compute_reference_states_nh18(gpu, staged, hemisphere):
     compare(tag + "tref", g[2], w[2], rtol=1e-9)
 
 
-@pytest.mark.parametrize("method", [0, 1, 2], ids=["window", "bruteforce", "scan"])
+@pytest.mark.parametrize("method", [0, 1, 2, 4], ids=["window", "bruteforce", "scan", "prefix"])
 @pytest.mark.parametrize("kind", ["nh18", "nhn22"])
 @pytest.mark.parametrize("hemisphere", ["north", "south"])
 def test_compute_flux_dirinv_nshem(gpu, staged, kind, hemisphere, method):
@@ -190,7 +190,7 @@ def test_compute_flux_dirinv_nshem(gpu, staged, kind, hemisphere, method):
         compare(f"{name}/{kind}/{hemisphere}/flux{method}/{nm}", a_, b_, rtol=rtol, atol=ascale * np.abs(b_).max())
 
 
-@pytest.mark.parametrize("method", [0, 1, 2], ids=["window", "bruteforce", "scan"])
+@pytest.mark.parametrize("method", [0, 1, 2, 4], ids=["window", "bruteforce", "scan", "prefix"])
 def test_compute_lwa_only_nhn22(gpu, staged, method):
     name, inputs, o18, _ = staged
     c = o18["config"]
@@ -221,7 +221,7 @@ def test_drop_in_pipeline_through_f2py_boundary(gpu, staged, kind):
         compare(f"{name}/{kind}/dropin/{f}", got[f], want[f], rtol=rtol, atol=atol)
 
 
-@pytest.mark.parametrize("method", [0, 2], ids=["window", "scan"])
+@pytest.mark.parametrize("method", [0, 2, 4], ids=["window", "scan", "prefix"])
 def test_lwa_with_nan_points_matches_the_double_loop(gpu, method):
     """A NaN PV value makes both of the reference's comparisons false (compute_flux_dirinv.f90:90, :101): the point
     belongs to no set of any row.  The fast LWA methods must treat it the same way as the double loop (method 1), and
@@ -235,7 +235,7 @@ def test_lwa_with_nan_points_matches_the_double_loop(gpu, method):
     for _ in range(40):
         pv[rng.integers(0, 96), rng.integers(24, 49), rng.integers(2, 47)] = np.nan
     if method == 0:   # (the interval scan forms its sums as differences of prefix sums: a NaN in u, once added, cannot
-        for _ in range(10):   # leave again — method 2 is exact for NaN PV only; the default method has no such limit)
+        for _ in range(10):   # leave again — methods 2 and 4 are exact for NaN PV only; the default method has no such limit)
             uu[rng.integers(0, 96), rng.integers(24, 49), rng.integers(2, 47)] = np.nan
     kw = dict(pv=pv, uu=uu, vv=vv, pt=pt, ncforce=np.zeros(pv.shape), tn0=o["tn0"], qref=o["qref"].T[-eq:],
               uref=o["uref"].T[-jd:], tref=o["ptref"].T[-jd:], jb=c["jb"], is_nhem=True, a=A, om=OM, dz=DZ, h=H,

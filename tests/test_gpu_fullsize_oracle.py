@@ -144,16 +144,58 @@ def test_equivalent_latitude_bins_are_exact(case, hemisphere):
         assert mism == 0
 
 
-def test_results_are_bit_reproducible(snap):
-    """the area histograms accumulate 64-bit fixed-point integers, the LWA kernels use no floating-point
-    atomics — two runs of the pipeline on the same inputs give bit-identical reference states and fluxes."""
+def test_prefix_sums_on_every_problem_match_the_oracle(snap, case):
+    """The benchmarked snapshot again with the prefix-sum LWA kernel (lwa_prefix.cu, method 4) on every (snapshot,
+    hemisphere) instead of the automatic choice."""
+    kind, want = case
+    f = _cls(kind)(*snap)
+    f.interpolate_fields(return_named_tuple=False)
+    f.compute_reference_states(return_named_tuple=False)
+    f.compute_lwa_and_barotropic_fluxes(return_named_tuple=False, method=4)
+    for name in ("lwa", "lwa_baro", "u_baro", "adv_flux_f1", "adv_flux_f2", "adv_flux_f3", "convergence_zonal_advective_flux"):
+        rec = compare(f"fullsize/{kind}/prefix/{name}", getattr(f, name), want[name], rtol=1e-8,
+                      atol=1e-9 * float(np.abs(want[name]).max()))
+        _note(what="field_prefix_kernel", kind=kind, grid=[NLON, NLAT], **rec)
+
+
+def test_upsampled_real_snapshot_matches_the_oracle():
+    """the reference's ERA-Interim snapshot interpolated to 1440 x 721.  Its PV contours meander by tens
+    of rows (17 x the LWA pairs of the analytic waves), the regime the automatic method hands to the prefix-sum kernel;
+    the windowed sums (method 3) must agree as well."""
+    from hn2016_falwa_b200.oopinterface import QGFieldNHN22
+    from hn2016_falwa_b200.synthetic import load_packed_snapshot, upsampled_snapshot
+    x0, y0, plev, u0, v0, t0 = load_packed_snapshot(os.path.join(ROOT, "tests", "golden", "era_interim_2005-01-23_00Z.npz"))
+    xlon, ylat, u, v, t = upsampled_snapshot(x0, y0, u0, v0, t0, NLON, NLAT)
+    want = pipeline.run_qgfield("nhn22", xlon, ylat, plev, u, v, t)
+    _note(what="lwa_pairs_upsampled_real", oracle=[[int(x) for x in row] for row in want["mask_count"]])
+    for method in (0, 3):
+        f = QGFieldNHN22(xlon, ylat, plev, u, v, t)
+        f.interpolate_fields(return_named_tuple=False)
+        f.compute_reference_states(return_named_tuple=False)
+        f.compute_lwa_and_barotropic_fluxes(return_named_tuple=False, method=method)
+        failures = []
+        for name in pipeline.USER_FIELDS:
+            rtol, atol = TOL.get(name, (1e-8, 1e-9 * float(np.abs(want[name]).max())))
+            try:
+                rec = compare(f"fullsize/upsampled/method{method}/{name}", getattr(f, name), want[name], rtol=rtol, atol=atol)
+            except AssertionError as e:
+                failures.append(str(e))
+                continue
+            _note(what="field_upsampled_real", method=method, grid=[NLON, NLAT], **rec)
+        assert not failures, "\n".join(failures)
+
+
+@pytest.mark.parametrize("method", [0, 4], ids=["automatic", "prefix"])
+def test_results_are_bit_reproducible(snap, method):
+    """the area histograms and the prefix-sum LWA accumulate 64-bit fixed-point integers, the windowed LWA
+    uses no atomics at all — two runs of the pipeline on the same inputs give bit-identical reference states and fluxes."""
     runs = []
     for _ in range(2):
         f = _cls("nhn22")(*snap)
         f.interpolate_fields(return_named_tuple=False)
         f.compute_reference_states(return_named_tuple=False)
-        f.compute_lwa_and_barotropic_fluxes(return_named_tuple=False)
+        f.compute_lwa_and_barotropic_fluxes(return_named_tuple=False, method=method)
         runs.append({n: np.array(getattr(f, n)) for n in ("qref", "uref", "ptref", "lwa", "lwa_baro", "adv_flux_f2")})
     diff = {n: int((runs[0][n] != runs[1][n]).sum()) for n in runs[0]}
-    _note(what="run_to_run_differences", kind="nhn22", **diff)
+    _note(what="run_to_run_differences", kind="nhn22", method=method, **diff)
     assert not any(diff.values()), diff
