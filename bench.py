@@ -184,14 +184,18 @@ def algorithmic_bytes(nlon, nlat, nd, kmax, nlev, has_avort=True):
 _CPU_INPUT = {}
 
 
-def _cpu_init(nlon, nlat, threads, precision):
+def _cpu_init(nlon, nlat, threads, precision, data="analytic"):
     """Pool initialiser: OpenMP width of this worker, arithmetic type of the native routines, and the worker's synthetic
     snapshot (generated once, reused every step)."""
     os.environ["OMP_NUM_THREADS"] = str(threads)
     from hn2016_falwa_b200.synthetic import synthetic_snapshot
     from oracle import f2py_shim
     f2py_shim.set_precision(np.float32 if precision == "f32" else np.float64)
-    _CPU_INPUT["inp"] = synthetic_snapshot(nlon=nlon, nlat=nlat, seed=1234 + os.getpid() % 97)
+    if data == "upsampled":
+        xlon, ylat, plev, u, v, t, _ = make_batch(nlon, nlat, 1, 0, data=data)
+        _CPU_INPUT["inp"] = (xlon, ylat, plev, u, v, t)
+    else:
+        _CPU_INPUT["inp"] = synthetic_snapshot(nlon=nlon, nlat=nlat, seed=1234 + os.getpid() % 97)
 
 
 def _cpu_one(_):
@@ -204,7 +208,7 @@ def _cpu_one(_):
 class CpuReference:
     """The CPU oracle pipeline on the host cores: `workers` processes x (cores // workers) OpenMP threads."""
 
-    def __init__(self, nlon, nlat, workers, precision="f64", threads=None):
+    def __init__(self, nlon, nlat, workers, precision="f64", threads=None, data="analytic"):
         import multiprocessing as mp
         import subprocess
         subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
@@ -213,7 +217,7 @@ class CpuReference:
         self.threads = threads or max(1, self.cores // self.workers)
         self.precision = precision
         self.pool = mp.get_context("spawn").Pool(self.workers, initializer=_cpu_init,
-                                                 initargs=(nlon, nlat, self.threads, precision))
+                                                 initargs=(nlon, nlat, self.threads, precision, data))
         self.pool.map(_cpu_one, [0] * 0)   # start the workers
 
     def step(self, snapshots):
@@ -227,8 +231,8 @@ class CpuReference:
         self.pool.join()
 
 
-def cpu_reference_rate(nlon, nlat, snapshots, workers, precision="f64", threads=None):
-    ref = CpuReference(nlon, nlat, workers, precision, threads)
+def cpu_reference_rate(nlon, nlat, snapshots, workers, precision="f64", threads=None, data="analytic"):
+    ref = CpuReference(nlon, nlat, workers, precision, threads, data)
     ref.step(ref.workers)            # untimed: worker start-up + input synthesis
     t0 = time.perf_counter()
     rate = ref.step(snapshots)
@@ -242,7 +246,7 @@ def run_reference(args, nlon, nlat, rank, world):
         return
     workers = cpu_split(nlon, os.cpu_count() or 1)
     per_step = workers if nlon > 1000 else 4 * workers
-    ref = CpuReference(nlon, nlat, workers)
+    ref = CpuReference(nlon, nlat, workers, data=args.data)
     for _ in range(max(1, args.warmup and 1)):
         ref.step(ref.workers)        # warm-up: worker start-up, input synthesis, library load (one pass is enough on a CPU)
     rates = [ref.step(per_step) for _ in range(max(1, args.steps))]
@@ -448,13 +452,13 @@ def run_b200(args, nlon, nlat, rank, world, local_rank):
                 os.sched_setaffinity(0, _ORIG_AFFINITY["cpus"])
             workers = cpu_split(nlon, os.cpu_count() or 1)   # the same split as `--impl reference`
             snaps = workers if nlon > 1000 else 4 * workers
-            rate, cores, workers, threads, wall = cpu_reference_rate(nlon, nlat, snaps, workers=workers)
+            rate, cores, workers, threads, wall = cpu_reference_rate(nlon, nlat, snaps, workers=workers, data=args.data)
             cpu = {"value": rate, "unit": "snapshots/s", "cores": cores, "kind": "port",
                    "sample": f"{snaps} synthetic {nlon}x{nlat} snapshot(s), {workers} process(es) x {threads} OpenMP "
                              f"threads, fp64, {wall:.1f} s wall"}
             if args.cpu_extra:   # the arithmetic type the reference ships (fp32) and a single core
-                r32, _, _, _, w32 = cpu_reference_rate(nlon, nlat, snaps, workers=workers, precision="f32")
-                r1, _, _, _, w1 = cpu_reference_rate(nlon, nlat, 1, workers=1, threads=1)
+                r32, _, _, _, w32 = cpu_reference_rate(nlon, nlat, snaps, workers=workers, precision="f32", data=args.data)
+                r1, _, _, _, w1 = cpu_reference_rate(nlon, nlat, 1, workers=1, threads=1, data=args.data)
                 cpu["fp32_as_shipped"] = {"value": r32, "sample": f"same split, fp32 native routines, {w32:.1f} s wall"}
                 cpu["single_core"] = {"value": r1, "sample": f"1 process x 1 thread, fp64, {w1:.1f} s wall"}
         line = {

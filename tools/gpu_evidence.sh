@@ -7,6 +7,7 @@ O=gpurun_out
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > $O/${T}_gpu.txt 2>&1
 python bench.py --cpu-extra > $O/${T}_bench.json 2> $O/${T}_bench.err; echo "bench rc=$?"
+python bench.py --data upsampled --no-cpu-baseline > $O/${T}_bench_upsampled.json 2>> $O/${T}_bench.err; echo "upsampled rc=$?"
 python bench.py --impl reference --steps 2 --warmup 1 > $O/${T}_bench_reference.json 2>> $O/${T}_bench.err; echo "reference rc=$?"
 python bench.py --config 4 --steps 2 --warmup 1 > $O/${T}_config4.json 2>> $O/${T}_bench.err; echo "config4 rc=$?"
 python bench.py --config 4 --impl reference --steps 1 --warmup 1 >> $O/${T}_config4.json 2>> $O/${T}_bench.err

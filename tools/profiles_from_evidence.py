@@ -15,7 +15,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HOT = ("interp_qgpv_kernel", "lwa_window_kernel", "flux_column_kernel", "area_hist3_kernel", "zonal_stats_kernel",
+HOT = ("interp_qgpv_kernel", "lwa_window_kernel", "lwa_prefix_kernel", "flux_column_kernel", "area_hist3_kernel", "zonal_stats_kernel",
        "theta_rowmean_kernel")
 CMD = "python bench.py --kernels-only --steps 1 --warmup 1 --batch 1"
 
@@ -104,7 +104,7 @@ def sass(dst_gz, dst_summary):
 def main(src, dst):
     G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
     commit = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
-    for s in ("bench.json", "bench_reference.json", "config4.json", "config5.json", "fp64_peak.json", "membw.txt",
+    for s in ("bench.json", "bench_upsampled.json", "bench_reference.json", "config4.json", "config5.json", "fp64_peak.json", "membw.txt",
               "ncu_launches.csv"):
         a = os.path.join(G, f"{src}_{s}")
         if os.path.exists(a):
