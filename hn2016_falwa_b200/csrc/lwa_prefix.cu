@@ -507,7 +507,7 @@ lwa_probe_kernel(PfxProbeArgs p) {
     __shared__ double Q[kWinMaxRows];
     __shared__ unsigned long long ssum[2];
     const int prob = blockIdx.y, b = prob / p.nhemi, h = prob % p.nhemi;
-    const int k = 2 + 8 * blockIdx.x;                       // 1-based level
+    const int k = 2 + 8 * (blockIdx.x >> 3);                // 1-based level; eight CTAs share its rows
     if (k > p.kmax - 1) return;
     const int js0 = p.jstart - 1, je0 = p.jend - 1, nact = je0 - js0 + 1;
     if (threadIdx.x < 2) ssum[threadIdx.x] = 0ull;
@@ -516,7 +516,8 @@ lwa_probe_kernel(PfxProbeArgs p) {
     __syncthreads();
     unsigned long long sum = 0, n = 0;
     const int ncol = (p.imax + 31) / 32;
-    for (int t = threadIdx.x; t < ncol * nact; t += blockDim.x) {
+    const int per = (nact + 7) >> 3, r0 = (blockIdx.x & 7) * per, r1 = min(nact, r0 + per);
+    for (int t = r0 * ncol + threadIdx.x; t < r1 * ncol; t += blockDim.x) {
         const int x = js0 + t / ncol, i = (t % ncol) * 32;
         const double q = p.sg[h] * p.pv[(size_t)b * p.in_batch + (size_t)(k - 1) * p.in_plane +
                                         (size_t)(p.in_row0[h] + p.in_rstep[h] * x) * p.imax + i];

@@ -1390,7 +1390,7 @@ static int lwa_fluxes_impl(const falwa_plan* P, int batch, const double* qgpv, c
                 pa.q_row0[h] = w.q_row0[h]; pa.q_rstep[h] = w.q_rstep[h]; pa.q_sg[h] = w.q_sg[h];
             }
             pa.acc = acc;
-            { FALWA_KERNEL("lwa_probe_kernel", st); lwa_probe_kernel<<<dim3(ceil_div(kmax - 2, 8), nprob), 256, 0, st>>>(pa);
+            { FALWA_KERNEL("lwa_probe_kernel", st); lwa_probe_kernel<<<dim3(8 * ceil_div(kmax - 2, 8), nprob), 256, 0, st>>>(pa);
               lwa_select_kernel<<<ceil_div(nprob, 128), 128, 0, st>>>(acc, sel, nprob, (double)lwa_rows, -1); }
             FALWA_LAUNCH_CHECK();
             if ((rc = lwa_window_launch(w, 1, qgpv, u, ncforce, nlat, batch, nprob, st, sel, 0))) return rc;
