@@ -65,26 +65,7 @@ __device__ __forceinline__ void pfx_add(uint32_t a, long long v) {
 __device__ __forceinline__ unsigned pfx_expo(double x) { return ((unsigned)__double2hiint(x) >> 20) & 0x7ffu; }
 __device__ __forceinline__ double pfx_pow2(int field) { return __hiloint2double(min(max(field, 1), 2045) << 20, 0); }
 
-// high word added unconditionally (no branch; adding zero is harmless)
-__device__ __forceinline__ void pfx_add_nb(uint32_t a, long long v) {
-    const unsigned lo = (unsigned)v, hi = (unsigned)((unsigned long long)v >> 32);
-    unsigned old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(lo) : "memory");
-    const unsigned add = hi + (((old + lo) < old) ? 1u : 0u);
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a + 4), "r"(add) : "memory");
-}
-// one bisection step on the padded running-maximum table: E (as a byte offset) moves up when table[E + STEP - 1] < q
-template <int STEP>
-__device__ __forceinline__ void pfx_bisect(uint32_t a_qt, int& eb, double q) {
-    const double t = lds64o<(STEP - 1) * 8>(a_qt + (uint32_t)eb);
-    if (t < q) eb += STEP * 8;
-}
-
-// LEAN (FALWA_PFX_LEAN=1, hemispheres of at most 375 rows): the same arithmetic with less integer overhead — scans without
-// per-entry bounds predicates (lanes past the column work on its unused tail), bisection on explicit shared addresses
-// with immediate offsets, branch-free carry adds.
-constexpr int kPfxLeanRows = 375;
-template <int MODE, bool COUNT, bool LEAN>
+template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(kPfxWarps * 32, 1)
 lwa_prefix_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_u, const WinArgs p,
                   const int* __restrict__ sel, int sel_want) {
@@ -297,23 +278,14 @@ lwa_prefix_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         int E[GPW];
         long long v1[GPW], v2[GPW], v3[GPW], v4[GPW];
         {
+            const double* qt = Qt + s * kPfxQt;
 #pragma unroll
             for (int gi = 0; gi < GPW; ++gi) E[gi] = 0;
-            if (LEAN) {
-                const uint32_t a_qt = win_smem(Qt) + (uint32_t)(s * kPfxQt * 8);
-#define PFX_STEP(S) _Pragma("unroll") for (int gi = 0; gi < GPW; ++gi) pfx_bisect<S>(a_qt, E[gi], q[gi]);
-                PFX_STEP(256) PFX_STEP(128) PFX_STEP(64) PFX_STEP(32) PFX_STEP(16) PFX_STEP(8) PFX_STEP(4) PFX_STEP(2) PFX_STEP(1)
-#undef PFX_STEP
 #pragma unroll
-                for (int gi = 0; gi < GPW; ++gi) E[gi] >>= 3;
-            } else {
-                const double* qt = Qt + s * kPfxQt;
+            for (int step = 256; step >= 1; step >>= 1) {
 #pragma unroll
-                for (int step = 256; step >= 1; step >>= 1) {
-#pragma unroll
-                    for (int gi = 0; gi < GPW; ++gi)
-                        if (qt[E[gi] + step - 1] < q[gi]) E[gi] += step;
-                }
+                for (int gi = 0; gi < GPW; ++gi)
+                    if (qt[E[gi] + step - 1] < q[gi]) E[gi] += step;
             }
             const double s1 = pfx_pow2(f1), s2 = pfx_pow2(f2), s3 = pfx_pow2(f3), s4 = pfx_pow2(f4);
             if (tid < kPfxArrays * kWinCols) sts_s64(a_d + (uint32_t)(tid * PD * 8), 0ll);                 // position 0
@@ -361,19 +333,10 @@ lwa_prefix_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             const int x = j00 + 4 * NW * gi;
             if (E[gi] >= 0 && E[gi] != x + 1) {
                 const uint32_t a = a_dc + (uint32_t)(E[gi] * 8);
-                if (LEAN) {
-                    const bool cyc = E[gi] > x + 1;
-                    const uint32_t a12 = a + (cyc ? 0u : 2 * ARR);
-                    pfx_add_nb(a12, cyc ? -v1[gi] : v1[gi]);
-                    pfx_add_nb(a12 + ARR, cyc ? -v2[gi] : v2[gi]);
-                    pfx_add_nb(a + 4 * ARR, -v3[gi]);
-                    pfx_add_nb(a + 5 * ARR, -v4[gi]);
-                } else {
-                    if (E[gi] > x + 1) { pfx_add(a, -v1[gi]); pfx_add(a + ARR, -v2[gi]); }
-                    else { pfx_add(a + 2 * ARR, v1[gi]); pfx_add(a + 3 * ARR, v2[gi]); }
-                    pfx_add(a + 4 * ARR, -v3[gi]);
-                    pfx_add(a + 5 * ARR, -v4[gi]);
-                }
+                if (E[gi] > x + 1) { pfx_add(a, -v1[gi]); pfx_add(a + ARR, -v2[gi]); }
+                else { pfx_add(a + 2 * ARR, v1[gi]); pfx_add(a + 3 * ARR, v2[gi]); }
+                pfx_add(a + 4 * ARR, -v3[gi]);
+                pfx_add(a + 5 * ARR, -v4[gi]);
             }
         }
         if (w == 0 && more) envelope(s ^ 1);
@@ -382,15 +345,13 @@ lwa_prefix_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         // ---- C: running sums over the threshold positions 0 .. nd-1, one warp per (array, column) ------------------
 #pragma unroll 1
         for (int pi = w; pi < kPfxArrays * kWinCols; pi += NW) {
-            // LEAN: nd <= 375, so positions 375 .. 387 of a column are never read back: lanes 29 .. 31 (whose own entries
-            // would lie past the column) run on them, and no entry needs a bounds predicate
-            const uint32_t base = a_d + (uint32_t)(pi * PD * 8) + (uint32_t)((LEAN ? min(lane * kPfxSpan, kPfxLeanRows) : lane * kPfxSpan) * 8);
+            const uint32_t base = a_d + (uint32_t)(pi * PD * 8) + (uint32_t)(lane * kPfxSpan * 8);
             long long v[kPfxSpan];
             long long run = 0;
 #pragma unroll
             for (int t = 0; t < kPfxSpan; ++t) {
                 const int m = lane * kPfxSpan + t;
-                if (LEAN || m < nd) run += lds_s64(base + t * 8);
+                if (m < nd) run += lds_s64(base + t * 8);
                 v[t] = run;
             }
             long long ex = run;
@@ -403,7 +364,7 @@ lwa_prefix_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 #pragma unroll
             for (int t = 0; t < kPfxSpan; ++t) {
                 const int m = lane * kPfxSpan + t;
-                if (LEAN || m < nd) sts_s64(base + t * 8, v[t] + off);
+                if (m < nd) sts_s64(base + t * 8, v[t] + off);
             }
         }
         __syncthreads();                                                                                   // (4)
@@ -608,14 +569,8 @@ static int lwa_prefix_launch(WinArgs a, int mode, const double* pv, const double
     };
     FALWA_KERNEL("lwa_prefix_kernel", st);
     const bool count = a.mask_count != nullptr;
-    static const int lean = tune_int("FALWA_PFX_LEAN", 0);
-    if (lean && a.nd <= kPfxLeanRows) {
-        if (mode == 1) rc = count ? go(lwa_prefix_kernel<1, true, true>) : go(lwa_prefix_kernel<1, false, true>);
-        else rc = count ? go(lwa_prefix_kernel<0, true, true>) : go(lwa_prefix_kernel<0, false, true>);
-    } else {
-        if (mode == 1) rc = count ? go(lwa_prefix_kernel<1, true, false>) : go(lwa_prefix_kernel<1, false, false>);
-        else rc = count ? go(lwa_prefix_kernel<0, true, false>) : go(lwa_prefix_kernel<0, false, false>);
-    }
+    if (mode == 1) rc = count ? go(lwa_prefix_kernel<1, true>) : go(lwa_prefix_kernel<1, false>);
+    else rc = count ? go(lwa_prefix_kernel<0, true>) : go(lwa_prefix_kernel<0, false>);
     if (rc) return rc;
     FALWA_LAUNCH_CHECK();
     return 0;
