@@ -1342,7 +1342,7 @@ static int lwa_fluxes_impl(const falwa_plan* P, int batch, const double* qgpv, c
     //         2 = interval scan, 3 = windowed sums
     const bool use_window = (method == 0 || method == 3 || method == 4) && !l3d && win_supported(nlon, nd, qgpv, u, ncforce);
     // 0: per (snapshot, hemisphere) the windowed sums or the prefix sums, by the sampled displacement of its PV contours;
-    // 3 / 4: one of them everywhere (FALWA_LWA_KERNEL=window|prefix does the same for method 0)
+    // 3 / 4: one of them everywhere (FALWA_LWA_FORCE=0|1 does the same for method 0)
     static const int lwa_force = tune_int("FALWA_LWA_FORCE", -1);       // -1 automatic, 0 window, 1 prefix
     static const int lwa_rows = tune_int("FALWA_LWA_SWITCH_ROWS", 10);  // mean displacement (rows) above which prefix sums win
     const int pfx_mode = !pfx_supported(nlon, nd, qgpv, u, ncforce) ? 0 : (method == 3 ? 0 : (method == 4 ? 1 : (lwa_force >= 0 ? lwa_force : -1)));
